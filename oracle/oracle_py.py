@@ -1,0 +1,240 @@
+"""ctypes loader for the CPU oracle (oracle/oracle.c).
+
+TEST INFRASTRUCTURE ONLY: imported by tests/, __graft_entry__.smoke() and
+bench.py's cpu_baseline / --impl reference legs.  The product package
+cupoch_b200/ must never import this module.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_SO = os.path.join(_HERE, "_build", "liboracle.so")
+
+P2P, P2PLANE, SYMMETRIC, COLORED, GICP = 1, 2, 3, 4, 5
+
+
+def build(force=False):
+    if force or not os.path.exists(_SO) or os.path.getmtime(_SO) < os.path.getmtime(os.path.join(_HERE, "oracle.c")):
+        subprocess.check_call(["make", "-C", _HERE, "-s"])
+    return _SO
+
+
+class IcpResult(C.Structure):
+    _fields_ = [("transformation", C.c_float * 16), ("fitness", C.c_float), ("inlier_rmse", C.c_float),
+                ("n_corr", C.c_int), ("iterations", C.c_int)]
+
+
+class IcpParams(C.Structure):
+    _fields_ = [("kind", C.c_int), ("max_distance", C.c_float), ("relative_fitness", C.c_float),
+                ("relative_rmse", C.c_float), ("max_iteration", C.c_int), ("det_thresh", C.c_float),
+                ("lambda_geometric", C.c_float), ("use_kdtree", C.c_int)]
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(_SO):
+            build()
+        _lib = C.CDLL(_SO)
+        _lib.orc_search_bruteforce.restype = C.c_long
+        _lib.orc_kdtree_build.restype = C.c_void_p
+        _lib.orc_kdtree_search.restype = C.c_long
+        _lib.orc_kdtree_search.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_float, C.c_void_p, C.c_void_p]
+        _lib.orc_kdtree_free.argtypes = [C.c_void_p]
+    return _lib
+
+
+def _f(a):
+    return None if a is None else np.ascontiguousarray(a, dtype=np.float32)
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def search(tgt, qry, k, radius=-1.0, kdtree=False):
+    """-> (idx[n,k] int32, d2[n,k] float32, count)"""
+    tgt, qry = _f(tgt).reshape(-1, 3), _f(qry).reshape(-1, 3)
+    n = len(qry)
+    idx = np.empty((n, k), np.int32)
+    d2 = np.empty((n, k), np.float32)
+    L = lib()
+    if kdtree:
+        t = L.orc_kdtree_build(_p(tgt), C.c_int(len(tgt)))
+        cnt = L.orc_kdtree_search(t, _p(qry), n, k, C.c_float(radius), _p(idx), _p(d2))
+        L.orc_kdtree_free(t)
+    else:
+        cnt = L.orc_search_bruteforce(_p(tgt), C.c_int(len(tgt)), _p(qry), C.c_int(n), C.c_int(k),
+                                      C.c_float(radius), _p(idx), _p(d2))
+    return idx, d2, int(cnt)
+
+
+class KDTree:
+    def __init__(self, tgt):
+        self.tgt = _f(tgt).reshape(-1, 3)
+        self.h = lib().orc_kdtree_build(_p(self.tgt), C.c_int(len(self.tgt)))
+
+    def search(self, qry, k, radius=-1.0):
+        qry = _f(qry).reshape(-1, 3)
+        n = len(qry)
+        idx = np.empty((n, k), np.int32)
+        d2 = np.empty((n, k), np.float32)
+        cnt = lib().orc_kdtree_search(self.h, _p(qry), n, k, C.c_float(radius), _p(idx), _p(d2))
+        return idx, d2, int(cnt)
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            lib().orc_kdtree_free(self.h)
+            self.h = None
+
+
+def transform_points(p, T):
+    p = _f(p).reshape(-1, 3).copy()
+    T = _f(T).reshape(16)
+    lib().orc_transform_points(_p(p), C.c_int(len(p)), _p(T))
+    return p
+
+
+def transform_normals(p, T):
+    p = _f(p).reshape(-1, 3).copy()
+    T = _f(T).reshape(16)
+    lib().orc_transform_normals(_p(p), C.c_int(len(p)), _p(T))
+    return p
+
+
+def rotate_covariances(c, T):
+    c = _f(c).reshape(-1, 9).copy()
+    T = _f(T).reshape(16)
+    lib().orc_rotate_covariances(_p(c), C.c_int(len(c)), _p(T))
+    return c.reshape(-1, 3, 3)
+
+
+def min_bound(p):
+    p = _f(p).reshape(-1, 3)
+    o = np.zeros(3, np.float32)
+    lib().orc_min_bound(_p(p), C.c_int(len(p)), _p(o))
+    return o
+
+
+def max_bound(p):
+    p = _f(p).reshape(-1, 3)
+    o = np.zeros(3, np.float32)
+    lib().orc_max_bound(_p(p), C.c_int(len(p)), _p(o))
+    return o
+
+
+def voxel_down_sample(pts, voxel, normals=None, colors=None):
+    pts, normals, colors = _f(pts).reshape(-1, 3), _f(normals), _f(colors)
+    n = len(pts)
+    op = np.empty((n, 3), np.float32)
+    on = np.empty((n, 3), np.float32) if normals is not None else None
+    oc = np.empty((n, 3), np.float32) if colors is not None else None
+    m = lib().orc_voxel_down_sample(_p(pts), _p(normals), _p(colors), C.c_int(n), C.c_float(voxel), _p(op), _p(on), _p(oc))
+    return op[:m].copy(), (on[:m].copy() if on is not None else None), (oc[:m].copy() if oc is not None else None)
+
+
+def estimate_normals(pts, knn=30, radius=0.0, max_nn=0):
+    pts = _f(pts).reshape(-1, 3)
+    out = np.empty_like(pts)
+    lib().orc_estimate_normals(_p(pts), C.c_int(len(pts)), C.c_int(knn), C.c_float(radius), C.c_int(max_nn), _p(out))
+    return out
+
+
+def normals_from_neighbors(pts, nbr):
+    pts = _f(pts).reshape(-1, 3)
+    nbr = np.ascontiguousarray(nbr, np.int32)
+    out = np.empty_like(pts)
+    lib().orc_normals_from_neighbors(_p(pts), C.c_int(len(pts)), _p(nbr), C.c_int(nbr.shape[1]), _p(out))
+    return out
+
+
+def covariances_from_normals(nrm, eps=1e-3):
+    nrm = _f(nrm).reshape(-1, 3)
+    out = np.empty((len(nrm), 9), np.float32)
+    lib().orc_covariances_from_normals(_p(nrm), C.c_int(len(nrm)), C.c_float(eps), _p(out))
+    return out.reshape(-1, 3, 3)
+
+
+def color_gradient(pts, nrm, col, nbr):
+    pts, nrm, col = _f(pts).reshape(-1, 3), _f(nrm).reshape(-1, 3), _f(col).reshape(-1, 3)
+    nbr = np.ascontiguousarray(nbr, np.int32)
+    out = np.empty_like(pts)
+    lib().orc_color_gradient(_p(pts), _p(nrm), _p(col), C.c_int(len(pts)), _p(nbr), C.c_int(nbr.shape[1]), _p(out))
+    return out
+
+
+def jtj_jtr(kind, src, tgt, corr, src_nrm=None, src_col=None, src_cov=None, tgt_nrm=None, tgt_col=None,
+            tgt_grad=None, tgt_cov=None, lambda_geometric=0.968):
+    a = [_f(x) for x in (src, src_nrm, src_col, src_cov, tgt, tgt_nrm, tgt_col, tgt_grad, tgt_cov)]
+    corr = np.ascontiguousarray(corr, np.int32).reshape(-1, 2)
+    sums = np.zeros(32, np.float64)
+    lib().orc_jtj_jtr(C.c_int(kind), *[_p(x) for x in a], _p(corr), C.c_int(len(corr)),
+                      C.c_float(lambda_geometric), _p(sums))
+    return sums
+
+
+def solve_jtj(jtj21, jtr, det_thresh=1e-6):
+    u, b = _f(jtj21).reshape(21), _f(jtr).reshape(6)
+    T = np.zeros(16, np.float32)
+    ok = lib().orc_solve_jtj(_p(u), _p(b), C.c_float(det_thresh), _p(T))
+    return bool(ok), T.reshape(4, 4)
+
+
+def kabsch(src, tgt, corr, n_model=None):
+    src, tgt = _f(src).reshape(-1, 3), _f(tgt).reshape(-1, 3)
+    corr = np.ascontiguousarray(corr, np.int32).reshape(-1, 2)
+    S = np.zeros(17, np.float64)
+    lib().orc_kabsch_sums(_p(src), _p(tgt), _p(corr), C.c_int(len(corr)), _p(S))
+    T = np.zeros(16, np.float32)
+    lib().orc_kabsch_from_sums(_p(S), C.c_int(len(src) if n_model is None else n_model), _p(T))
+    return T.reshape(4, 4), S
+
+
+def correspondences(src, tgt, max_distance, kdtree=True):
+    src, tgt = _f(src).reshape(-1, 3), _f(tgt).reshape(-1, 3)
+    n = len(src)
+    corr = np.empty((n, 2), np.int32)
+    nc, fit, rmse = C.c_int(0), C.c_float(0), C.c_float(0)
+    kd = lib().orc_kdtree_build(_p(tgt), C.c_int(len(tgt))) if kdtree else None
+    lib().orc_correspondences(_p(src), C.c_int(n), _p(tgt), C.c_int(len(tgt)), C.c_void_p(kd), C.c_float(max_distance),
+                              _p(corr), C.byref(nc), C.byref(fit), C.byref(rmse))
+    if kd:
+        lib().orc_kdtree_free(kd)
+    return corr[:nc.value].copy(), fit.value, rmse.value
+
+
+def registration_icp(kind, src, tgt, max_distance, init=None, src_nrm=None, src_col=None, src_cov=None,
+                     tgt_nrm=None, tgt_col=None, tgt_grad=None, tgt_cov=None, relative_fitness=1e-6,
+                     relative_rmse=1e-6, max_iteration=30, det_thresh=1e-6, lambda_geometric=0.968,
+                     use_kdtree=True, trace=False):
+    src, tgt = _f(src).reshape(-1, 3), _f(tgt).reshape(-1, 3)
+    n, m = len(src), len(tgt)
+    init = np.eye(4, dtype=np.float32) if init is None else _f(init).reshape(4, 4)
+    prm = IcpParams(kind, max_distance, relative_fitness, relative_rmse, max_iteration, det_thresh,
+                    lambda_geometric, 1 if use_kdtree else 0)
+    res = IcpResult()
+    corr = np.empty((max(n, 1), 2), np.int32)
+    tr = np.zeros((max_iteration + 1, 16), np.float32) if trace else None
+    a = [_f(x) for x in (src_nrm, src_col, src_cov)]
+    b = [_f(x) for x in (tgt_nrm, tgt_col, tgt_grad, tgt_cov)]
+    lib().orc_registration_icp(_p(src), _p(a[0]), _p(a[1]), _p(a[2]), C.c_int(n), _p(tgt), _p(b[0]), _p(b[1]),
+                               _p(b[2]), _p(b[3]), C.c_int(m), _p(init.reshape(16)), C.byref(prm), C.byref(res),
+                               _p(corr), _p(tr))
+    out = {
+        "transformation": np.array(res.transformation, np.float32).reshape(4, 4),
+        "fitness": res.fitness, "inlier_rmse": res.inlier_rmse,
+        "correspondence_set": corr[:res.n_corr].copy(), "iterations": res.iterations,
+    }
+    if trace:
+        out["trace"] = tr[:res.iterations + 1].reshape(-1, 4, 4)
+    return out
+
+
+def num_threads():
+    return int(lib().orc_num_threads())
