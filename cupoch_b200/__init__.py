@@ -1,0 +1,21 @@
+"""cupoch_b200 -- B200-native drop-in for cupoch's ICP / kNN / voxel-grid hot path.
+
+    import cupoch_b200 as cph
+    res = cph.registration.registration_icp(source, target, 0.02, init,
+            cph.registration.TransformationEstimationPointToPlane())
+
+Mirrors `import cupoch as cph` for: cph.geometry.{PointCloud, KDTreeFlann, KDTreeSearchParamKNN,
+KDTreeSearchParamRadius}, cph.registration.{registration_icp, registration_generalized_icp,
+registration_colored_icp, ICPConvergenceCriteria, TransformationEstimation*, RegistrationResult},
+cph.utility.Vector3fVector.  All computation runs in libcupoch_b200.so (hand-written sm_100a CUDA);
+there is no CPU fallback.
+"""
+from . import _lib, geometry, registration, utility  # noqa: F401
+
+__version__ = "0.1.0"
+
+
+def initialize_allocator(mode=None, initial_pool_size=0, devices=None):
+    """cupoch.initialize_allocator (cupoch_pybind.cpp:47-50).  The B200 engine uses the CUDA
+    stream-ordered pool with an unlimited release threshold; nothing to configure."""
+    return None

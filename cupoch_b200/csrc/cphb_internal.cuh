@@ -1,0 +1,320 @@
+// cphb_internal.cuh -- shared host/device definitions of the B200 engine.
+// sm_100a only.  Not part of the public interface (see include/cupoch_b200.h).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "cupoch_b200.h"
+
+// ---------------------------------------------------------------------------
+// Spatial index layout (DESIGN.md "Data layout in HBM")
+//   pts   : float4[n_leaves*LEAF]  points in 3-D Hilbert order, w = original
+//           index bits; tail padded with (FLT_MAX,FLT_MAX,FLT_MAX, -1)
+//   boxes : per level, Box[ceil32(count)]; level 0 = leaves (LEAF consecutive
+//           points), level l node j = union of level l-1 nodes [32j, 32j+32).
+//           Padding boxes are empty (lo=+inf, hi=-inf) so their distance is
+//           +inf and no traversal ever enters them.
+// A warp owns 32 queries; it tests the 32 children of a node with one lane per
+// child and walks children nearest-first, so the only divergence is the loop
+// trip count.  Leaves are fetched by one TMA bulk copy (cp.async.bulk) into a
+// per-warp shared-memory tile and scanned with broadcast LDS.128.
+// ---------------------------------------------------------------------------
+#define CPHB_LEAF 32
+#define CPHB_LEVELS 6 /* box levels always built: 32^5 * LEAF points max */
+#define CPHB_FULL 0xffffffffu
+
+struct Box {
+    float4 lo;
+    float4 hi;
+};
+
+struct IndexView {
+    const float4 *pts;
+    const Box *boxes[CPHB_LEVELS];
+    unsigned long long n;
+    unsigned n_leaves;
+    int top; /* smallest level with <= 32 nodes */
+};
+
+struct cphb_index {
+    IndexView v;
+    void *arena;
+    size_t arena_bytes;
+    float *bounds; /* device: 6 ordered-uint encoded floats (min xyz, max xyz) */
+    int device;
+    cudaStream_t stream; /* stream the arena was allocated on */
+};
+
+// ---------------------------------------------------------------------------
+// host helpers
+// ---------------------------------------------------------------------------
+void cphb_set_error(const char *fmt, ...);
+extern unsigned long long g_cphb_launches;
+
+#define CPHB_CUDA(call)                                                                   \
+    do {                                                                                  \
+        cudaError_t e__ = (call);                                                         \
+        if (e__ != cudaSuccess) {                                                         \
+            cphb_set_error("%s:%d %s: %s", __FILE__, __LINE__, #call, cudaGetErrorString(e__)); \
+            return CPHB_ERR_CUDA;                                                         \
+        }                                                                                 \
+    } while (0)
+
+#define CPHB_LAUNCH(kernel, grid, block, smem, stream, ...)                 \
+    do {                                                                    \
+        kernel<<<(grid), (block), (smem), (cudaStream_t)(stream)>>>(__VA_ARGS__); \
+        ++g_cphb_launches;                                                  \
+    } while (0)
+
+#define CPHB_CHECK_LAUNCH()                                                               \
+    do {                                                                                  \
+        cudaError_t e__ = cudaGetLastError();                                             \
+        if (e__ != cudaSuccess) {                                                         \
+            cphb_set_error("%s:%d kernel launch: %s", __FILE__, __LINE__, cudaGetErrorString(e__)); \
+            return CPHB_ERR_CUDA;                                                         \
+        }                                                                                 \
+    } while (0)
+
+static inline size_t cphb_align(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+// stream-ordered allocation (pool retained across calls; no cudaMalloc in loops)
+int cphb_alloc_async(void **p, size_t bytes, cudaStream_t s);
+void cphb_free_async(void *p, cudaStream_t s);
+
+// radix sort of (key,value) u32 pairs by the low `bits` bits (CUB; index build
+// and source ordering only -- never inside the per-iteration loop). sort.cu
+int cphb_sort_pairs_u32(const uint32_t *keys_in, uint32_t *keys_out, const uint32_t *vals_in,
+                        uint32_t *vals_out, size_t n, int bits, cudaStream_t s);
+int cphb_sort_pairs_u64(const uint64_t *keys_in, uint64_t *keys_out, const uint32_t *vals_in,
+                        uint32_t *vals_out, size_t n, int bits, cudaStream_t s);
+
+// index.cu internals reused by icp.cu (Hilbert-ordering of the source)
+// perm_out[pos] = original index of the pos-th point along the Hilbert curve.
+// bounds_dev6: device buffer of 6 ordered-uint floats; computed here unless
+// bounds_given (then the existing bounds, e.g. the target index's, are used so
+// queries and targets share one curve).
+int cphb_hilbert_order(const float *xyz, size_t n, uint32_t *perm_out /*device n*/,
+                       float *bounds_dev6 /*or NULL*/, int bounds_given, cudaStream_t s);
+
+#ifdef __CUDACC__
+// ---------------------------------------------------------------------------
+// device helpers
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ int lane_id() { return threadIdx.x & 31; }
+
+// order-preserving float <-> uint (for atomicMin/Max and REDUX on signed floats)
+__host__ __device__ __forceinline__ unsigned f2ord(float f) {
+#ifdef __CUDA_ARCH__
+    unsigned u = __float_as_uint(f);
+#else
+    union { float f; unsigned u; } c; c.f = f; unsigned u = c.u;
+#endif
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__host__ __device__ __forceinline__ float ord2f(unsigned o) {
+    unsigned u = (o & 0x80000000u) ? (o & 0x7fffffffu) : ~o;
+#ifdef __CUDA_ARCH__
+    return __uint_as_float(u);
+#else
+    union { float f; unsigned u; } c; c.u = u; return c.f;
+#endif
+}
+
+// squared distance, fixed operation order (DESIGN.md "arithmetic contract"):
+// d = q - p per axis; d2 = fma(dz,dz, fma(dy,dy, dx*dx))
+__device__ __forceinline__ float dist2(float qx, float qy, float qz, float px, float py, float pz) {
+    float dx = qx - px, dy = qy - py, dz = qz - pz;
+    return __fmaf_rn(dz, dz, __fmaf_rn(dy, dy, __fmul_rn(dx, dx)));
+}
+__device__ __forceinline__ float dot3(float a0, float a1, float a2, float b0, float b1, float b2) {
+    return __fmaf_rn(a2, b2, __fmaf_rn(a1, b1, __fmul_rn(a0, b0)));
+}
+__device__ __forceinline__ float det2(float a, float b, float c, float d) {
+    return __fmaf_rn(a, b, -__fmul_rn(c, d));
+}
+
+// lower bound of dist2 between any point of box [lo,hi] and any point of the
+// query box [qlo,qhi]; same op order as dist2 so it never exceeds a real d2.
+__device__ __forceinline__ float box_dist2(const float4 &lo, const float4 &hi, const float (&qlo)[3],
+                                           const float (&qhi)[3]) {
+    float dx = fmaxf(0.f, fmaxf(lo.x - qhi[0], qlo[0] - hi.x));
+    float dy = fmaxf(0.f, fmaxf(lo.y - qhi[1], qlo[1] - hi.y));
+    float dz = fmaxf(0.f, fmaxf(lo.z - qhi[2], qlo[2] - hi.z));
+    return __fmaf_rn(dz, dz, __fmaf_rn(dy, dy, __fmul_rn(dx, dx)));
+}
+
+// ---- 3-D Hilbert index, 10 bits per axis (Skilling's transpose form) --------
+__device__ __forceinline__ uint32_t hilbert30(uint32_t x, uint32_t y, uint32_t z) {
+    uint32_t X[3] = {x, y, z};
+    const uint32_t M = 1u << 9;
+#pragma unroll
+    for (uint32_t Q = M; Q > 1; Q >>= 1) {
+        uint32_t P = Q - 1;
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+            if (X[i] & Q) {
+                X[0] ^= P;
+            } else {
+                uint32_t t = (X[0] ^ X[i]) & P;
+                X[0] ^= t;
+                X[i] ^= t;
+            }
+        }
+    }
+    X[1] ^= X[0];
+    X[2] ^= X[1];
+    uint32_t t = 0;
+#pragma unroll
+    for (uint32_t Q = M; Q > 1; Q >>= 1)
+        if (X[2] & Q) t ^= Q - 1;
+    X[0] ^= t; X[1] ^= t; X[2] ^= t;
+    uint32_t key = 0;
+#pragma unroll
+    for (int b = 9; b >= 0; --b) {
+        key = (key << 3) | (((X[0] >> b) & 1u) << 2) | (((X[1] >> b) & 1u) << 1) | ((X[2] >> b) & 1u);
+    }
+    return key;
+}
+
+// ---- TMA bulk copy + mbarrier (raw PTX; SASS: UBLKCP / SYNCS) ----------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) {
+    return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint64_t *bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fence_mbar_init() {
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void fence_proxy_async_smem() {
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void tma_bulk_g2s(void *dst_smem, const void *src_gmem, unsigned bytes,
+                                             uint64_t *bar) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+            smem_u32(dst_smem)),
+        "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+        : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, unsigned parity) {
+    unsigned ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+
+// ---------------------------------------------------------------------------
+// Warp-cooperative exact nearest-neighbour traversal (k = 1).
+// best = (d2 bits << 32) | original index: one u64 min implements
+// "smaller d2, ties -> smaller index" (the oracle's rule).
+// ---------------------------------------------------------------------------
+struct WarpSearch {
+    float qx, qy, qz;           // this lane's query
+    float wlo[3], whi[3];       // warp-uniform AABB of the valid queries
+    unsigned long long best;    // this lane's best key
+    unsigned bound;             // warp-uniform max over valid lanes of (best >> 32)
+    unsigned phase;             // mbarrier parity (warp-uniform)
+    bool valid;                 // lane holds a real query
+    float4 *tile;               // per-warp smem leaf tile [CPHB_LEAF]
+    uint64_t *bar;              // per-warp mbarrier
+};
+
+// key strictly below (r2, idx 0): accepts exactly d2 < r2
+__device__ __forceinline__ unsigned long long init_key(float r2) {
+    return ((unsigned long long)__float_as_uint(r2) << 32) - 1ull;
+}
+
+template <class W>
+__device__ __forceinline__ void warp_query_box(W &w) {
+    unsigned lo[3], hi[3];
+    lo[0] = w.valid ? f2ord(w.qx) : 0xffffffffu; hi[0] = w.valid ? f2ord(w.qx) : 0u;
+    lo[1] = w.valid ? f2ord(w.qy) : 0xffffffffu; hi[1] = w.valid ? f2ord(w.qy) : 0u;
+    lo[2] = w.valid ? f2ord(w.qz) : 0xffffffffu; hi[2] = w.valid ? f2ord(w.qz) : 0u;
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        w.wlo[a] = ord2f(__reduce_min_sync(CPHB_FULL, lo[a]));
+        w.whi[a] = ord2f(__reduce_max_sync(CPHB_FULL, hi[a]));
+    }
+}
+
+// fetch one leaf tile by TMA into the warp's smem tile and wait for it
+template <class W>
+__device__ __forceinline__ void fetch_leaf(const IndexView &ix, unsigned leaf, W &w) {
+    if (lane_id() == 0) {
+        mbar_expect_tx(w.bar, CPHB_LEAF * 16);
+        tma_bulk_g2s(w.tile, ix.pts + (size_t)leaf * CPHB_LEAF, CPHB_LEAF * 16, w.bar);
+    }
+    while (!mbar_try_wait(w.bar, w.phase)) {
+    }
+    w.phase ^= 1u;
+}
+
+__device__ __forceinline__ void scan_leaf(const IndexView &ix, unsigned leaf, WarpSearch &w) {
+    fetch_leaf(ix, leaf, w);
+    unsigned long long best = w.best;
+#pragma unroll
+    for (int j = 0; j < CPHB_LEAF; ++j) {
+        float4 p = w.tile[j];
+        float d2 = dist2(w.qx, w.qy, w.qz, p.x, p.y, p.z);
+        unsigned long long key = ((unsigned long long)__float_as_uint(d2) << 32) | __float_as_uint(p.w);
+        best = (key < best) ? key : best;
+    }
+    w.best = best;
+    __syncwarp();  // all lanes done with the tile before lane 0 re-arms it
+    w.bound = __reduce_max_sync(CPHB_FULL, w.valid ? (unsigned)(best >> 32) : 0u);
+}
+
+// W provides: wlo/whi (warp AABB), bound (warp-uniform cull bound, d2 bits) and
+// an overload scan_leaf(ix, leaf, W&) that updates bound.
+template <int LV, class W>
+struct Visit {
+    static __device__ __forceinline__ void run(const IndexView &ix, unsigned group, W &w) {
+        const Box *b = ix.boxes[LV] + ((size_t)group * 32 + lane_id());
+        float4 lo = __ldg(&b->lo), hi = __ldg(&b->hi);
+        unsigned dbits = __float_as_uint(box_dist2(lo, hi, w.wlo, w.whi));
+        unsigned active = __ballot_sync(CPHB_FULL, dbits <= w.bound);
+        while (active) {
+            unsigned cand = ((active >> lane_id()) & 1u) ? dbits : 0xffffffffu;
+            unsigned dmin = __reduce_min_sync(CPHB_FULL, cand);
+            if (dmin > w.bound) break;  // everything left is farther than the current bound
+            unsigned who = __ballot_sync(CPHB_FULL, cand == dmin);
+            int src = __ffs(who) - 1;
+            active &= ~(1u << src);
+            unsigned child = group * 32 + src;
+            if constexpr (LV == 0) scan_leaf(ix, child, w);
+            else Visit<LV - 1, W>::run(ix, child, w);
+        }
+    }
+};
+
+// top-level entry: TOP is the compile-time depth the kernel was built for; the
+// index always has CPHB_LEVELS levels so a deeper kernel on a small cloud only
+// walks a few single-child nodes.
+template <int TOP, class W>
+__device__ __forceinline__ void warp_nn_search(const IndexView &ix, W &w) {
+    Visit<TOP, W>::run(ix, 0u, w);
+}
+
+template <class W>
+__device__ __forceinline__ void warp_search_setup(W &w, float4 *tile, uint64_t *bar) {
+    w.tile = tile;
+    w.bar = bar;
+    w.phase = 0;
+    if (lane_id() == 0) {
+        mbar_init(bar, 1);
+        fence_mbar_init();
+    }
+    __syncwarp();
+}
+#endif  // __CUDACC__

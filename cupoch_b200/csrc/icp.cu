@@ -1,0 +1,1082 @@
+// icp.cu -- fused ICP iteration (one launch per iteration) + device-side 6x6
+// solve / Kabsch / convergence logic + the RegistrationICP driver.
+//
+// Replaces, per iteration, the reference's ~13 thrust launches and >= 2 host
+// synchronisations:
+//   pcd.Transform(update)                      registration.cu:160, geometry_utils.cu:34-54,257-265
+//   kdtree.SearchRadius(.., 1, ..)             registration.cu:47, kdtree_cuda_3d_index.cu:52-154
+//   error2 / correspondence list               registration.cu:50-69
+//   ComputeJTJandJTr / Kabsch sums             eigen.inl:92-145, kabsch.cu:48-104
+//   SolveJacobianSystemAndObtainExtrinsicMatrix eigen.cu:75-122 (host Eigen LDLT in the reference)
+//   transformation = update * transformation   registration.cu:159
+//   convergence test                           registration.cu:165-170
+//
+// Arithmetic contract: per-row float32 arithmetic in the stated
+// order with explicit FMAs (this file is compiled with -fmad=false, so only
+// the __fmaf_rn/fma calls below fuse); sums of exact float*float products in
+// float64, reduced in a fixed order (warp -> block -> grid), rounded once to
+// float32; the 6x6 LDLT, se(3) exponential and 4x4 composition use unfused
+// float32 like the reference's host code.
+#include <float.h>
+#include <math.h>
+#include <string.h>
+
+#include "cphb_internal.cuh"
+#include "cphb_eigen3.cuh"
+
+#define ICP_BLOCK 256
+#define ICP_WARPS (ICP_BLOCK / 32)
+#define ROW_STRIDE 9 /* doubles per staged row: J0..J5, r, d2, one */
+
+struct IcpState {
+    double total[32];
+    double local[32];
+    float T[16];
+    float U[16];
+    float fitness, rmse;
+    int done;        // 0 running, 1 converged (materialise correspondences next), 2 finished
+    int iterations;  // updates applied
+    int converged;
+    int apply_u;
+    unsigned ticket;
+    int pad;
+    long long n_corr;
+};
+
+struct IcpArgs {
+    IndexView ix;
+    float4 *src;            // working copy, Hilbert order, w = original index
+    float4 *src_nrm;        // working normals (Symmetric) or null
+    float4 *src_cov;        // working covariances: 3 float4 rows per point, [3][n_pad] (GICP) or null
+    const float4 *src_col;  // colors in Hilbert order (Colored) or null
+    const float *tgt_xyz, *tgt_nrm, *tgt_col, *tgt_grad, *tgt_cov;
+    IcpState *st;
+    double *partials;
+    int32_t *corr_index;  // [n_src] matched target index per ORIGINAL source index, or null
+    unsigned long long n_total;
+    unsigned n_src, n_pad;
+    float r2;
+    float rel_fitness, rel_rmse, det_thresh, sg, sp;
+    int launch_idx, max_iter;
+    int tgt_cov_col_major;
+    int defer_finalize;  // multi-GPU: stop after writing st->local
+    int step_mode;       // debug hook: one search + sums, no solve
+};
+
+// sums layout (32 doubles): JTJ kinds: 0..20 JTJ upper | 21..26 JTr | 27 r^2 | 28 sum d2 | 29 count
+//                           P2P      : 0..2 sum s | 3..5 sum t | 6..14 sum s t^T | 28 sum d2 | 29 count
+__constant__ unsigned char c_pair_jtj[32][2] = {
+    {0, 0}, {0, 1}, {0, 2}, {0, 3}, {0, 4}, {0, 5}, {1, 1}, {1, 2}, {1, 3}, {1, 4}, {1, 5},
+    {2, 2}, {2, 3}, {2, 4}, {2, 5}, {3, 3}, {3, 4}, {3, 5}, {4, 4}, {4, 5}, {5, 5},
+    {0, 6}, {1, 6}, {2, 6}, {3, 6}, {4, 6}, {5, 6}, {6, 6}, {7, 8}, {8, 8}, {8, 8}, {8, 8}};
+__constant__ unsigned char c_pair_p2p[32][2] = {
+    {0, 8}, {1, 8}, {2, 8}, {3, 8}, {4, 8}, {5, 8}, {0, 3}, {0, 4}, {0, 5}, {1, 3}, {1, 4},
+    {1, 5}, {2, 3}, {2, 4}, {2, 5}, {8, 8}, {8, 8}, {8, 8}, {8, 8}, {8, 8}, {8, 8},
+    {8, 8}, {8, 8}, {8, 8}, {8, 8}, {8, 8}, {8, 8}, {8, 8}, {7, 8}, {8, 8}, {8, 8}, {8, 8}};
+__constant__ unsigned c_live_jtj = 0x3fffffffu;                          // lanes 0..29
+__constant__ unsigned c_live_p2p = 0x00007fffu | (1u << 28) | (1u << 29);  // 0..14, 28, 29
+
+// ===========================================================================
+// finalize: 6x6 solve / Kabsch / convergence (one thread)
+// ===========================================================================
+__device__ float det6_partial_piv(const float *A_in) {
+    float A[36];
+    for (int i = 0; i < 36; ++i) A[i] = A_in[i];
+    float det = 1.f;
+    for (int k = 0; k < 6; ++k) {
+        int p = k;
+        float best = fabsf(A[6 * k + k]);
+        for (int i = k + 1; i < 6; ++i)
+            if (fabsf(A[6 * i + k]) > best) { best = fabsf(A[6 * i + k]); p = i; }
+        if (best == 0.f) return 0.f;
+        if (p != k) {
+            for (int j = 0; j < 6; ++j) { float t = A[6 * k + j]; A[6 * k + j] = A[6 * p + j]; A[6 * p + j] = t; }
+            det = -det;
+        }
+        float piv = A[6 * k + k];
+        det = det * piv;
+        for (int i = k + 1; i < 6; ++i) {
+            float f = A[6 * i + k] / piv;
+            for (int j = k + 1; j < 6; ++j) A[6 * i + j] = A[6 * i + j] - f * A[6 * k + j];
+        }
+    }
+    return det;
+}
+// Eigen LDLT (diagonal pivoting, lower) + solve; eigen.cu:103 A.ldlt().solve(b)
+__device__ void ldlt6_solve(const float *A_in, const float *b, float *x) {
+    float A[36];
+    for (int i = 0; i < 36; ++i) A[i] = A_in[i];
+    int tr[6];
+    for (int k = 0; k < 6; ++k) {
+        int ib = k;
+        float big = fabsf(A[6 * k + k]);
+        for (int i = k + 1; i < 6; ++i)
+            if (fabsf(A[6 * i + i]) > big) { big = fabsf(A[6 * i + i]); ib = i; }
+        tr[k] = ib;
+        if (ib != k) {
+            for (int j = 0; j < k; ++j) { float t = A[6 * k + j]; A[6 * k + j] = A[6 * ib + j]; A[6 * ib + j] = t; }
+            for (int i = ib + 1; i < 6; ++i) { float t = A[6 * i + k]; A[6 * i + k] = A[6 * i + ib]; A[6 * i + ib] = t; }
+            { float t = A[6 * k + k]; A[6 * k + k] = A[6 * ib + ib]; A[6 * ib + ib] = t; }
+            for (int i = k + 1; i < ib; ++i) { float t = A[6 * i + k]; A[6 * i + k] = A[6 * ib + i]; A[6 * ib + i] = t; }
+        }
+        float temp[6];
+        if (k > 0) {
+            for (int j = 0; j < k; ++j) temp[j] = A[6 * j + j] * A[6 * k + j];
+            float s = 0.f;
+            for (int j = 0; j < k; ++j) s = s + A[6 * k + j] * temp[j];
+            A[6 * k + k] = A[6 * k + k] - s;
+            for (int i = k + 1; i < 6; ++i) {
+                float s2 = 0.f;
+                for (int j = 0; j < k; ++j) s2 = s2 + A[6 * i + j] * temp[j];
+                A[6 * i + k] = A[6 * i + k] - s2;
+            }
+        }
+        float akk = A[6 * k + k];
+        if (fabsf(akk) > 0.f)
+            for (int i = k + 1; i < 6; ++i) A[6 * i + k] = A[6 * i + k] / akk;
+    }
+    float y[6];
+    for (int i = 0; i < 6; ++i) y[i] = b[i];
+    for (int k = 0; k < 6; ++k)
+        if (tr[k] != k) { float t = y[k]; y[k] = y[tr[k]]; y[tr[k]] = t; }
+    for (int i = 0; i < 6; ++i) {
+        float s = y[i];
+        for (int j = 0; j < i; ++j) s = s - A[6 * i + j] * y[j];
+        y[i] = s;
+    }
+    for (int i = 0; i < 6; ++i) y[i] = (fabsf(A[6 * i + i]) > FLT_MIN) ? y[i] / A[6 * i + i] : 0.f;
+    for (int i = 5; i >= 0; --i) {
+        float s = y[i];
+        for (int j = i + 1; j < 6; ++j) s = s - A[6 * j + i] * y[j];
+        y[i] = s;
+    }
+    for (int k = 5; k >= 0; --k)
+        if (tr[k] != k) { float t = y[k]; y[k] = y[tr[k]]; y[tr[k]] = t; }
+    for (int i = 0; i < 6; ++i) x[i] = y[i];
+}
+__device__ void identity4(float *T) {
+    for (int i = 0; i < 16; ++i) T[i] = (i % 5 == 0) ? 1.f : 0.f;
+}
+__device__ void se3_exp(const float *x, float *T) {  // eigen.cu:28-50
+    identity4(T);
+    T[3] = x[3]; T[7] = x[4]; T[11] = x[5];
+    float th = sqrtf((x[0] * x[0] + x[1] * x[1]) + x[2] * x[2]);
+    if (th == 0) return;
+    float w0 = x[0] / th, w1 = x[1] / th, w2 = x[2] / th;
+    float c = (float)cos((double)th), s = (float)sin((double)th);
+    float oc = 1 - c;
+    T[0] = c + w0 * w0 * oc;
+    T[1] = w0 * w1 * oc - w2 * s;
+    T[2] = w1 * s + w0 * w2 * oc;
+    T[4] = w2 * s + w0 * w1 * oc;
+    T[5] = c + w1 * w1 * oc;
+    T[6] = -w0 * s + w1 * w2 * oc;
+    T[8] = -w1 * s + w0 * w2 * oc;
+    T[9] = w0 * s + w1 * w2 * oc;
+    T[10] = c + w2 * w2 * oc;
+}
+__device__ bool solve_jtj(const double *S, float det_thresh, float *T) {
+    float A[36], b[6], x[6];
+    int p = 0;
+    for (int a = 0; a < 6; ++a)
+        for (int c = a; c < 6; ++c) { float v = (float)S[p++]; A[6 * a + c] = v; A[6 * c + a] = v; }
+    for (int a = 0; a < 6; ++a) b[a] = -(float)S[21 + a];
+    identity4(T);
+    if (det_thresh > 0) {  // eigen.cu:88-100
+        float det = det6_partial_piv(A);
+        if (fabsf(det) < det_thresh || isnan(det) || isinf(det)) return false;
+    }
+    ldlt6_solve(A, b, x);
+    se3_exp(x, T);
+    return true;
+}
+__device__ void matmul4(const float *A, const float *B, float *C) {  // registration.cu:159
+    float R[16];
+    for (int i = 0; i < 4; ++i)
+        for (int j = 0; j < 4; ++j)
+            R[4 * i + j] = ((A[4 * i] * B[j] + A[4 * i + 1] * B[4 + j]) + A[4 * i + 2] * B[8 + j]) + A[4 * i + 3] * B[12 + j];
+    for (int i = 0; i < 16; ++i) C[i] = R[i];
+}
+// one-sided Jacobi SVD (double) -- stands in for Eigen::JacobiSVD<Matrix3f> (kabsch.cu:108-109);
+// R = V diag(1,1,det(UV)) U^T is unique whatever the SVD's sign/ordering conventions.
+__device__ void svd3(const double *A, double *U, double *s, double *V) {
+    double B[9];
+    for (int i = 0; i < 9; ++i) { B[i] = A[i]; V[i] = (i % 4 == 0) ? 1.0 : 0.0; }
+    for (int sweep = 0; sweep < 60; ++sweep) {
+        double off = 0;
+        for (int p = 0; p < 2; ++p)
+            for (int q = p + 1; q < 3; ++q) {
+                double al = 0, be = 0, ga = 0;
+                for (int i = 0; i < 3; ++i) {
+                    al += B[3 * i + p] * B[3 * i + p];
+                    be += B[3 * i + q] * B[3 * i + q];
+                    ga += B[3 * i + p] * B[3 * i + q];
+                }
+                if (fabs(ga) <= 1e-300 || fabs(ga) <= 1e-17 * sqrt(al * be)) continue;
+                off += fabs(ga);
+                double zeta = (be - al) / (2.0 * ga);
+                double t = ((zeta >= 0) ? 1.0 : -1.0) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
+                double c = 1.0 / sqrt(1.0 + t * t), sn = c * t;
+                for (int i = 0; i < 3; ++i) {
+                    double bp = B[3 * i + p], bq = B[3 * i + q];
+                    B[3 * i + p] = c * bp - sn * bq;
+                    B[3 * i + q] = sn * bp + c * bq;
+                    double vp = V[3 * i + p], vq = V[3 * i + q];
+                    V[3 * i + p] = c * vp - sn * vq;
+                    V[3 * i + q] = sn * vp + c * vq;
+                }
+            }
+        if (off == 0) break;
+    }
+    for (int j = 0; j < 3; ++j) {
+        double nn = sqrt(B[j] * B[j] + B[3 + j] * B[3 + j] + B[6 + j] * B[6 + j]);
+        s[j] = nn;
+        for (int i = 0; i < 3; ++i) U[3 * i + j] = (nn > 0) ? B[3 * i + j] / nn : 0.0;
+    }
+    for (int j = 0; j < 3; ++j)
+        if (s[j] == 0) {
+            int a = (j + 1) % 3, b = (j + 2) % 3;
+            if (s[a] > 0 && s[b] > 0) {
+                U[j] = U[3 + a] * U[6 + b] - U[6 + a] * U[3 + b];
+                U[3 + j] = U[6 + a] * U[b] - U[a] * U[6 + b];
+                U[6 + j] = U[a] * U[3 + b] - U[3 + a] * U[b];
+            }
+        }
+}
+// kabsch.cu:42-120 incl. the divide-by-model.size() quirk (:76-78,107)
+__device__ void kabsch_from_sums(const double *S, unsigned long long n_model, float *T) {
+    identity4(T);
+    double C = S[29];
+    float div = 1.0f / (float)n_model;
+    float mc[3], tc[3];
+    for (int a = 0; a < 3; ++a) { mc[a] = (float)S[a] * div; tc[a] = (float)S[3 + a] * div; }
+    double H[9];
+    for (int a = 0; a < 3; ++a)
+        for (int b = 0; b < 3; ++b) {
+            double h = S[6 + 3 * a + b] - (double)mc[a] * S[3 + b] - S[a] * (double)tc[b] + C * (double)mc[a] * (double)tc[b];
+            H[3 * a + b] = (double)((float)h / (float)n_model);
+        }
+    double U[9], sv[3], V[9], UV[9];
+    svd3(H, U, sv, V);
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j) UV[3 * i + j] = U[3 * i] * V[j] + U[3 * i + 1] * V[3 + j] + U[3 * i + 2] * V[6 + j];
+    double dd = UV[0] * (UV[4] * UV[8] - UV[5] * UV[7]) - UV[1] * (UV[3] * UV[8] - UV[5] * UV[6]) +
+                UV[2] * (UV[3] * UV[7] - UV[4] * UV[6]);
+    double ss[3] = {1.0, 1.0, dd};
+    float R[9];
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j) {
+            double r = 0;
+            for (int k = 0; k < 3; ++k) r += V[3 * i + k] * ss[k] * U[3 * j + k];
+            R[3 * i + j] = (float)r;
+        }
+    for (int i = 0; i < 3; ++i) {
+        for (int j = 0; j < 3; ++j) T[4 * i + j] = R[3 * i + j];
+        T[4 * i + 3] = tc[i] - dot3(R[3 * i], R[3 * i + 1], R[3 * i + 2], mc[0], mc[1], mc[2]);
+    }
+}
+
+// registration.cu:71-78,154-172 -- runs in ONE thread after the grid-wide sum.
+template <int KIND>
+__device__ void icp_finalize(const IcpArgs &a, IcpState *st) {
+    const double *S = st->total;
+    double cnt = S[29];
+    float fit = 0.f, rmse = 0.f;
+    if (cnt > 0) {
+        fit = (float)cnt / (float)a.n_total;
+        rmse = sqrtf((float)S[28] / (float)cnt);
+    }
+    float pf = st->fitness, pr = st->rmse;
+    st->fitness = fit;
+    st->rmse = rmse;
+    st->n_corr = (long long)cnt;
+    if (a.step_mode) return;
+    if (a.launch_idx > 0 && fabsf(pf - fit) < a.rel_fitness && fabsf(pr - rmse) < a.rel_rmse) {
+        st->converged = 1;
+        st->done = (a.corr_index && a.launch_idx < a.max_iter) ? 1 : 2;
+        return;
+    }
+    if (a.launch_idx >= a.max_iter) {
+        st->done = 2;
+        return;
+    }
+    float Up[16];
+    identity4(Up);
+    if (cnt > 0) {
+        if (KIND == CPHB_EST_POINT_TO_POINT) {
+            kabsch_from_sums(S, a.n_total, Up);
+        } else {
+            bool have = true;
+            if ((KIND == CPHB_EST_POINT_TO_PLANE || KIND == CPHB_EST_COLORED_ICP) && !a.tgt_nrm) have = false;
+            if (KIND == CPHB_EST_SYMMETRIC && (!a.tgt_nrm || !a.src_nrm)) have = false;
+            if (KIND == CPHB_EST_COLORED_ICP && (!a.tgt_col || !a.src_col)) have = false;
+            if (KIND == CPHB_EST_GENERALIZED_ICP && (!a.tgt_cov || !a.src_cov)) have = false;
+            if (have) {
+                float dt = (KIND == CPHB_EST_GENERALIZED_ICP) ? -1.f : a.det_thresh;
+                bool ok = solve_jtj(S, dt, Up);
+                if (ok && KIND == CPHB_EST_SYMMETRIC) {  // transformation_estimation.cu:319-339
+                    double R[9], R2[9];
+                    for (int i = 0; i < 3; ++i)
+                        for (int j = 0; j < 3; ++j) R[3 * i + j] = (double)Up[4 * i + j];
+                    for (int i = 0; i < 3; ++i)
+                        for (int j = 0; j < 3; ++j)
+                            R2[3 * i + j] = R[3 * i] * R[j] + R[3 * i + 1] * R[3 + j] + R[3 * i + 2] * R[6 + j];
+                    for (int i = 0; i < 3; ++i)
+                        for (int j = 0; j < 3; ++j) Up[4 * i + j] = (float)R2[3 * i + j];
+                }
+            }
+        }
+    }
+    float Tn[16];
+    matmul4(Up, st->T, Tn);
+    for (int i = 0; i < 16; ++i) { st->T[i] = Tn[i]; st->U[i] = Up[i]; }
+    st->apply_u = 1;
+    st->iterations += 1;
+}
+
+// ===========================================================================
+// the fused per-iteration kernel
+// ===========================================================================
+template <int KIND, int TOP>
+__global__ void __launch_bounds__(ICP_BLOCK) icp_iteration_kernel(const __grid_constant__ IcpArgs a) {
+    __shared__ __align__(16) float4 s_tile[ICP_WARPS][CPHB_LEAF];
+    __shared__ uint64_t s_bar[ICP_WARPS];
+    __shared__ double s_rows[ICP_WARPS][32 * ROW_STRIDE];
+    __shared__ double s_acc[ICP_WARPS][32];
+    __shared__ unsigned s_last;
+
+    IcpState *st = a.st;
+    const int done = *(volatile int *)&st->done;
+    if (done == 2) return;
+    const bool materialize = (done == 1);
+    const bool apply = !materialize && !a.step_mode ? (*(volatile int *)&st->apply_u != 0) : (a.step_mode != 0);
+    const int warp = threadIdx.x >> 5, lane = lane_id();
+
+    WarpSearch w;
+    warp_search_setup(w, s_tile[warp], &s_bar[warp]);
+
+    const unsigned i = blockIdx.x * ICP_BLOCK + threadIdx.x;  // position in Hilbert order (< n_pad)
+    float4 s = a.src[i];
+    const unsigned orig = __float_as_uint(s.w);
+    w.valid = i < a.n_src;
+
+    // ---- PointCloud::Transform(update) on the working copy (pointcloud.cu:293-299) ----
+    float sn[3] = {0.f, 0.f, 0.f};
+    float Cs[9];
+    if (apply) {
+        float U[12];
+#pragma unroll
+        for (int k = 0; k < 12; ++k) U[k] = st->U[k];
+        float x = s.x, y = s.y, z = s.z;
+        s.x = __fadd_rn(dot3(U[0], U[1], U[2], x, y, z), U[3]);
+        s.y = __fadd_rn(dot3(U[4], U[5], U[6], x, y, z), U[7]);
+        s.z = __fadd_rn(dot3(U[8], U[9], U[10], x, y, z), U[11]);
+        if (!a.step_mode) a.src[i] = s;
+        if (KIND == CPHB_EST_SYMMETRIC && a.src_nrm) {
+            float4 n4 = a.src_nrm[i];
+            sn[0] = dot3(U[0], U[1], U[2], n4.x, n4.y, n4.z);
+            sn[1] = dot3(U[4], U[5], U[6], n4.x, n4.y, n4.z);
+            sn[2] = dot3(U[8], U[9], U[10], n4.x, n4.y, n4.z);
+            if (!a.step_mode) a.src_nrm[i] = make_float4(sn[0], sn[1], sn[2], 0.f);
+        }
+        if (KIND == CPHB_EST_GENERALIZED_ICP && a.src_cov) {
+            float C[9], tmp[9];
+#pragma unroll
+            for (int r = 0; r < 3; ++r) {
+                float4 c4 = a.src_cov[(size_t)r * a.n_pad + i];
+                C[3 * r] = c4.x; C[3 * r + 1] = c4.y; C[3 * r + 2] = c4.z;
+            }
+            const float R[9] = {U[0], U[1], U[2], U[4], U[5], U[6], U[8], U[9], U[10]};
+#pragma unroll
+            for (int r = 0; r < 3; ++r)
+#pragma unroll
+                for (int c = 0; c < 3; ++c)
+                    tmp[3 * r + c] = dot3(R[3 * r], R[3 * r + 1], R[3 * r + 2], C[c], C[3 + c], C[6 + c]);
+#pragma unroll
+            for (int r = 0; r < 3; ++r)
+#pragma unroll
+                for (int c = 0; c < 3; ++c)
+                    Cs[3 * r + c] = dot3(tmp[3 * r], tmp[3 * r + 1], tmp[3 * r + 2], R[3 * c], R[3 * c + 1], R[3 * c + 2]);
+            if (!a.step_mode)
+#pragma unroll
+                for (int r = 0; r < 3; ++r)
+                    a.src_cov[(size_t)r * a.n_pad + i] = make_float4(Cs[3 * r], Cs[3 * r + 1], Cs[3 * r + 2], 0.f);
+        }
+    } else {
+        if (KIND == CPHB_EST_SYMMETRIC && a.src_nrm) {
+            float4 n4 = a.src_nrm[i];
+            sn[0] = n4.x; sn[1] = n4.y; sn[2] = n4.z;
+        }
+        if (KIND == CPHB_EST_GENERALIZED_ICP && a.src_cov) {
+#pragma unroll
+            for (int r = 0; r < 3; ++r) {
+                float4 c4 = a.src_cov[(size_t)r * a.n_pad + i];
+                Cs[3 * r] = c4.x; Cs[3 * r + 1] = c4.y; Cs[3 * r + 2] = c4.z;
+            }
+        }
+    }
+
+    // ---- SearchRadius(.., max_nn = 1) (registration.cu:47) -----------------------------
+    w.qx = s.x; w.qy = s.y; w.qz = s.z;
+    const unsigned long long init = (a.r2 > 0.f) ? init_key(a.r2) : 0ull;
+    w.best = init;
+    w.bound = (unsigned)(init >> 32);
+    warp_query_box(w);
+    if (__any_sync(CPHB_FULL, w.valid)) warp_nn_search<TOP>(a.ix, w);
+    const bool found = w.valid && (w.best != init);
+    const unsigned j = (unsigned)(w.best & 0xffffffffull);
+    const float d2 = __uint_as_float((unsigned)(w.best >> 32));
+
+    if (a.corr_index && w.valid && (materialize || a.step_mode || a.launch_idx == a.max_iter))
+        a.corr_index[orig] = found ? (int32_t)j : -1;
+    if (materialize) {
+        // nothing to accumulate: fitness / rmse / T of this pose are already in the state
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            __threadfence();
+            unsigned t = atomicAdd(&st->ticket, 1u);
+            if (t == gridDim.x - 1) { st->ticket = 0; st->done = 2; }
+        }
+        return;
+    }
+
+    // ---- rows: J (6), r; staged as doubles, one row of 9 per lane -----------------------
+    double *rows = s_rows[warp];
+    const unsigned char(*pair)[2] = (KIND == CPHB_EST_POINT_TO_POINT) ? c_pair_p2p : c_pair_jtj;
+    const int ca = pair[lane][0], cb = pair[lane][1];
+    double acc = 0.0;
+    constexpr int NROWS = (KIND == CPHB_EST_COLORED_ICP) ? 2 : (KIND == CPHB_EST_GENERALIZED_ICP) ? 3 : 1;
+    float J[NROWS][6], r[NROWS];
+#pragma unroll
+    for (int q = 0; q < NROWS; ++q) {
+        r[q] = 0.f;
+#pragma unroll
+        for (int c = 0; c < 6; ++c) J[q][c] = 0.f;
+    }
+    bool use = found;
+    if (found) {
+        const float vs[3] = {s.x, s.y, s.z};
+        const float vt[3] = {a.tgt_xyz[3 * (size_t)j], a.tgt_xyz[3 * (size_t)j + 1], a.tgt_xyz[3 * (size_t)j + 2]};
+        if (KIND == CPHB_EST_POINT_TO_POINT) {
+            J[0][0] = vs[0]; J[0][1] = vs[1]; J[0][2] = vs[2];
+            J[0][3] = vt[0]; J[0][4] = vt[1]; J[0][5] = vt[2];
+        } else if (KIND == CPHB_EST_POINT_TO_PLANE) {  // transformation_estimation.cu:34-56
+            if (a.tgt_nrm) {
+                const float nt[3] = {a.tgt_nrm[3 * (size_t)j], a.tgt_nrm[3 * (size_t)j + 1], a.tgt_nrm[3 * (size_t)j + 2]};
+                r[0] = dot3(vs[0] - vt[0], vs[1] - vt[1], vs[2] - vt[2], nt[0], nt[1], nt[2]);
+                cross3(vs, nt, J[0]);
+                J[0][3] = nt[0]; J[0][4] = nt[1]; J[0][5] = nt[2];
+            }
+        } else if (KIND == CPHB_EST_SYMMETRIC) {  // transformation_estimation.cu:58-90
+            if (a.tgt_nrm && a.src_nrm) {
+                const float nn[3] = {sn[0] + a.tgt_nrm[3 * (size_t)j], sn[1] + a.tgt_nrm[3 * (size_t)j + 1],
+                                     sn[2] + a.tgt_nrm[3 * (size_t)j + 2]};
+                const float sm[3] = {vs[0] + vt[0], vs[1] + vt[1], vs[2] + vt[2]};
+                r[0] = dot3(vs[0] - vt[0], vs[1] - vt[1], vs[2] - vt[2], nn[0], nn[1], nn[2]);
+                cross3(sm, nn, J[0]);
+                J[0][3] = nn[0]; J[0][4] = nn[1]; J[0][5] = nn[2];
+            }
+        } else if (KIND == CPHB_EST_COLORED_ICP) {  // colored_icp.cu:150-216
+            if (a.tgt_nrm && a.tgt_col && a.src_col && a.tgt_grad) {
+                const size_t j3 = 3 * (size_t)j;
+                const float nt[3] = {a.tgt_nrm[j3], a.tgt_nrm[j3 + 1], a.tgt_nrm[j3 + 2]};
+                const float gt[3] = {a.tgt_grad[j3], a.tgt_grad[j3 + 1], a.tgt_grad[j3 + 2]};
+                const float4 cs = a.src_col[i];
+                const float d[3] = {vs[0] - vt[0], vs[1] - vt[1], vs[2] - vt[2]};
+                const float dn = dot3(d[0], d[1], d[2], nt[0], nt[1], nt[2]);
+                float cr[3];
+                cross3(vs, nt, cr);
+#pragma unroll
+                for (int c = 0; c < 3; ++c) { J[0][c] = a.sg * cr[c]; J[0][3 + c] = a.sg * nt[c]; }
+                r[0] = a.sg * dn;
+                float pd[3];
+#pragma unroll
+                for (int c = 0; c < 3; ++c) pd[c] = __fmaf_rn(-dn, nt[c], vs[c]) - vt[c];
+                const float is = intensity(cs.x, cs.y, cs.z);
+                const float it = intensity(a.tgt_col[j3], a.tgt_col[j3 + 1], a.tgt_col[j3 + 2]);
+                const float is0 = dot3(gt[0], gt[1], gt[2], pd[0], pd[1], pd[2]) + it;
+                float M[9];
+#pragma unroll
+                for (int p = 0; p < 3; ++p)
+#pragma unroll
+                    for (int q = 0; q < 3; ++q)
+                        M[3 * p + q] = (p == q) ? (float)(1.0 - (double)(nt[p] * nt[p]))
+                                                : (-nt[p < q ? p : q]) * nt[p < q ? q : p];
+                float gm[3];
+#pragma unroll
+                for (int q = 0; q < 3; ++q) gm[q] = dot3(-gt[0], -gt[1], -gt[2], M[q], M[3 + q], M[6 + q]);
+                cross3(vs, gm, cr);
+#pragma unroll
+                for (int c = 0; c < 3; ++c) { J[1 % NROWS][c] = a.sp * cr[c]; J[1 % NROWS][3 + c] = a.sp * gm[c]; }
+                r[1 % NROWS] = a.sp * (is - is0);
+            }
+        } else if (KIND == CPHB_EST_GENERALIZED_ICP) {  // generalized_icp.cu:63-105
+            if (a.tgt_cov && a.src_cov) {
+                float Mx[9], Mi[9], W[9];
+                const float *ct = a.tgt_cov + 9 * (size_t)j;
+#pragma unroll
+                for (int p = 0; p < 3; ++p)
+#pragma unroll
+                    for (int q = 0; q < 3; ++q)
+                        Mx[3 * p + q] = ct[a.tgt_cov_col_major ? (3 * q + p) : (3 * p + q)] + Cs[3 * p + q];
+                inverse3x3(Mx, Mi);
+                sqrt_matrix3x3(Mi, W);
+                const float d[3] = {vs[0] - vt[0], vs[1] - vt[1], vs[2] - vt[2]};
+#pragma unroll
+                for (int q = 0; q < 3; ++q) {
+                    const float *wr = W + 3 * q;
+                    J[q % NROWS][0] = __fmaf_rn(wr[2], vs[1], -(wr[1] * vs[2]));
+                    J[q % NROWS][1] = __fmaf_rn(wr[2], -vs[0], wr[0] * vs[2]);
+                    J[q % NROWS][2] = __fmaf_rn(wr[1], vs[0], -(wr[0] * vs[1]));
+                    J[q % NROWS][3] = wr[0]; J[q % NROWS][4] = wr[1]; J[q % NROWS][5] = wr[2];
+                    r[q % NROWS] = dot3(wr[0], wr[1], wr[2], d[0], d[1], d[2]);
+                }
+            }
+        }
+    }
+    // stage + accumulate: lane L adds column pair (ca, cb) over the 32 staged rows, in row order
+#pragma unroll
+    for (int q = 0; q < NROWS; ++q) {
+        double *my = rows + lane * ROW_STRIDE;
+#pragma unroll
+        for (int c = 0; c < 6; ++c) my[c] = (double)J[q][c];
+        my[6] = (double)r[q];
+        my[7] = (q == 0 && use) ? (double)d2 : 0.0;
+        my[8] = (q == 0 && use) ? 1.0 : 0.0;
+        __syncwarp();
+#pragma unroll 8
+        for (int t = 0; t < 32; ++t) acc = fma(rows[t * ROW_STRIDE + ca], rows[t * ROW_STRIDE + cb], acc);
+        __syncwarp();
+    }
+    {
+        const unsigned live = (KIND == CPHB_EST_POINT_TO_POINT) ? c_live_p2p : c_live_jtj;
+        if (!((live >> lane) & 1u)) acc = 0.0;
+    }
+
+    // ---- block sum (fixed order) -> partials[block][32] ---------------------------------
+    s_acc[warp][lane] = acc;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        double t = 0.0;
+#pragma unroll
+        for (int k = 0; k < ICP_WARPS; ++k) t += s_acc[k][threadIdx.x];
+        a.partials[(size_t)blockIdx.x * 32 + threadIdx.x] = t;
+        __threadfence();
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned t = atomicAdd(&st->ticket, 1u);
+        s_last = (t == gridDim.x - 1) ? 1u : 0u;
+    }
+    __syncthreads();
+    if (!s_last) return;
+
+    // ---- last block: grid sum in block order, then the host-side part of the loop ---------
+    __threadfence();
+    {
+        const int c = threadIdx.x & 31, g = threadIdx.x >> 5;
+        double t = 0.0;
+        for (unsigned b = g; b < gridDim.x; b += ICP_WARPS) t += __ldcg(&a.partials[(size_t)b * 32 + c]);
+        s_acc[g][c] = t;
+    }
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        double t = 0.0;
+#pragma unroll
+        for (int k = 0; k < ICP_WARPS; ++k) t += s_acc[k][threadIdx.x];
+        if (a.defer_finalize) st->local[threadIdx.x] = t;
+        else st->total[threadIdx.x] = t;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        st->ticket = 0;
+        if (!a.defer_finalize) icp_finalize<KIND>(a, st);
+        __threadfence();
+    }
+}
+
+// multi-GPU: runs after the all-reduce of st->local into st->total
+template <int KIND>
+__global__ void icp_finalize_kernel(const __grid_constant__ IcpArgs a) {
+    if (threadIdx.x == 0 && a.st->done != 2) icp_finalize<KIND>(a, a.st);
+}
+
+// ---------------------------------------------------------------------------
+// source preparation + correspondence compaction kernels
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) gather_source_kernel(const float *__restrict__ xyz, const float *__restrict__ nrm,
+                                                            const float *__restrict__ col, const float *__restrict__ cov,
+                                                            int cov_col_major, const uint32_t *__restrict__ perm,
+                                                            unsigned n, unsigned n_pad, float4 *o_xyz, float4 *o_nrm,
+                                                            float4 *o_col, float4 *o_cov) {
+    unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_pad) return;
+    if (i < n) {
+        size_t j = perm[i];
+        o_xyz[i] = make_float4(xyz[3 * j], xyz[3 * j + 1], xyz[3 * j + 2], __uint_as_float((unsigned)j));
+        if (o_nrm) o_nrm[i] = make_float4(nrm[3 * j], nrm[3 * j + 1], nrm[3 * j + 2], 0.f);
+        if (o_col) o_col[i] = make_float4(col[3 * j], col[3 * j + 1], col[3 * j + 2], 0.f);
+        if (o_cov) {
+            const float *c = cov + 9 * j;
+            for (int r = 0; r < 3; ++r)
+                o_cov[(size_t)r * n_pad + i] = cov_col_major ? make_float4(c[r], c[3 + r], c[6 + r], 0.f)
+                                                             : make_float4(c[3 * r], c[3 * r + 1], c[3 * r + 2], 0.f);
+        }
+    } else {
+        // padding lanes: a copy of the last real point keeps loads in bounds; w = -1, never "valid"
+        size_t j = n ? perm[n - 1] : 0;
+        float4 p = n ? make_float4(xyz[3 * j], xyz[3 * j + 1], xyz[3 * j + 2], 0.f) : make_float4(0.f, 0.f, 0.f, 0.f);
+        p.w = __uint_as_float(0xffffffffu);
+        o_xyz[i] = p;
+        if (o_nrm) o_nrm[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (o_col) o_col[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (o_cov)
+            for (int r = 0; r < 3; ++r) o_cov[(size_t)r * n_pad + i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+}
+
+// stable compaction of (i, corr_index[i]) with corr_index[i] >= 0 (registration.cu:54-69)
+#define CMP_BLOCK 1024
+__global__ void __launch_bounds__(CMP_BLOCK) compact_count_kernel(const int32_t *__restrict__ ci, unsigned n,
+                                                                  unsigned *block_counts) {
+    __shared__ unsigned s_w[32];
+    unsigned i = blockIdx.x * CMP_BLOCK + threadIdx.x;
+    bool v = i < n && ci[i] >= 0;
+    unsigned m = __ballot_sync(CPHB_FULL, v);
+    if (lane_id() == 0) s_w[threadIdx.x >> 5] = __popc(m);
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        unsigned c = s_w[threadIdx.x];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(CPHB_FULL, c, o);
+        if (threadIdx.x == 0) block_counts[blockIdx.x] = c;
+    }
+}
+__global__ void __launch_bounds__(1024) compact_scan_kernel(unsigned *block_counts, unsigned nb, unsigned *total) {
+    __shared__ unsigned s_w[32];
+    __shared__ unsigned s_carry;
+    if (threadIdx.x == 0) s_carry = 0;
+    __syncthreads();
+    for (unsigned base = 0; base < nb; base += 1024) {
+        unsigned i = base + threadIdx.x;
+        unsigned v = i < nb ? block_counts[i] : 0u;
+        unsigned x = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            unsigned y = __shfl_up_sync(CPHB_FULL, x, o);
+            if (lane_id() >= o) x += y;
+        }
+        if (lane_id() == 31) s_w[threadIdx.x >> 5] = x;
+        __syncthreads();
+        if (threadIdx.x < 32) {
+            unsigned ws = s_w[threadIdx.x], z = ws;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                unsigned y = __shfl_up_sync(CPHB_FULL, z, o);
+                if (lane_id() >= o) z += y;
+            }
+            s_w[threadIdx.x] = z - ws;
+        }
+        __syncthreads();
+        unsigned excl = x - v + s_w[threadIdx.x >> 5] + s_carry;
+        if (i < nb) block_counts[i] = excl;
+        __syncthreads();
+        if (threadIdx.x == 1023) s_carry = excl + v;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *total = s_carry;
+}
+__global__ void __launch_bounds__(CMP_BLOCK) compact_write_kernel(const int32_t *__restrict__ ci, unsigned n,
+                                                                  const unsigned *__restrict__ block_offsets,
+                                                                  int32_t *out_pairs) {
+    __shared__ unsigned s_w[32];
+    unsigned i = blockIdx.x * CMP_BLOCK + threadIdx.x;
+    int32_t j = i < n ? ci[i] : -1;
+    bool v = j >= 0;
+    unsigned m = __ballot_sync(CPHB_FULL, v);
+    if (lane_id() == 0) s_w[threadIdx.x >> 5] = __popc(m);
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        unsigned ws = s_w[threadIdx.x], z = ws;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            unsigned y = __shfl_up_sync(CPHB_FULL, z, o);
+            if (lane_id() >= o) z += y;
+        }
+        s_w[threadIdx.x] = z - ws;
+    }
+    __syncthreads();
+    if (v) {
+        unsigned pos = block_offsets[blockIdx.x] + s_w[threadIdx.x >> 5] + __popc(m & ((1u << lane_id()) - 1u));
+        out_pairs[2 * (size_t)pos] = (int32_t)i;
+        out_pairs[2 * (size_t)pos + 1] = j;
+    }
+}
+
+// PointCloud::Transform as a standalone op (pointcloud.cu:293-299)
+__global__ void __launch_bounds__(256) transform_kernel(float *p, float *nrm, float *cov, int cov_col_major, size_t n,
+                                                        const float *__restrict__ Tdev) {
+    size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float U[12];
+#pragma unroll
+    for (int k = 0; k < 12; ++k) U[k] = Tdev[k];
+    if (p) {
+        float x = p[3 * i], y = p[3 * i + 1], z = p[3 * i + 2];
+        p[3 * i] = __fadd_rn(dot3(U[0], U[1], U[2], x, y, z), U[3]);
+        p[3 * i + 1] = __fadd_rn(dot3(U[4], U[5], U[6], x, y, z), U[7]);
+        p[3 * i + 2] = __fadd_rn(dot3(U[8], U[9], U[10], x, y, z), U[11]);
+    }
+    if (nrm) {
+        float x = nrm[3 * i], y = nrm[3 * i + 1], z = nrm[3 * i + 2];
+        nrm[3 * i] = dot3(U[0], U[1], U[2], x, y, z);
+        nrm[3 * i + 1] = dot3(U[4], U[5], U[6], x, y, z);
+        nrm[3 * i + 2] = dot3(U[8], U[9], U[10], x, y, z);
+    }
+    if (cov) {
+        float C[9], tmp[9], O[9];
+        float *c = cov + 9 * i;
+        for (int r = 0; r < 3; ++r)
+            for (int q = 0; q < 3; ++q) C[3 * r + q] = c[cov_col_major ? 3 * q + r : 3 * r + q];
+        const float R[9] = {U[0], U[1], U[2], U[4], U[5], U[6], U[8], U[9], U[10]};
+        for (int r = 0; r < 3; ++r)
+            for (int q = 0; q < 3; ++q)
+                tmp[3 * r + q] = dot3(R[3 * r], R[3 * r + 1], R[3 * r + 2], C[q], C[3 + q], C[6 + q]);
+        for (int r = 0; r < 3; ++r)
+            for (int q = 0; q < 3; ++q)
+                O[3 * r + q] = dot3(tmp[3 * r], tmp[3 * r + 1], tmp[3 * r + 2], R[3 * q], R[3 * q + 1], R[3 * q + 2]);
+        for (int r = 0; r < 3; ++r)
+            for (int q = 0; q < 3; ++q) c[cov_col_major ? 3 * q + r : 3 * r + q] = O[3 * r + q];
+    }
+}
+
+// ===========================================================================
+// host driver
+// ===========================================================================
+int cphb_nccl_allreduce_f64(void *comm, const double *send, double *recv, size_t count, cudaStream_t s);  // nccl_dyn.cu
+
+struct cphb_icp {
+    cphb_index *index;
+    cphb_icp_params prm;
+    cphb_cloud tgt;
+    unsigned n_src, n_pad;
+    void *arena;
+    size_t arena_bytes;
+    float4 *pristine_xyz, *pristine_nrm, *pristine_cov;  // Hilbert-ordered source as given
+    float4 *work_xyz, *work_nrm, *work_cov;
+    float4 *src_col;
+    IcpState *st;
+    IcpState *h_st;  // pinned
+    cudaEvent_t ev0, ev1;
+    double *partials;
+    int32_t *corr_index;
+    unsigned *cmp_counts;
+    unsigned *cmp_total;
+    unsigned grid;
+    cudaStream_t stream;
+};
+
+static bool is_identity4(const float *T) {  // Eigen isIdentity(1e-5), registration.cu:148
+    for (int i = 0; i < 4; ++i)
+        for (int j = 0; j < 4; ++j) {
+            float v = T[4 * i + j];
+            if (i == j) { if (fabsf(v - 1.f) > 1e-5f) return false; }
+            else if (fabsf(v) > 1e-5f) return false;
+        }
+    return true;
+}
+
+template <int KIND>
+static void launch_iteration(const cphb_icp *icp, const IcpArgs &a, cudaStream_t s) {
+    if (icp->index->v.top <= 3) CPHB_LAUNCH((icp_iteration_kernel<KIND, 3>), icp->grid, ICP_BLOCK, 0, s, a);
+    else CPHB_LAUNCH((icp_iteration_kernel<KIND, 5>), icp->grid, ICP_BLOCK, 0, s, a);
+}
+static void launch_iteration_kind(const cphb_icp *icp, const IcpArgs &a, cudaStream_t s) {
+    switch (icp->prm.estimation) {
+        case CPHB_EST_POINT_TO_POINT: launch_iteration<CPHB_EST_POINT_TO_POINT>(icp, a, s); break;
+        case CPHB_EST_POINT_TO_PLANE: launch_iteration<CPHB_EST_POINT_TO_PLANE>(icp, a, s); break;
+        case CPHB_EST_SYMMETRIC: launch_iteration<CPHB_EST_SYMMETRIC>(icp, a, s); break;
+        case CPHB_EST_COLORED_ICP: launch_iteration<CPHB_EST_COLORED_ICP>(icp, a, s); break;
+        case CPHB_EST_GENERALIZED_ICP: launch_iteration<CPHB_EST_GENERALIZED_ICP>(icp, a, s); break;
+    }
+}
+static void launch_finalize_kind(const cphb_icp *icp, const IcpArgs &a, cudaStream_t s) {
+    switch (icp->prm.estimation) {
+        case CPHB_EST_POINT_TO_POINT: CPHB_LAUNCH(icp_finalize_kernel<CPHB_EST_POINT_TO_POINT>, 1, 32, 0, s, a); break;
+        case CPHB_EST_POINT_TO_PLANE: CPHB_LAUNCH(icp_finalize_kernel<CPHB_EST_POINT_TO_PLANE>, 1, 32, 0, s, a); break;
+        case CPHB_EST_SYMMETRIC: CPHB_LAUNCH(icp_finalize_kernel<CPHB_EST_SYMMETRIC>, 1, 32, 0, s, a); break;
+        case CPHB_EST_COLORED_ICP: CPHB_LAUNCH(icp_finalize_kernel<CPHB_EST_COLORED_ICP>, 1, 32, 0, s, a); break;
+        case CPHB_EST_GENERALIZED_ICP: CPHB_LAUNCH(icp_finalize_kernel<CPHB_EST_GENERALIZED_ICP>, 1, 32, 0, s, a); break;
+    }
+}
+
+extern "C" int cphb_icp_create(const cphb_cloud *source, const cphb_cloud *target, const cphb_icp_params *params,
+                               void *stream, cphb_icp **out) {
+    cudaStream_t s = (cudaStream_t)stream;
+    if (!source || !target || !params || !out) {
+        cphb_set_error("cphb_icp_create: null argument");
+        return CPHB_ERR_INVALID;
+    }
+    if (params->estimation < CPHB_EST_POINT_TO_POINT || params->estimation > CPHB_EST_GENERALIZED_ICP) {
+        cphb_set_error("cphb_icp_create: estimation %d has no fused path (use the facade's generic loop)",
+                       params->estimation);
+        return CPHB_ERR_UNSUPPORTED;
+    }
+    if (source->n > 0x7fffff00ull || target->n > 0x7fffffffull) {
+        cphb_set_error("cphb_icp_create: cloud exceeds int32 indices");
+        return CPHB_ERR_INVALID;
+    }
+    cphb_icp *icp = new cphb_icp();
+    memset(icp, 0, sizeof(*icp));
+    icp->prm = *params;
+    icp->tgt = *target;
+    icp->stream = s;
+    int rc = cphb_index_create(target->points, target->n, s, &icp->index);
+    if (rc) { delete icp; return rc; }
+    const unsigned n = (unsigned)source->n;
+    const unsigned n_pad = (unsigned)cphb_align(n ? n : 1, ICP_BLOCK);
+    icp->n_src = n;
+    icp->n_pad = n_pad;
+    icp->grid = n_pad / ICP_BLOCK;
+    const bool want_nrm = params->estimation == CPHB_EST_SYMMETRIC && source->normals;
+    const bool want_col = params->estimation == CPHB_EST_COLORED_ICP && source->colors;
+    const bool want_cov = params->estimation == CPHB_EST_GENERALIZED_ICP && source->covariances;
+    size_t off = 0;
+    auto take = [&](size_t bytes) { size_t o = off; off = cphb_align(off + bytes, 256); return o; };
+    size_t o_pxyz = take(sizeof(float4) * n_pad), o_wxyz = take(sizeof(float4) * n_pad);
+    size_t o_pnrm = want_nrm ? take(sizeof(float4) * n_pad) : 0, o_wnrm = want_nrm ? take(sizeof(float4) * n_pad) : 0;
+    size_t o_pcov = want_cov ? take(sizeof(float4) * 3 * n_pad) : 0, o_wcov = want_cov ? take(sizeof(float4) * 3 * n_pad) : 0;
+    size_t o_col = want_col ? take(sizeof(float4) * n_pad) : 0;
+    size_t o_st = take(sizeof(IcpState));
+    size_t o_part = take(sizeof(double) * 32 * icp->grid);
+    size_t o_ci = take(sizeof(int32_t) * n_pad);
+    unsigned cmp_blocks = (n_pad + CMP_BLOCK - 1) / CMP_BLOCK;
+    size_t o_cc = take(sizeof(unsigned) * (cmp_blocks + 1));
+    size_t o_ct = take(16);
+    size_t o_perm = take(sizeof(uint32_t) * n_pad);
+    icp->arena_bytes = off;
+    rc = cphb_alloc_async(&icp->arena, off, s);
+    if (rc) { cphb_index_destroy(icp->index); delete icp; return rc; }
+    char *b = (char *)icp->arena;
+    icp->pristine_xyz = (float4 *)(b + o_pxyz);
+    icp->work_xyz = (float4 *)(b + o_wxyz);
+    icp->pristine_nrm = want_nrm ? (float4 *)(b + o_pnrm) : nullptr;
+    icp->work_nrm = want_nrm ? (float4 *)(b + o_wnrm) : nullptr;
+    icp->pristine_cov = want_cov ? (float4 *)(b + o_pcov) : nullptr;
+    icp->work_cov = want_cov ? (float4 *)(b + o_wcov) : nullptr;
+    icp->src_col = want_col ? (float4 *)(b + o_col) : nullptr;
+    icp->st = (IcpState *)(b + o_st);
+    icp->partials = (double *)(b + o_part);
+    icp->corr_index = (int32_t *)(b + o_ci);
+    icp->cmp_counts = (unsigned *)(b + o_cc);
+    icp->cmp_total = (unsigned *)(b + o_ct);
+    uint32_t *perm = (uint32_t *)(b + o_perm);
+    CPHB_CUDA(cudaMallocHost((void **)&icp->h_st, sizeof(IcpState)));
+    CPHB_CUDA(cudaEventCreate(&icp->ev0));
+    CPHB_CUDA(cudaEventCreate(&icp->ev1));
+    if (n) {
+        rc = cphb_hilbert_order(source->points, n, perm, nullptr, 0, s);
+        if (rc) { cphb_icp_destroy(icp); return rc; }
+    }
+    CPHB_LAUNCH(gather_source_kernel, n_pad / 256, 256, 0, s, source->points, source->normals, source->colors,
+                source->covariances, source->cov_col_major, perm, n, n_pad, icp->pristine_xyz, icp->pristine_nrm,
+                icp->src_col, icp->pristine_cov);
+    CPHB_CHECK_LAUNCH();
+    *out = icp;
+    return CPHB_OK;
+}
+
+extern "C" void cphb_icp_destroy(cphb_icp *icp) {
+    if (!icp) return;
+    if (icp->arena) cudaFreeAsync(icp->arena, icp->stream);
+    if (icp->h_st) cudaFreeHost(icp->h_st);
+    if (icp->ev0) cudaEventDestroy(icp->ev0);
+    if (icp->ev1) cudaEventDestroy(icp->ev1);
+    cphb_index_destroy(icp->index);
+    delete icp;
+}
+
+static void fill_args(const cphb_icp *icp, IcpArgs &a) {
+    memset(&a, 0, sizeof(a));
+    a.ix = icp->index->v;
+    a.src = icp->work_xyz;
+    a.src_nrm = icp->work_nrm;
+    a.src_cov = icp->work_cov;
+    a.src_col = icp->src_col;
+    a.tgt_xyz = icp->tgt.points;
+    a.tgt_nrm = icp->tgt.normals;
+    a.tgt_col = icp->tgt.colors;
+    a.tgt_grad = icp->tgt.color_gradient;
+    a.tgt_cov = icp->tgt.covariances;
+    a.tgt_cov_col_major = icp->tgt.cov_col_major;
+    a.st = icp->st;
+    a.partials = icp->partials;
+    a.n_src = icp->n_src;
+    a.n_pad = icp->n_pad;
+    a.n_total = icp->n_src;
+    float r = icp->prm.max_correspondence_distance;
+    a.r2 = (r > 0.f) ? r * r : 0.f;  // registration.cu:40-42: r <= 0 -> no correspondences
+    a.rel_fitness = icp->prm.relative_fitness;
+    a.rel_rmse = icp->prm.relative_rmse;
+    a.det_thresh = icp->prm.det_thresh;
+    a.max_iter = icp->prm.max_iteration > 0 ? icp->prm.max_iteration : 0;
+    float lg = icp->prm.lambda_geometric;
+    if (lg < 0.f || lg > 1.0f) lg = 0.968f;  // colored_icp.cu:48-52
+    a.sg = (float)sqrt((double)lg);
+    float lp = (float)(1.0 - (double)lg);
+    a.sp = (float)sqrt((double)lp);
+}
+
+static int reset_working_copy(cphb_icp *icp, cudaStream_t s) {
+    CPHB_CUDA(cudaMemcpyAsync(icp->work_xyz, icp->pristine_xyz, sizeof(float4) * icp->n_pad, cudaMemcpyDeviceToDevice, s));
+    if (icp->work_nrm)
+        CPHB_CUDA(cudaMemcpyAsync(icp->work_nrm, icp->pristine_nrm, sizeof(float4) * icp->n_pad, cudaMemcpyDeviceToDevice, s));
+    if (icp->work_cov)
+        CPHB_CUDA(cudaMemcpyAsync(icp->work_cov, icp->pristine_cov, sizeof(float4) * 3 * icp->n_pad, cudaMemcpyDeviceToDevice, s));
+    return CPHB_OK;
+}
+
+static int compact_correspondences(cphb_icp *icp, int32_t *corr_out, cudaStream_t s) {
+    unsigned n = icp->n_src;
+    unsigned nb = (n + CMP_BLOCK - 1) / CMP_BLOCK;
+    if (nb == 0) nb = 1;
+    CPHB_LAUNCH(compact_count_kernel, nb, CMP_BLOCK, 0, s, icp->corr_index, n, icp->cmp_counts);
+    CPHB_LAUNCH(compact_scan_kernel, 1, 1024, 0, s, icp->cmp_counts, nb, icp->cmp_total);
+    CPHB_LAUNCH(compact_write_kernel, nb, CMP_BLOCK, 0, s, icp->corr_index, n, icp->cmp_counts, corr_out);
+    CPHB_CHECK_LAUNCH();
+    return CPHB_OK;
+}
+
+extern "C" int cphb_icp_run(cphb_icp *icp, const float h_init[16], void *nccl_comm, cphb_icp_result *h_result,
+                            int32_t *corr_out, void *stream) {
+    cudaStream_t s = (cudaStream_t)stream;
+    if (!icp || !h_init || !h_result) {
+        cphb_set_error("cphb_icp_run: null argument");
+        return CPHB_ERR_INVALID;
+    }
+    int rc = reset_working_copy(icp, s);
+    if (rc) return rc;
+    IcpState *h = icp->h_st;
+    memset(h, 0, sizeof(*h));
+    memcpy(h->T, h_init, 64);
+    memcpy(h->U, h_init, 64);
+    h->apply_u = is_identity4(h_init) ? 0 : 1;
+    CPHB_CUDA(cudaMemcpyAsync(icp->st, h, sizeof(IcpState), cudaMemcpyHostToDevice, s));
+    IcpArgs a;
+    fill_args(icp, a);
+    a.corr_index = corr_out ? icp->corr_index : nullptr;
+    unsigned long long n_total = icp->n_src;
+    if (nccl_comm) {
+        // global source size: one tiny all-reduce before the loop
+        double *tmp = icp->partials;  // scratch
+        double hn = (double)icp->n_src;
+        CPHB_CUDA(cudaMemcpyAsync(tmp, &hn, 8, cudaMemcpyHostToDevice, s));
+        rc = cphb_nccl_allreduce_f64(nccl_comm, tmp, tmp, 1, s);
+        if (rc) return rc;
+        CPHB_CUDA(cudaMemcpyAsync(&hn, tmp, 8, cudaMemcpyDeviceToHost, s));
+        CPHB_CUDA(cudaStreamSynchronize(s));
+        n_total = (unsigned long long)hn;
+        a.defer_finalize = 1;
+    }
+    a.n_total = n_total;
+    // launches 0..max_iter: search (+ update).  If the convergence test stops the loop at launch
+    // j < max_iter, launch j+1 re-runs that search only to materialise its correspondences;
+    // launches after "done" exit at their first instruction.
+    const unsigned long long launches0 = g_cphb_launches;
+    CPHB_CUDA(cudaEventRecord(icp->ev0, s));
+    for (int it = 0; it <= a.max_iter; ++it) {
+        a.launch_idx = it;
+        launch_iteration_kind(icp, a, s);
+        if (nccl_comm) {
+            rc = cphb_nccl_allreduce_f64(nccl_comm, icp->st->local, icp->st->total, 32, s);
+            if (rc) return rc;
+            launch_finalize_kind(icp, a, s);
+        }
+    }
+    CPHB_CUDA(cudaEventRecord(icp->ev1, s));
+    const int loop_launches = (int)(g_cphb_launches - launches0);
+    CPHB_CHECK_LAUNCH();
+    if (corr_out) {
+        rc = compact_correspondences(icp, corr_out, s);
+        if (rc) return rc;
+    }
+    CPHB_CUDA(cudaMemcpyAsync(h, icp->st, sizeof(IcpState), cudaMemcpyDeviceToHost, s));
+    CPHB_CUDA(cudaStreamSynchronize(s));
+    memcpy(h_result->transformation, h->T, 64);
+    h_result->fitness = h->fitness;
+    h_result->inlier_rmse = h->rmse;
+    h_result->n_correspondences = h->n_corr;
+    h_result->iterations = h->iterations;
+    h_result->converged = h->converged;
+    h_result->loop_ms = 0.f;
+    cudaEventElapsedTime(&h_result->loop_ms, icp->ev0, icp->ev1);
+    h_result->loop_launches = loop_launches;
+    return CPHB_OK;
+}
+
+extern "C" int cphb_icp_step(cphb_icp *icp, const float h_T[16], double h_sums[32], int32_t *corr_index, void *stream) {
+    cudaStream_t s = (cudaStream_t)stream;
+    if (!icp || !h_T || !h_sums) {
+        cphb_set_error("cphb_icp_step: null argument");
+        return CPHB_ERR_INVALID;
+    }
+    int rc = reset_working_copy(icp, s);
+    if (rc) return rc;
+    IcpState *h = icp->h_st;
+    memset(h, 0, sizeof(*h));
+    memcpy(h->T, h_T, 64);
+    memcpy(h->U, h_T, 64);
+    h->apply_u = 1;
+    CPHB_CUDA(cudaMemcpyAsync(icp->st, h, sizeof(IcpState), cudaMemcpyHostToDevice, s));
+    IcpArgs a;
+    fill_args(icp, a);
+    a.step_mode = 1;
+    a.corr_index = icp->corr_index;
+    launch_iteration_kind(icp, a, s);
+    CPHB_CHECK_LAUNCH();
+    if (corr_index)
+        CPHB_CUDA(cudaMemcpyAsync(corr_index, icp->corr_index, sizeof(int32_t) * icp->n_src, cudaMemcpyDeviceToDevice, s));
+    CPHB_CUDA(cudaMemcpyAsync(h, icp->st, sizeof(IcpState), cudaMemcpyDeviceToHost, s));
+    CPHB_CUDA(cudaStreamSynchronize(s));
+    memcpy(h_sums, h->total, sizeof(double) * 32);
+    return CPHB_OK;
+}
+
+extern "C" int cphb_registration_icp(const cphb_cloud *source, const cphb_cloud *target, const float h_init[16],
+                                     const cphb_icp_params *params, void *nccl_comm, cphb_icp_result *h_result,
+                                     int32_t *corr_out, void *stream) {
+    cphb_icp *icp = nullptr;
+    int rc = cphb_icp_create(source, target, params, stream, &icp);
+    if (rc) return rc;
+    rc = cphb_icp_run(icp, h_init, nccl_comm, h_result, corr_out, stream);
+    cphb_icp_destroy(icp);
+    return rc;
+}
+
+extern "C" int cphb_evaluate_registration(const cphb_cloud *source, const cphb_cloud *target,
+                                          float max_correspondence_distance, const float h_T[16],
+                                          cphb_icp_result *h_result, int32_t *corr_out, void *stream) {
+    cphb_icp_params p;
+    memset(&p, 0, sizeof(p));
+    p.estimation = CPHB_EST_POINT_TO_POINT;
+    p.max_correspondence_distance = max_correspondence_distance;
+    p.max_iteration = 0;
+    cphb_cloud src = *source, tgt = *target;
+    src.normals = src.colors = src.covariances = nullptr;
+    tgt.normals = tgt.colors = tgt.covariances = tgt.color_gradient = nullptr;
+    return cphb_registration_icp(&src, &tgt, h_T, &p, nullptr, h_result, corr_out, stream);
+}
+
+extern "C" int cphb_transform(float *points, float *normals, float *covariances, int cov_col_major, size_t n,
+                              const float h_T[16], void *stream) {
+    cudaStream_t s = (cudaStream_t)stream;
+    if (n == 0) return CPHB_OK;
+    float *Td = nullptr;
+    int rc = cphb_alloc_async((void **)&Td, 64, s);
+    if (rc) return rc;
+    CPHB_CUDA(cudaMemcpyAsync(Td, h_T, 64, cudaMemcpyHostToDevice, s));
+    CPHB_LAUNCH(transform_kernel, (unsigned)((n + 255) / 256), 256, 0, s, points, normals, covariances, cov_col_major, n, Td);
+    CPHB_CHECK_LAUNCH();
+    cphb_free_async(Td, s);
+    return CPHB_OK;
+}

@@ -1,0 +1,367 @@
+// index.cu -- spatial index build (replaces KDTreeFlann::SetRawData + the
+// vendored FLANN CUDA kd-tree builder, kdtree_flann.inl:125-144,
+// kdtree_cuda_builder.h:401-700).
+//
+// Build = bounds reduce -> 30-bit 3-D Hilbert keys -> radix sort -> gather to
+// float4 (w = original index) -> per-leaf AABBs -> 5 levels of 32-ary AABBs.
+// No pointers, no per-level host synchronisation: ~12 launches, all
+// stream-ordered.
+#include <float.h>
+#include <stdarg.h>
+#include <string.h>
+
+#include "cphb_internal.cuh"
+
+// ---------------------------------------------------------------------------
+// library-wide host state
+// ---------------------------------------------------------------------------
+static thread_local char t_err[512] = "";
+unsigned long long g_cphb_launches = 0;
+
+void cphb_set_error(const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(t_err, sizeof(t_err), fmt, ap);
+    va_end(ap);
+}
+extern "C" const char *cphb_last_error(void) { return t_err; }
+extern "C" int cphb_version(void) { return CPHB_VERSION; }
+extern "C" uint64_t cphb_launch_count(void) { return g_cphb_launches; }
+extern "C" int cphb_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+extern "C" int cphb_set_device(int d) {
+    CPHB_CUDA(cudaSetDevice(d));
+    return CPHB_OK;
+}
+
+int cphb_alloc_async(void **p, size_t bytes, cudaStream_t s) {
+    static thread_local int pool_ready_dev = -1;
+    int dev = 0;
+    CPHB_CUDA(cudaGetDevice(&dev));
+    if (pool_ready_dev != dev) {
+        cudaMemPool_t pool;
+        CPHB_CUDA(cudaDeviceGetDefaultMemPool(&pool, dev));
+        uint64_t thr = UINT64_MAX;  // keep freed blocks: no cudaMalloc on later calls
+        CPHB_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr));
+        pool_ready_dev = dev;
+    }
+    CPHB_CUDA(cudaMallocAsync(p, bytes ? bytes : 16, s));
+    return CPHB_OK;
+}
+void cphb_free_async(void *p, cudaStream_t s) {
+    if (p) cudaFreeAsync(p, s);
+}
+
+extern "C" void *cphb_malloc(size_t bytes) {
+    void *p = nullptr;
+    if (cudaMalloc(&p, bytes ? bytes : 16) != cudaSuccess) {
+        cphb_set_error("cudaMalloc(%zu) failed: %s", bytes, cudaGetErrorString(cudaGetLastError()));
+        return nullptr;
+    }
+    return p;
+}
+extern "C" void cphb_free(void *p) {
+    if (p) cudaFree(p);
+}
+extern "C" void *cphb_malloc_host(size_t bytes) {
+    void *p = nullptr;
+    if (cudaMallocHost(&p, bytes ? bytes : 16) != cudaSuccess) {
+        cphb_set_error("cudaMallocHost(%zu) failed: %s", bytes, cudaGetErrorString(cudaGetLastError()));
+        return nullptr;
+    }
+    return p;
+}
+extern "C" void cphb_free_host(void *p) {
+    if (p) cudaFreeHost(p);
+}
+extern "C" int cphb_memcpy_h2d(void *dst, const void *src, size_t bytes, void *stream) {
+    CPHB_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, (cudaStream_t)stream));
+    return CPHB_OK;
+}
+extern "C" int cphb_memcpy_d2h(void *dst, const void *src, size_t bytes, void *stream) {
+    CPHB_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    return CPHB_OK;
+}
+extern "C" int cphb_memset(void *dst, int value, size_t bytes, void *stream) {
+    CPHB_CUDA(cudaMemsetAsync(dst, value, bytes, (cudaStream_t)stream));
+    return CPHB_OK;
+}
+extern "C" int cphb_stream_synchronize(void *stream) {
+    CPHB_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+    return CPHB_OK;
+}
+
+// ---------------------------------------------------------------------------
+// kernels
+// ---------------------------------------------------------------------------
+__global__ void bounds_init_kernel(unsigned *b) {
+    if (threadIdx.x < 3) b[threadIdx.x] = 0xffffffffu;
+    else if (threadIdx.x < 6) b[threadIdx.x] = 0u;
+}
+
+// element-wise min / max (eigen.inl:197-221); order independent, exact.
+__global__ void __launch_bounds__(256) bounds_kernel(const float *__restrict__ xyz, size_t n, unsigned *b) {
+    unsigned lo[3] = {0xffffffffu, 0xffffffffu, 0xffffffffu}, hi[3] = {0u, 0u, 0u};
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+            unsigned o = f2ord(xyz[3 * i + a]);
+            lo[a] = min(lo[a], o);
+            hi[a] = max(hi[a], o);
+        }
+    }
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        lo[a] = __reduce_min_sync(CPHB_FULL, lo[a]);
+        hi[a] = __reduce_max_sync(CPHB_FULL, hi[a]);
+    }
+    if (lane_id() == 0) {
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+            atomicMin(&b[a], lo[a]);
+            atomicMax(&b[3 + a], hi[a]);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) hilbert_key_kernel(const float *__restrict__ xyz, size_t n,
+                                                          const unsigned *__restrict__ b, uint32_t *keys,
+                                                          uint32_t *vals) {
+    size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float mn[3] = {ord2f(b[0]), ord2f(b[1]), ord2f(b[2])};
+    float ext = fmaxf(fmaxf(ord2f(b[3]) - mn[0], ord2f(b[4]) - mn[1]), ord2f(b[5]) - mn[2]);
+    float scale = (ext > 0.f && ext < FLT_MAX) ? 1023.999f / ext : 0.f;
+    uint32_t c[3];
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        float v = (xyz[3 * i + a] - mn[a]) * scale;
+        c[a] = (uint32_t)fminf(fmaxf(v, 0.f), 1023.f);
+    }
+    keys[i] = hilbert30(c[0], c[1], c[2]);
+    vals[i] = (uint32_t)i;
+}
+
+// pts[pos] = (xyz[perm[pos]], perm[pos]); tail padding = (FLT_MAX x3, -1)
+__global__ void __launch_bounds__(256) gather_points_kernel(const float *__restrict__ xyz,
+                                                            const uint32_t *__restrict__ perm, size_t n,
+                                                            size_t n_pad, float4 *pts) {
+    size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (i >= n_pad) return;
+    float4 p;
+    if (i < n) {
+        uint32_t j = perm[i];
+        p.x = xyz[3 * (size_t)j];
+        p.y = xyz[3 * (size_t)j + 1];
+        p.z = xyz[3 * (size_t)j + 2];
+        p.w = __uint_as_float(j);
+    } else {
+        p.x = p.y = p.z = FLT_MAX;
+        p.w = __uint_as_float(0xffffffffu);
+    }
+    pts[i] = p;
+}
+
+// one warp per leaf (CPHB_LEAF == 32): AABB of its real points
+__global__ void __launch_bounds__(256) leaf_box_kernel(const float4 *__restrict__ pts, size_t n,
+                                                       size_t n_boxes_pad, Box *boxes) {
+    size_t leaf = (blockIdx.x * (size_t)blockDim.x + threadIdx.x) >> 5;
+    if (leaf >= n_boxes_pad) return;
+    size_t i = leaf * CPHB_LEAF + lane_id();
+    unsigned lo[3] = {0xffffffffu, 0xffffffffu, 0xffffffffu}, hi[3] = {0u, 0u, 0u};
+    if (i < n) {
+        float4 p = pts[i];
+        lo[0] = hi[0] = f2ord(p.x);
+        lo[1] = hi[1] = f2ord(p.y);
+        lo[2] = hi[2] = f2ord(p.z);
+    }
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        lo[a] = __reduce_min_sync(CPHB_FULL, lo[a]);
+        hi[a] = __reduce_max_sync(CPHB_FULL, hi[a]);
+    }
+    if (lane_id() == 0) {
+        Box b;
+        bool empty = lo[0] == 0xffffffffu && hi[0] == 0u;
+        b.lo = empty ? make_float4(INFINITY, INFINITY, INFINITY, 0.f)
+                     : make_float4(ord2f(lo[0]), ord2f(lo[1]), ord2f(lo[2]), 0.f);
+        b.hi = empty ? make_float4(-INFINITY, -INFINITY, -INFINITY, 0.f)
+                     : make_float4(ord2f(hi[0]), ord2f(hi[1]), ord2f(hi[2]), 0.f);
+        boxes[leaf] = b;
+    }
+}
+
+// one warp per parent: union of its 32 children (children array is padded with
+// empty boxes, so no bounds logic is needed beyond the parent count)
+__global__ void __launch_bounds__(256) upper_box_kernel(const Box *__restrict__ child, size_t n_child,
+                                                        size_t n_parent_pad, Box *parent) {
+    size_t p = (blockIdx.x * (size_t)blockDim.x + threadIdx.x) >> 5;
+    if (p >= n_parent_pad) return;
+    size_t c = p * 32 + lane_id();
+    float4 lo = make_float4(INFINITY, INFINITY, INFINITY, 0.f), hi = make_float4(-INFINITY, -INFINITY, -INFINITY, 0.f);
+    if (c < n_child) {
+        lo = child[c].lo;
+        hi = child[c].hi;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        lo.x = fminf(lo.x, __shfl_xor_sync(CPHB_FULL, lo.x, o));
+        lo.y = fminf(lo.y, __shfl_xor_sync(CPHB_FULL, lo.y, o));
+        lo.z = fminf(lo.z, __shfl_xor_sync(CPHB_FULL, lo.z, o));
+        hi.x = fmaxf(hi.x, __shfl_xor_sync(CPHB_FULL, hi.x, o));
+        hi.y = fmaxf(hi.y, __shfl_xor_sync(CPHB_FULL, hi.y, o));
+        hi.z = fmaxf(hi.z, __shfl_xor_sync(CPHB_FULL, hi.z, o));
+    }
+    if (lane_id() == 0) {
+        Box b;
+        b.lo = lo;
+        b.hi = hi;
+        parent[p] = b;
+    }
+}
+
+// ---------------------------------------------------------------------------
+// host
+// ---------------------------------------------------------------------------
+int cphb_hilbert_order(const float *xyz, size_t n, uint32_t *perm_out, float *bounds_dev6, int bounds_given,
+                       cudaStream_t s) {
+    if (n == 0) return CPHB_OK;
+    unsigned *b = (unsigned *)bounds_dev6;
+    if (!b) bounds_given = 0;
+    void *own = nullptr;
+    if (!b) {
+        int rc = cphb_alloc_async(&own, 32, s);
+        if (rc) return rc;
+        b = (unsigned *)own;
+    }
+    uint32_t *scratch = nullptr;
+    int rc = cphb_alloc_async((void **)&scratch, sizeof(uint32_t) * 3 * n, s);
+    if (rc) return rc;
+    uint32_t *keys = scratch, *keys2 = scratch + n, *vals = scratch + 2 * n;
+    if (!bounds_given) {
+        CPHB_LAUNCH(bounds_init_kernel, 1, 32, 0, s, b);
+        int grid = (int)((n + 255) / 256);
+        if (grid > 148 * 8) grid = 148 * 8;
+        CPHB_LAUNCH(bounds_kernel, grid, 256, 0, s, xyz, n, b);
+    }
+    CPHB_LAUNCH(hilbert_key_kernel, (unsigned)((n + 255) / 256), 256, 0, s, xyz, n, b, keys, vals);
+    CPHB_CHECK_LAUNCH();
+    rc = cphb_sort_pairs_u32(keys, keys2, vals, perm_out, n, 30, s);
+    cphb_free_async(scratch, s);
+    cphb_free_async(own, s);
+    return rc;
+}
+
+extern "C" int cphb_index_create(const float *xyz, size_t n, void *stream, cphb_index **out) {
+    cudaStream_t s = (cudaStream_t)stream;
+    if (!out || (n && !xyz)) {
+        cphb_set_error("cphb_index_create: null argument");
+        return CPHB_ERR_INVALID;
+    }
+    if (n > (size_t)0x7fffffff) {
+        cphb_set_error("cphb_index_create: n=%zu exceeds int32 indices", n);
+        return CPHB_ERR_INVALID;
+    }
+    cphb_index *ix = new cphb_index();
+    memset(ix, 0, sizeof(*ix));
+    CPHB_CUDA(cudaGetDevice(&ix->device));
+    ix->stream = s;
+    size_t count[CPHB_LEVELS], pad[CPHB_LEVELS];
+    count[0] = (n + CPHB_LEAF - 1) / CPHB_LEAF;
+    for (int l = 0; l < CPHB_LEVELS; ++l) {
+        if (l) count[l] = (count[l - 1] + 31) / 32;
+        pad[l] = cphb_align(count[l] ? count[l] : 1, 32);
+    }
+    if (count[CPHB_LEVELS - 1] > 32) {
+        cphb_set_error("cphb_index_create: n=%zu too large for %d levels", n, CPHB_LEVELS);
+        delete ix;
+        return CPHB_ERR_INVALID;
+    }
+    size_t n_pad = (count[0] ? count[0] : 1) * CPHB_LEAF;
+    size_t off_pts = 0;
+    size_t off = cphb_align(n_pad * sizeof(float4), 256);
+    size_t off_box[CPHB_LEVELS];
+    for (int l = 0; l < CPHB_LEVELS; ++l) {
+        off_box[l] = off;
+        off = cphb_align(off + pad[l] * sizeof(Box), 256);
+    }
+    size_t off_bounds = off;
+    off += 256;
+    size_t off_perm = off;
+    off = cphb_align(off + sizeof(uint32_t) * (n ? n : 1), 256);
+    ix->arena_bytes = off;
+    int rc = cphb_alloc_async(&ix->arena, off, s);
+    if (rc) {
+        delete ix;
+        return rc;
+    }
+    char *base = (char *)ix->arena;
+    float4 *pts = (float4 *)(base + off_pts);
+    Box *boxes[CPHB_LEVELS];
+    for (int l = 0; l < CPHB_LEVELS; ++l) boxes[l] = (Box *)(base + off_box[l]);
+    ix->bounds = (float *)(base + off_bounds);
+    uint32_t *perm = (uint32_t *)(base + off_perm);
+
+    if (n) {
+        rc = cphb_hilbert_order(xyz, n, perm, ix->bounds, 0, s);
+        if (rc) {
+            cphb_free_async(ix->arena, s);
+            delete ix;
+            return rc;
+        }
+    } else {
+        CPHB_LAUNCH(bounds_init_kernel, 1, 32, 0, s, (unsigned *)ix->bounds);
+    }
+    CPHB_LAUNCH(gather_points_kernel, (unsigned)((n_pad + 255) / 256), 256, 0, s, xyz, perm, n, n_pad, pts);
+    CPHB_LAUNCH(leaf_box_kernel, (unsigned)((pad[0] * 32 + 255) / 256), 256, 0, s, pts, n, pad[0], boxes[0]);
+    for (int l = 1; l < CPHB_LEVELS; ++l)
+        CPHB_LAUNCH(upper_box_kernel, (unsigned)((pad[l] * 32 + 255) / 256), 256, 0, s, boxes[l - 1], count[l - 1],
+                    pad[l], boxes[l]);
+    CPHB_CHECK_LAUNCH();
+
+    ix->v.pts = pts;
+    for (int l = 0; l < CPHB_LEVELS; ++l) ix->v.boxes[l] = boxes[l];
+    ix->v.n = n;
+    ix->v.n_leaves = (unsigned)count[0];
+    int top = 0;
+    while (count[top] > 32) ++top;
+    ix->v.top = top;
+    *out = ix;
+    return CPHB_OK;
+}
+
+extern "C" void cphb_index_destroy(cphb_index *ix) {
+    if (!ix) return;
+    if (ix->arena) cudaFreeAsync(ix->arena, ix->stream);
+    delete ix;
+}
+extern "C" size_t cphb_index_size(const cphb_index *ix) { return ix ? (size_t)ix->v.n : 0; }
+
+extern "C" int cphb_min_max_bound(const float *points, size_t n, float h_min[3], float h_max[3], void *stream) {
+    cudaStream_t s = (cudaStream_t)stream;
+    for (int a = 0; a < 3; ++a) h_min[a] = h_max[a] = 0.f;  // reference: Zero() for an empty cloud
+    if (n == 0) return CPHB_OK;
+    unsigned *b = nullptr;
+    int rc = cphb_alloc_async((void **)&b, 32, s);
+    if (rc) return rc;
+    CPHB_LAUNCH(bounds_init_kernel, 1, 32, 0, s, b);
+    int grid = (int)((n + 255) / 256);
+    if (grid > 148 * 8) grid = 148 * 8;
+    CPHB_LAUNCH(bounds_kernel, grid, 256, 0, s, points, n, b);
+    CPHB_CHECK_LAUNCH();
+    unsigned h[6];
+    CPHB_CUDA(cudaMemcpyAsync(h, b, sizeof(h), cudaMemcpyDeviceToHost, s));
+    CPHB_CUDA(cudaStreamSynchronize(s));
+    cphb_free_async(b, s);
+    for (int a = 0; a < 3; ++a) {
+        h_min[a] = ord2f(h[a]);
+        h_max[a] = ord2f(h[3 + a]);
+    }
+    return CPHB_OK;
+}

@@ -1,0 +1,217 @@
+// search.cu -- batched exact kNN / radius search on the Hilbert-AABB index.
+// Replaces KDTreeFlann::SearchKNN / SearchRadius (kdtree_flann.cu:35-80,
+// kdtree_flann.inl:70-122) and flann's nearestKernel
+// (kdtree_cuda_3d_index.cu:52-154) with its result sets (result_set.h).
+//
+// Queries are ordered along the target's Hilbert curve first (one radix sort)
+// so that each warp's 32 queries form a compact cluster; a warp then walks the
+// 32-ary AABB hierarchy cooperatively (cphb_internal.cuh).  Results are written
+// back at the queries' original positions.
+#include <float.h>
+
+#include "cphb_internal.cuh"
+
+// ---------------------------------------------------------------------------
+// k-best result set per lane, kept in shared memory as list[k][32] (column =
+// lane, so any mix of insert positions is bank-conflict free).  Ascending by
+// key = (d2 bits, index).  Mirrors KnnRadiusResultSet (result_set.h:372-474):
+// strict d2 < r2, unfilled slots idx=-1 / d2=+inf.
+// ---------------------------------------------------------------------------
+struct WarpSearchK {
+    float qx, qy, qz;
+    float wlo[3], whi[3];
+    unsigned bound;
+    unsigned phase;
+    bool valid;
+    float4 *tile;
+    uint64_t *bar;
+    unsigned long long *list;  // this lane's column
+    int k;
+    unsigned long long worst;  // == list[(k-1)*32]
+};
+
+__device__ __forceinline__ void scan_leaf(const IndexView &ix, unsigned leaf, WarpSearchK &w) {
+    fetch_leaf(ix, leaf, w);
+    const int k = w.k;
+#pragma unroll 4
+    for (int j = 0; j < CPHB_LEAF; ++j) {
+        float4 p = w.tile[j];
+        float d2 = dist2(w.qx, w.qy, w.qz, p.x, p.y, p.z);
+        unsigned long long key = ((unsigned long long)__float_as_uint(d2) << 32) | __float_as_uint(p.w);
+        if (key < w.worst) {
+            int pos = k - 1;
+            while (pos > 0) {
+                unsigned long long prev = w.list[(pos - 1) * 32];
+                if (prev <= key) break;
+                w.list[pos * 32] = prev;
+                --pos;
+            }
+            w.list[pos * 32] = key;
+            w.worst = w.list[(k - 1) * 32];
+        }
+    }
+    __syncwarp();
+    w.bound = __reduce_max_sync(CPHB_FULL, w.valid ? (unsigned)(w.worst >> 32) : 0u);
+}
+
+template <int TOP>
+__global__ void __launch_bounds__(256) search1_kernel(IndexView ix, const float *__restrict__ qxyz,
+                                                      const uint32_t *__restrict__ perm, size_t nq, float r2,
+                                                      int32_t *__restrict__ out_idx, float *__restrict__ out_d2,
+                                                      unsigned long long *count) {
+    __shared__ __align__(16) float4 s_tile[8][CPHB_LEAF];
+    __shared__ uint64_t s_bar[8];
+    const int warp = threadIdx.x >> 5;
+    WarpSearch w;
+    warp_search_setup(w, s_tile[warp], &s_bar[warp]);
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    w.valid = i < nq;
+    size_t pos = 0;
+    w.qx = w.qy = w.qz = 0.f;
+    if (w.valid) {
+        pos = perm ? perm[i] : i;
+        w.qx = qxyz[3 * pos];
+        w.qy = qxyz[3 * pos + 1];
+        w.qz = qxyz[3 * pos + 2];
+    }
+    const unsigned long long init = (r2 > 0.f) ? init_key(r2) : 0ull;  // r2==0: d2 < 0 never holds
+    w.best = init;
+    w.bound = (unsigned)(init >> 32);
+    warp_query_box(w);
+    if (__any_sync(CPHB_FULL, w.valid)) warp_nn_search<TOP>(ix, w);
+    bool found = w.valid && w.best != init;
+    if (w.valid) {
+        out_idx[pos] = found ? (int32_t)(unsigned)(w.best & 0xffffffffull) : -1;
+        out_d2[pos] = found ? __uint_as_float((unsigned)(w.best >> 32)) : INFINITY;
+    }
+    unsigned f = __ballot_sync(CPHB_FULL, found);
+    if (count && lane_id() == 0 && f) atomicAdd(count, (unsigned long long)__popc(f));
+}
+
+template <int TOP>
+__global__ void searchk_kernel(IndexView ix, const float *__restrict__ qxyz, const uint32_t *__restrict__ perm,
+                               size_t nq, float r2, int k, int32_t *__restrict__ out_idx,
+                               float *__restrict__ out_d2, unsigned long long *count) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    const int nwarp = blockDim.x >> 5;
+    const int warp = threadIdx.x >> 5;
+    float4 *tiles = (float4 *)smem;
+    uint64_t *bars = (uint64_t *)(tiles + (size_t)nwarp * CPHB_LEAF);
+    unsigned long long *lists = (unsigned long long *)(bars + nwarp);
+    WarpSearchK w;
+    warp_search_setup(w, tiles + (size_t)warp * CPHB_LEAF, &bars[warp]);
+    w.k = k;
+    w.list = lists + (size_t)warp * k * 32 + lane_id();
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    w.valid = i < nq;
+    size_t pos = 0;
+    w.qx = w.qy = w.qz = 0.f;
+    if (w.valid) {
+        pos = perm ? perm[i] : i;
+        w.qx = qxyz[3 * pos];
+        w.qy = qxyz[3 * pos + 1];
+        w.qz = qxyz[3 * pos + 2];
+    }
+    const unsigned long long init = (r2 > 0.f) ? init_key(r2) : 0ull;  // r2==0: d2 < 0 never holds
+    for (int j = 0; j < k; ++j) w.list[j * 32] = init;
+    w.worst = init;
+    w.bound = (unsigned)(init >> 32);
+    warp_query_box(w);
+    if (__any_sync(CPHB_FULL, w.valid)) warp_nn_search<TOP>(ix, w);
+    int filled = 0;
+    if (w.valid) {
+        for (int j = 0; j < k; ++j) {
+            unsigned long long key = w.list[j * 32];
+            bool ok = key < init;
+            out_idx[pos * k + j] = ok ? (int32_t)(unsigned)(key & 0xffffffffull) : -1;
+            out_d2[pos * k + j] = ok ? __uint_as_float((unsigned)(key >> 32)) : INFINITY;
+            filled += ok;
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) filled += __shfl_xor_sync(CPHB_FULL, filled, o);
+    if (count && lane_id() == 0 && filled) atomicAdd(count, (unsigned long long)filled);
+}
+
+// ---------------------------------------------------------------------------
+// host
+// ---------------------------------------------------------------------------
+static int search_impl(const cphb_index *index, const float *query, size_t nq, float r2, int k, int32_t *idx,
+                       float *d2, int64_t *h_count, cudaStream_t s) {
+    if (!index || !query || !idx || !d2) {
+        cphb_set_error("search: null argument");
+        return CPHB_ERR_INVALID;
+    }
+    // kdtree_flann.cu:46-48,70-72: empty data / query -> -1
+    if (index->v.n == 0 || nq == 0) {
+        cphb_set_error("search: empty index or query (reference returns -1)");
+        return CPHB_ERR_INVALID;
+    }
+    if (k < 0 || k > 100) {  // NUM_MAX_NN, kdtree_search_param.h:26
+        cphb_set_error("search: k=%d outside [0,100]", k);
+        return CPHB_ERR_INVALID;
+    }
+    if (h_count) *h_count = 0;
+    if (k == 0) return CPHB_OK;
+    uint32_t *perm = nullptr;
+    unsigned long long *count = nullptr;
+    int rc;
+    if (nq > 32) {
+        rc = cphb_alloc_async((void **)&perm, sizeof(uint32_t) * nq, s);
+        if (rc) return rc;
+        rc = cphb_hilbert_order(query, nq, perm, index->bounds, 1, s);
+        if (rc) return rc;
+    }
+    if (h_count) {
+        rc = cphb_alloc_async((void **)&count, 16, s);
+        if (rc) return rc;
+        CPHB_CUDA(cudaMemsetAsync(count, 0, 8, s));
+    }
+    const int top = index->v.top;
+    if (k == 1) {
+        unsigned grid = (unsigned)((nq + 255) / 256);
+        if (top <= 3)
+            CPHB_LAUNCH(search1_kernel<3>, grid, 256, 0, s, index->v, query, perm, nq, r2, idx, d2, count);
+        else
+            CPHB_LAUNCH(search1_kernel<5>, grid, 256, 0, s, index->v, query, perm, nq, r2, idx, d2, count);
+    } else {
+        size_t per_warp = CPHB_LEAF * sizeof(float4) + sizeof(uint64_t) + (size_t)k * 32 * sizeof(unsigned long long);
+        int warps = (int)((96 * 1024) / per_warp);
+        if (warps > 8) warps = 8;
+        if (warps < 1) warps = 1;
+        size_t smem = per_warp * warps;
+        unsigned block = warps * 32;
+        unsigned grid = (unsigned)((nq + block - 1) / block);
+        if (top <= 3) {
+            CPHB_CUDA(cudaFuncSetAttribute(searchk_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+            CPHB_LAUNCH(searchk_kernel<3>, grid, block, smem, s, index->v, query, perm, nq, r2, k, idx, d2, count);
+        } else {
+            CPHB_CUDA(cudaFuncSetAttribute(searchk_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+            CPHB_LAUNCH(searchk_kernel<5>, grid, block, smem, s, index->v, query, perm, nq, r2, k, idx, d2, count);
+        }
+    }
+    CPHB_CHECK_LAUNCH();
+    cphb_free_async(perm, s);
+    if (h_count) {
+        unsigned long long h = 0;
+        CPHB_CUDA(cudaMemcpyAsync(&h, count, 8, cudaMemcpyDeviceToHost, s));
+        CPHB_CUDA(cudaStreamSynchronize(s));
+        *h_count = (int64_t)h;
+        cphb_free_async(count, s);
+    }
+    return CPHB_OK;
+}
+
+extern "C" int cphb_search_radius(const cphb_index *index, const float *query, size_t n_query, float radius,
+                                  int max_nn, int32_t *idx, float *d2, int64_t *h_count, void *stream) {
+    float r2 = radius * radius;  // kdtree_flann.inl:120 float(radius * radius); r2 == 0 matches nothing
+    return search_impl(index, query, n_query, r2, max_nn, idx, d2, h_count, (cudaStream_t)stream);
+}
+extern "C" int cphb_search_hybrid(const cphb_index *index, const float *query, size_t n_query, float radius,
+                                  int max_nn, int32_t *idx, float *d2, int64_t *h_count, void *stream) {
+    return cphb_search_radius(index, query, n_query, radius, max_nn, idx, d2, h_count, stream);
+}
+extern "C" int cphb_search_knn(const cphb_index *index, const float *query, size_t n_query, int knn, int32_t *idx,
+                               float *d2, int64_t *h_count, void *stream) {
+    return search_impl(index, query, n_query, INFINITY, knn, idx, d2, h_count, (cudaStream_t)stream);
+}

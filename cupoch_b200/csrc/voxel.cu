@@ -1,0 +1,249 @@
+// voxel.cu -- PointCloud::VoxelDownSample (down_sample.cu:170-273) as a voxel
+// hash build instead of the reference's comparison merge-sort of int3 keys
+// with zipped payloads (thrust::sort_by_key + reduce_by_key, :194-222).
+//
+//   bounds -> key = floor((p - origin)/voxel) (down_sample.cu:64-75)
+//   insert : open-addressing table of packed 64-bit keys (atomicCAS, linear
+//            probing); lanes of a warp that hold the same key elect one
+//            inserter (__match_any_sync), so coherent (scan-ordered) inputs
+//            issue one CAS per voxel per warp
+//   assign : occupied slots get dense ids
+//   accum  : per point, probe (read-only) -> id -> float64 atomic adds of
+//            xyz / normal / colour + count (order-independent to 1e-16, so the
+//            float32 result is reproducible and equals the oracle's)
+//   order  : radix sort of the (few) voxel keys restores the reference's
+//            lexicographic (x,y,z) output order (helper.h:113-121)
+//   final  : mean; normals mean-then-normalise (down_sample.cu:78-90)
+// The table is sized by min(n, #grid cells) so for dense grids it stays L2 resident.
+#include <float.h>
+#include <math.h>
+
+#include "cphb_internal.cuh"
+
+#define VX_EMPTY 0xffffffffffffffffull
+
+struct VoxelGrid {
+    float org[3];
+    float voxel;
+    int sy, sz;  // shifts: key = x << (sy) | y << sz | z  (sy = by + bz, sz = bz)
+};
+
+__device__ __forceinline__ unsigned long long voxel_key(const float *p, const VoxelGrid &g) {
+    // compute_key_functor (down_sample.cu:70-73): floor((pt - min_bound) / voxel_size) cast to int
+    long long kx = (long long)(int)floorf(__fdiv_rn(p[0] - g.org[0], g.voxel));
+    long long ky = (long long)(int)floorf(__fdiv_rn(p[1] - g.org[1], g.voxel));
+    long long kz = (long long)(int)floorf(__fdiv_rn(p[2] - g.org[2], g.voxel));
+    return ((unsigned long long)kx << g.sy) | ((unsigned long long)ky << g.sz) | (unsigned long long)kz;
+}
+__device__ __forceinline__ unsigned hash64(unsigned long long k) {
+    k ^= k >> 33;
+    k *= 0xff51afd7ed558ccdull;
+    k ^= k >> 33;
+    k *= 0xc4ceb9fe1a85ec53ull;
+    k ^= k >> 33;
+    return (unsigned)k;
+}
+
+__global__ void __launch_bounds__(256) voxel_table_init_kernel(unsigned long long *keys, size_t T, unsigned *counter) {
+    size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (i < T) keys[i] = VX_EMPTY;
+    if (i == 0) *counter = 0;
+}
+
+__global__ void __launch_bounds__(256) voxel_insert_kernel(const float *__restrict__ pts, size_t n, VoxelGrid g,
+                                                           unsigned long long *keys, unsigned mask) {
+    size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    bool valid = i < n;
+    unsigned long long key = valid ? voxel_key(pts + 3 * i, g) : VX_EMPTY;
+    // warp-cooperative dedup: one inserter per distinct key in the warp
+    unsigned peers = __match_any_sync(CPHB_FULL, key);
+    bool leader = valid && (__ffs(peers) - 1 == lane_id());
+    if (!leader) return;
+    unsigned h = hash64(key) & mask;
+    while (true) {
+        unsigned long long prev = atomicCAS(&keys[h], VX_EMPTY, key);
+        if (prev == VX_EMPTY || prev == key) break;
+        h = (h + 1) & mask;
+    }
+}
+
+__global__ void __launch_bounds__(256) voxel_assign_kernel(const unsigned long long *__restrict__ keys, size_t T,
+                                                           unsigned *ids, unsigned long long *dense_keys,
+                                                           unsigned *dense_ids, unsigned *counter) {
+    size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    bool occ = i < T && keys[i] != VX_EMPTY;
+    unsigned m = __ballot_sync(CPHB_FULL, occ);
+    unsigned base = 0;
+    if (lane_id() == 0 && m) base = atomicAdd(counter, (unsigned)__popc(m));
+    base = __shfl_sync(CPHB_FULL, base, 0);
+    if (occ) {
+        unsigned id = base + __popc(m & ((1u << lane_id()) - 1u));
+        ids[i] = id;
+        dense_keys[id] = keys[i];
+        dense_ids[id] = id;
+    }
+}
+
+__global__ void __launch_bounds__(256) voxel_zero_kernel(double *sums, unsigned *counts, size_t n_sums, size_t n_counts) {
+    size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (i < n_sums) sums[i] = 0.0;
+    if (i < n_counts) counts[i] = 0u;
+}
+
+template <int A>  // A attribute vectors per point: 1 points, 2 (+normals or colours), 3 both
+__global__ void __launch_bounds__(256) voxel_accum_kernel(const float *__restrict__ pts, const float *__restrict__ a1,
+                                                          const float *__restrict__ a2, size_t n, VoxelGrid g,
+                                                          const unsigned long long *__restrict__ keys,
+                                                          const unsigned *__restrict__ ids, unsigned mask, double *sums,
+                                                          unsigned *counts) {
+    size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float p[3] = {pts[3 * i], pts[3 * i + 1], pts[3 * i + 2]};
+    unsigned long long key = voxel_key(p, g);
+    unsigned h = hash64(key) & mask;
+    while (keys[h] != key) h = (h + 1) & mask;
+    const unsigned id = ids[h];
+    double *s = sums + (size_t)id * 3 * A;
+    atomicAdd(s + 0, (double)p[0]);
+    atomicAdd(s + 1, (double)p[1]);
+    atomicAdd(s + 2, (double)p[2]);
+    if (A >= 2) {
+        atomicAdd(s + 3, (double)a1[3 * i]);
+        atomicAdd(s + 4, (double)a1[3 * i + 1]);
+        atomicAdd(s + 5, (double)a1[3 * i + 2]);
+    }
+    if (A >= 3) {
+        atomicAdd(s + 6, (double)a2[3 * i]);
+        atomicAdd(s + 7, (double)a2[3 * i + 1]);
+        atomicAdd(s + 8, (double)a2[3 * i + 2]);
+    }
+    atomicAdd(counts + id, 1u);
+}
+
+template <int A>
+__global__ void __launch_bounds__(256) voxel_final_kernel(const unsigned *__restrict__ order, unsigned n_out,
+                                                          const double *__restrict__ sums,
+                                                          const unsigned *__restrict__ counts, int a1_is_normal,
+                                                          float *out_p, float *out_a1, float *out_a2) {
+    unsigned pos = blockIdx.x * blockDim.x + threadIdx.x;
+    if (pos >= n_out) return;
+    unsigned id = order[pos];
+    const double *s = sums + (size_t)id * 3 * A;
+    float cnt = (float)counts[id];
+    // divide_tuple_functor: x / (float)count
+    out_p[3 * pos] = __fdiv_rn((float)s[0], cnt);
+    out_p[3 * pos + 1] = __fdiv_rn((float)s[1], cnt);
+    out_p[3 * pos + 2] = __fdiv_rn((float)s[2], cnt);
+    if (A >= 2) {
+        float v[3] = {__fdiv_rn((float)s[3], cnt), __fdiv_rn((float)s[4], cnt), __fdiv_rn((float)s[5], cnt)};
+        if (a1_is_normal) {  // normalize_and_divide_tuple_functor (down_sample.cu:78-90)
+            float nn = sqrtf(dot3(v[0], v[1], v[2], v[0], v[1], v[2]));
+            if (nn > 0.f) { v[0] = __fdiv_rn(v[0], nn); v[1] = __fdiv_rn(v[1], nn); v[2] = __fdiv_rn(v[2], nn); }
+        }
+        out_a1[3 * pos] = v[0]; out_a1[3 * pos + 1] = v[1]; out_a1[3 * pos + 2] = v[2];
+    }
+    if (A >= 3) {
+        out_a2[3 * pos] = __fdiv_rn((float)s[6], cnt);
+        out_a2[3 * pos + 1] = __fdiv_rn((float)s[7], cnt);
+        out_a2[3 * pos + 2] = __fdiv_rn((float)s[8], cnt);
+    }
+}
+
+static int bits_for(double cells) {
+    int b = 1;
+    while (b < 63 && (double)(1ull << b) < cells) ++b;
+    return b;
+}
+
+extern "C" int cphb_voxel_down_sample(const float *points, const float *normals, const float *colors, size_t n,
+                                      float voxel_size, float *out_points, float *out_normals, float *out_colors,
+                                      size_t *h_n_out, void *stream) {
+    cudaStream_t s = (cudaStream_t)stream;
+    if (!h_n_out) {
+        cphb_set_error("cphb_voxel_down_sample: h_n_out is null");
+        return CPHB_ERR_INVALID;
+    }
+    *h_n_out = 0;
+    if (voxel_size <= 0.0f || n == 0) return CPHB_OK;  // down_sample.cu:173-176 (warn + empty cloud)
+    if (!points || !out_points || (normals && !out_normals) || (colors && !out_colors)) {
+        cphb_set_error("cphb_voxel_down_sample: null argument");
+        return CPHB_ERR_INVALID;
+    }
+    if (n > 0x7fffffffull) {
+        cphb_set_error("cphb_voxel_down_sample: n exceeds int32");
+        return CPHB_ERR_INVALID;
+    }
+    float mn[3], mx[3];
+    int rc = cphb_min_max_bound(points, n, mn, mx, stream);
+    if (rc) return rc;
+    VoxelGrid g;
+    g.voxel = voxel_size;
+    float ext = 0.f;
+    double cells = 1.0, dims[3];
+    for (int a = 0; a < 3; ++a) {
+        g.org[a] = mn[a] - voxel_size * 0.5f;       // :180
+        float hi = mx[a] + voxel_size * 0.5f;       // :181
+        if (hi - g.org[a] > ext) ext = hi - g.org[a];
+        dims[a] = (double)floorf((mx[a] - g.org[a]) / voxel_size) + 1.0;
+        cells *= dims[a];
+    }
+    if (voxel_size * (float)2147483647 < ext) return CPHB_OK;  // :183-187 "voxel_size is too small"
+    int bx = bits_for(dims[0]), by = bits_for(dims[1]), bz = bits_for(dims[2]);
+    if (bx + by + bz > 63) {
+        cphb_set_error("cphb_voxel_down_sample: grid %gx%gx%g needs %d key bits (> 63)", dims[0], dims[1], dims[2],
+                       bx + by + bz);
+        return CPHB_ERR_UNSUPPORTED;
+    }
+    g.sz = bz;
+    g.sy = by + bz;
+    const size_t cap = (cells < (double)n) ? (size_t)cells : n;  // max possible voxel count
+    size_t T = 1024;
+    while (T < 2 * cap) T <<= 1;
+    const unsigned mask = (unsigned)(T - 1);
+    const int A = 1 + (normals ? 1 : 0) + (colors ? 1 : 0);
+
+    size_t off = 0;
+    auto take = [&](size_t bytes) { size_t o = off; off = cphb_align(off + bytes, 256); return o; };
+    size_t o_keys = take(T * 8), o_ids = take(T * 4), o_dk = take(cap * 8), o_dk2 = take(cap * 8);
+    size_t o_di = take(cap * 4), o_ord = take(cap * 4), o_sums = take(cap * 3 * A * 8), o_cnt = take(cap * 4), o_ctr = take(16);
+    char *base = nullptr;
+    rc = cphb_alloc_async((void **)&base, off, s);
+    if (rc) return rc;
+    unsigned long long *keys = (unsigned long long *)(base + o_keys);
+    unsigned *ids = (unsigned *)(base + o_ids);
+    unsigned long long *dk = (unsigned long long *)(base + o_dk), *dk2 = (unsigned long long *)(base + o_dk2);
+    unsigned *di = (unsigned *)(base + o_di), *order = (unsigned *)(base + o_ord);
+    double *sums = (double *)(base + o_sums);
+    unsigned *counts = (unsigned *)(base + o_cnt), *counter = (unsigned *)(base + o_ctr);
+
+    CPHB_LAUNCH(voxel_table_init_kernel, (unsigned)((T + 255) / 256), 256, 0, s, keys, T, counter);
+    CPHB_LAUNCH(voxel_insert_kernel, (unsigned)((n + 255) / 256), 256, 0, s, points, n, g, keys, mask);
+    CPHB_LAUNCH(voxel_assign_kernel, (unsigned)((T + 255) / 256), 256, 0, s, keys, T, ids, dk, di, counter);
+    size_t nz = cap * 3 * A;
+    CPHB_LAUNCH(voxel_zero_kernel, (unsigned)((nz + 255) / 256), 256, 0, s, sums, counts, nz, cap);
+    const float *a1 = normals ? normals : colors, *a2 = colors;
+    unsigned gridn = (unsigned)((n + 255) / 256);
+    if (A == 1) CPHB_LAUNCH(voxel_accum_kernel<1>, gridn, 256, 0, s, points, a1, a2, n, g, keys, ids, mask, sums, counts);
+    else if (A == 2) CPHB_LAUNCH(voxel_accum_kernel<2>, gridn, 256, 0, s, points, a1, a2, n, g, keys, ids, mask, sums, counts);
+    else CPHB_LAUNCH(voxel_accum_kernel<3>, gridn, 256, 0, s, points, a1, a2, n, g, keys, ids, mask, sums, counts);
+    CPHB_CHECK_LAUNCH();
+    unsigned h_cnt = 0;
+    CPHB_CUDA(cudaMemcpyAsync(&h_cnt, counter, 4, cudaMemcpyDeviceToHost, s));
+    CPHB_CUDA(cudaStreamSynchronize(s));
+    const unsigned n_out = h_cnt;
+    rc = cphb_sort_pairs_u64((const uint64_t *)dk, (uint64_t *)dk2, di, order, n_out, bx + by + bz, s);
+    if (rc) { cphb_free_async(base, s); return rc; }
+    unsigned gridv = (n_out + 255) / 256;
+    if (n_out) {
+        if (A == 1) CPHB_LAUNCH(voxel_final_kernel<1>, gridv, 256, 0, s, order, n_out, sums, counts, 0, out_points, nullptr, nullptr);
+        else if (A == 2)
+            CPHB_LAUNCH(voxel_final_kernel<2>, gridv, 256, 0, s, order, n_out, sums, counts, normals ? 1 : 0, out_points,
+                        normals ? out_normals : out_colors, nullptr);
+        else CPHB_LAUNCH(voxel_final_kernel<3>, gridv, 256, 0, s, order, n_out, sums, counts, 1, out_points, out_normals, out_colors);
+        CPHB_CHECK_LAUNCH();
+    }
+    cphb_free_async(base, s);
+    CPHB_CUDA(cudaStreamSynchronize(s));
+    *h_n_out = n_out;
+    return CPHB_OK;
+}

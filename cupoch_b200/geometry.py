@@ -1,0 +1,218 @@
+"""cupoch.geometry mirror (hot-path subset): PointCloud, KDTreeFlann, KDTreeSearchParam*.
+
+Names, argument meaning and error behaviour follow src/python/cupoch_pybind/geometry/
+pointcloud.cpp and kdtree_flann.cpp; computation goes through the C ABI only.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from .utility import DeviceArray, Matrix3fVector, Vector3fVector, as_f16
+
+NUM_MAX_NN = 100  # kdtree_search_param.h:26
+
+
+class KDTreeSearchParam:
+    pass
+
+
+class KDTreeSearchParamKNN(KDTreeSearchParam):
+    def __init__(self, knn=30):
+        self.knn = int(knn)
+
+    def __repr__(self):
+        return "geometry::KDTreeSearchParamKNN with knn = %d" % self.knn
+
+
+class KDTreeSearchParamRadius(KDTreeSearchParam):
+    def __init__(self, radius, max_nn):
+        self.radius = float(radius)
+        self.max_nn = int(max_nn)
+
+    def __repr__(self):
+        return "geometry::KDTreeSearchParamRadius with radius = %f, max_nn = %d" % (self.radius, self.max_nn)
+
+
+class PointCloud:
+    """geometry::PointCloud (pointcloud.h:43-263): points_/normals_/colors_/covariances_ on the device."""
+
+    def __init__(self, points=None):
+        self._points = self._normals = self._colors = self._covariances = None
+        self._color_gradient = None  # PointCloudForColoredICP (colored_icp.cu:36-40)
+        if points is not None:
+            self.points = points
+
+    points = property(lambda s: s._points, lambda s, v: setattr(s, "_points", Vector3fVector(v)))
+    normals = property(lambda s: s._normals, lambda s, v: setattr(s, "_normals", Vector3fVector(v)))
+    colors = property(lambda s: s._colors, lambda s, v: setattr(s, "_colors", Vector3fVector(v)))
+    covariances = property(lambda s: s._covariances, lambda s, v: setattr(s, "_covariances", Matrix3fVector(v)))
+
+    def __len__(self):
+        return 0 if self._points is None else len(self._points)
+
+    def is_empty(self):
+        return len(self) == 0
+
+    # pointcloud.h:82-94: "non-empty and same length as points"
+    def has_points(self):
+        return len(self) > 0
+
+    def _has(self, a):
+        return len(self) > 0 and a is not None and len(a) == len(self)
+
+    def has_normals(self):
+        return self._has(self._normals)
+
+    def has_colors(self):
+        return self._has(self._colors)
+
+    def has_covariances(self):
+        return self._has(self._covariances)
+
+    def _cloud(self, with_attrs=True):
+        c = _lib.Cloud()
+        c.points = self._points.ptr if self._points is not None else None
+        c.n = len(self)
+        if with_attrs:
+            c.normals = self._normals.ptr if self.has_normals() else None
+            c.colors = self._colors.ptr if self.has_colors() else None
+            c.covariances = self._covariances.ptr if self.has_covariances() else None
+            c.color_gradient = self._color_gradient.ptr if self._has(self._color_gradient) else None
+        c.cov_col_major = 0
+        return c
+
+    # -- geometry ops ---------------------------------------------------------
+    def transform(self, transformation):
+        """PointCloud::Transform (pointcloud.cu:293-299), in place."""
+        if len(self):
+            _lib.check(_lib.lib().cphb_transform(
+                self._points.ptr, self._normals.ptr if self.has_normals() else None,
+                self._covariances.ptr if self.has_covariances() else None, 0, len(self), as_f16(transformation), None))
+        return self
+
+    def get_min_bound(self):
+        return self._bounds()[0]
+
+    def get_max_bound(self):
+        return self._bounds()[1]
+
+    def _bounds(self):
+        mn, mx = (C.c_float * 3)(), (C.c_float * 3)()
+        if len(self):
+            _lib.check(_lib.lib().cphb_min_max_bound(self._points.ptr, len(self), mn, mx, None))
+        return np.array(mn, np.float32), np.array(mx, np.float32)
+
+    def voxel_down_sample(self, voxel_size):
+        """PointCloud::VoxelDownSample (down_sample.cu:170-273)."""
+        out = PointCloud()
+        n = len(self)
+        if n == 0:
+            return out
+        hn, hc = self.has_normals(), self.has_colors()
+        op = DeviceArray((n, 3), np.float32)
+        on = DeviceArray((n, 3), np.float32) if hn else None
+        oc = DeviceArray((n, 3), np.float32) if hc else None
+        m = C.c_size_t(0)
+        _lib.check(_lib.lib().cphb_voxel_down_sample(
+            self._points.ptr, self._normals.ptr if hn else None, self._colors.ptr if hc else None, n,
+            float(voxel_size), op.ptr, on.ptr if hn else None, oc.ptr if hc else None, C.byref(m), None))
+        m = m.value
+
+        def cut(a):
+            return None if a is None else DeviceArray((m, 3), np.float32, ptr=a.ptr, base=a)
+        out._points, out._normals, out._colors = cut(op), cut(on), cut(oc)
+        return out
+
+    def estimate_normals(self, search_param=None):
+        """PointCloud::EstimateNormals (estimate_normals.cu:82-127)."""
+        search_param = search_param or KDTreeSearchParamKNN()
+        n = len(self)
+        if n == 0:
+            return True
+        out = DeviceArray((n, 3), np.float32)
+        if isinstance(search_param, KDTreeSearchParamKNN):
+            knn, radius, max_nn = search_param.knn, 0.0, 0
+        else:
+            knn, radius, max_nn = 0, search_param.radius, search_param.max_nn
+        _lib.check(_lib.lib().cphb_estimate_normals(self._points.ptr, n, knn, radius, max_nn, out.ptr, None))
+        self._normals = out
+        return True
+
+
+class KDTreeFlann:
+    """knn::KDTreeFlann (kdtree_flann.h:43-124), exposed as cupoch.geometry.KDTreeFlann
+    (kdtree_flann.cpp:93-95)."""
+
+    def __init__(self, geometry=None):
+        self._h = None
+        self._n = 0
+        if geometry is not None:
+            self.set_geometry(geometry)
+
+    def set_geometry(self, geometry):
+        pts = geometry.points if isinstance(geometry, PointCloud) else Vector3fVector(geometry)
+        self._release()
+        n = 0 if pts is None else len(pts)
+        h = C.c_void_p()
+        _lib.require_gpu()
+        _lib.check(_lib.lib().cphb_index_create(pts.ptr if n else None, n, None, C.byref(h)))
+        self._h, self._n = h, n
+        return True
+
+    def _release(self):
+        if self._h:
+            _lib.lib().cphb_stream_synchronize(None)
+            _lib.lib().cphb_index_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self._release()
+        except Exception:
+            pass
+
+    # -- batch (device) API: KDTreeFlann::SearchKNN / SearchRadius on device vectors --------------
+    def search_knn(self, query, knn):
+        return self._search(query, knn, None)
+
+    def search_radius(self, query, radius, max_nn):
+        return self._search(query, max_nn, radius)
+
+    search_hybrid = search_radius  # north_star's name
+
+    def _search(self, query, k, radius):
+        q = Vector3fVector(query)
+        nq = 0 if q is None else len(q)
+        if self._h is None or self._n == 0 or nq == 0 or k < 0 or (radius is None and k > NUM_MAX_NN):
+            return -1, None, None  # kdtree_flann.cu:46-48,70-72
+        idx = DeviceArray((nq, max(k, 1)), np.int32)
+        d2 = DeviceArray((nq, max(k, 1)), np.float32)
+        cnt = C.c_int64(0)
+        L = _lib.lib()
+        if radius is None:
+            rc = L.cphb_search_knn(self._h, q.ptr, nq, k, idx.ptr, d2.ptr, C.byref(cnt), None)
+        else:
+            rc = L.cphb_search_radius(self._h, q.ptr, nq, float(radius), k, idx.ptr, d2.ptr, C.byref(cnt), None)
+        if rc == -1:  # CPHB_ERR_INVALID == the reference's -1
+            return -1, None, None
+        _lib.check(rc)
+        return int(cnt.value), idx, d2
+
+    # -- single host query API (kdtree_flann.cpp:103-143) ---------------------------------------
+    def search_vector_3f(self, query, search_param):
+        if isinstance(search_param, KDTreeSearchParamKNN):
+            return self.search_knn_vector_3f(query, search_param.knn)
+        return self.search_radius_vector_3f(query, search_param.radius, search_param.max_nn)
+
+    def search_knn_vector_3f(self, query, knn):
+        k, idx, d2 = self.search_knn(np.asarray(query, np.float32).reshape(1, 3), knn)
+        if k < 0:
+            raise RuntimeError("search_knn_vector_3f() error!")
+        return k, idx.cpu().reshape(-1), d2.cpu().reshape(-1)
+
+    def search_radius_vector_3f(self, query, radius, max_nn):
+        k, idx, d2 = self.search_radius(np.asarray(query, np.float32).reshape(1, 3), radius, max_nn)
+        if k < 0:
+            raise RuntimeError("search_radius_vector_3f() error!")
+        return k, idx.cpu().reshape(-1), d2.cpu().reshape(-1)

@@ -1,0 +1,240 @@
+"""cupoch.registration mirror (ICP subset): registration_icp / registration_generalized_icp /
+registration_colored_icp, ICPConvergenceCriteria, TransformationEstimation*, RegistrationResult.
+Signatures follow src/python/cupoch_pybind/registration/registration.cpp:62-478.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from .geometry import KDTreeSearchParamKNN, PointCloud
+from .utility import DeviceArray, as_f16
+
+
+class ICPConvergenceCriteria:  # registration.h:35-49
+    def __init__(self, relative_fitness=1e-6, relative_rmse=1e-6, max_iteration=30):
+        self.relative_fitness = float(relative_fitness)
+        self.relative_rmse = float(relative_rmse)
+        self.max_iteration = int(max_iteration)
+
+    def __repr__(self):
+        return ("registration::ICPConvergenceCriteria class with relative_fitness=%e, relative_rmse=%e, "
+                "and max_iteration=%d" % (self.relative_fitness, self.relative_rmse, self.max_iteration))
+
+
+class TransformationEstimation:  # transformation_estimation.h:49-77
+    _type = _lib.EST_UNSPECIFIED
+
+    def get_transformation_estimation_type(self):
+        return self._type
+
+
+class TransformationEstimationPointToPoint(TransformationEstimation):
+    _type = _lib.EST_POINT_TO_POINT
+
+    def __repr__(self):
+        return "TransformationEstimationPointToPoint"
+
+
+class TransformationEstimationPointToPlane(TransformationEstimation):
+    _type = _lib.EST_POINT_TO_PLANE
+
+    def __init__(self, det_thresh=1e-6):
+        self.det_thresh = float(det_thresh)
+
+    def __repr__(self):
+        return "TransformationEstimationPointToPlane"
+
+
+class TransformationEstimationSymmetricMethod(TransformationEstimation):
+    _type = _lib.EST_SYMMETRIC
+
+    def __init__(self, det_thresh=1e-6):
+        self.det_thresh = float(det_thresh)
+
+    def __repr__(self):
+        return "TransformationEstimationSymmetricMethod"
+
+
+class TransformationEstimationForGeneralizedICP(TransformationEstimation):  # generalized_icp.h:14-52
+    _type = _lib.EST_GENERALIZED_ICP
+
+    def __init__(self, epsilon=1e-3):
+        self.epsilon = float(epsilon)
+
+    def __repr__(self):
+        return "TransformationEstimationForGeneralizedICP with epsilon=%g" % self.epsilon
+
+
+class TransformationEstimationForColoredICP(TransformationEstimation):  # colored_icp.cu:42-71
+    _type = _lib.EST_COLORED_ICP
+
+    def __init__(self, lambda_geometric=0.968, det_thresh=1e-6):
+        if lambda_geometric < 0 or lambda_geometric > 1.0:
+            lambda_geometric = 0.968
+        self.lambda_geometric = float(lambda_geometric)
+        self.det_thresh = float(det_thresh)
+
+
+class RegistrationResult:  # registration.h:51-67
+    def __init__(self, transformation=None):
+        self.transformation = np.eye(4, dtype=np.float32) if transformation is None else np.asarray(transformation, np.float32)
+        self.correspondence_set = np.zeros((0, 2), np.int32)
+        self.inlier_rmse = 0.0
+        self.fitness = 0.0
+        self.iterations = 0
+        self.converged = False
+
+    def __repr__(self):
+        return ("registration::RegistrationResult with fitness=%f, inlier_rmse=%f, and correspondence_set size of %d"
+                % (self.fitness, self.inlier_rmse, len(self.correspondence_set)))
+
+
+def _params(estimation, max_distance, criteria):
+    p = _lib.IcpParams()
+    p.estimation = estimation.get_transformation_estimation_type()
+    p.max_correspondence_distance = float(max_distance)
+    p.relative_fitness = criteria.relative_fitness
+    p.relative_rmse = criteria.relative_rmse
+    p.max_iteration = criteria.max_iteration
+    p.det_thresh = getattr(estimation, "det_thresh", -1.0)
+    p.lambda_geometric = getattr(estimation, "lambda_geometric", 0.968)
+    p.flags = 0
+    return p
+
+
+def _result(res, corr, want_corr):
+    out = RegistrationResult(np.array(res.transformation, np.float32).reshape(4, 4))
+    out.fitness = float(res.fitness)
+    out.inlier_rmse = float(res.inlier_rmse)
+    out.iterations = int(res.iterations)
+    out.converged = bool(res.converged)
+    out.loop_ms = float(res.loop_ms)
+    out.loop_launches = int(res.loop_launches)
+    if want_corr:
+        nc = int(res.n_correspondences)
+        out.correspondence_set = corr.cpu()[:nc].copy() if nc else np.zeros((0, 2), np.int32)
+    return out
+
+
+def registration_icp(source, target, max_correspondence_distance, init=None,
+                     estimation_method=None, criteria=None, nccl_comm=None, return_correspondences=True):
+    """registration::RegistrationICP (registration.cu:121-173)."""
+    estimation_method = estimation_method or TransformationEstimationPointToPoint()
+    criteria = criteria or ICPConvergenceCriteria()
+    init = np.eye(4, dtype=np.float32) if init is None else init
+    if max_correspondence_distance <= 0.0:
+        pass  # registration.cu:130-132 only logs; the search then yields no correspondences
+    if estimation_method.get_transformation_estimation_type() == _lib.EST_UNSPECIFIED:
+        raise NotImplementedError("user-defined TransformationEstimation: use the generic loop in the C++ facade")
+    _lib.require_gpu()
+    sc, tc = source._cloud(), target._cloud()
+    p = _params(estimation_method, max_correspondence_distance, criteria)
+    res = _lib.IcpResult()
+    corr = DeviceArray((max(len(source), 1), 2), np.int32) if return_correspondences else None
+    _lib.check(_lib.lib().cphb_registration_icp(C.byref(sc), C.byref(tc), as_f16(init), C.byref(p), nccl_comm,
+                                                C.byref(res), corr.ptr if corr else None, None))
+    return _result(res, corr, return_correspondences)
+
+
+def evaluate_registration(source, target, max_correspondence_distance, transformation=None):
+    """registration::EvaluateRegistration (registration.cu:106-119)."""
+    T = np.eye(4, dtype=np.float32) if transformation is None else transformation
+    _lib.require_gpu()
+    sc, tc = source._cloud(False), target._cloud(False)
+    res = _lib.IcpResult()
+    corr = DeviceArray((max(len(source), 1), 2), np.int32)
+    _lib.check(_lib.lib().cphb_evaluate_registration(C.byref(sc), C.byref(tc), float(max_correspondence_distance),
+                                                     as_f16(T), C.byref(res), corr.ptr, None))
+    return _result(res, corr, True)
+
+
+def _with_covariances(pcd, epsilon):
+    """InitializePointCloudForGeneralizedICP (generalized_icp.cu:37-61)."""
+    if pcd.has_covariances():
+        return pcd
+    out = PointCloud()
+    out._points, out._normals, out._colors = pcd._points, pcd._normals, pcd._colors
+    if not out.has_normals():
+        out.estimate_normals(KDTreeSearchParamKNN(20))
+    n = len(out)
+    cov = DeviceArray((n, 3, 3), np.float32)
+    if n:
+        _lib.check(_lib.lib().cphb_covariances_from_normals(out._normals.ptr, n, float(epsilon), cov.ptr, 0, None))
+    out._covariances = cov
+    return out
+
+
+def registration_generalized_icp(source, target, max_correspondence_distance, init=None, estimation=None,
+                                 criteria=None, nccl_comm=None, return_correspondences=True):
+    """registration::RegistrationGeneralizedICP (generalized_icp.cu:185-198)."""
+    estimation = estimation or TransformationEstimationForGeneralizedICP()
+    return registration_icp(_with_covariances(source, estimation.epsilon), _with_covariances(target, estimation.epsilon),
+                            max_correspondence_distance, init, estimation, criteria, nccl_comm, return_correspondences)
+
+
+def initialize_pointcloud_for_colored_icp(target, radius, max_nn=30):
+    """InitializePointCloudForColoredICP (colored_icp.cu:120-148)."""
+    out = PointCloud()
+    out._points, out._normals, out._colors = target._points, target._normals, target._colors
+    n = len(out)
+    grad = DeviceArray((n, 3), np.float32)
+    if n:
+        if not (out.has_normals() and out.has_colors()):
+            _lib.check(_lib.lib().cphb_memset(grad.ptr, 0, grad.nbytes, None))
+        else:
+            _lib.check(_lib.lib().cphb_color_gradient(out._points.ptr, out._normals.ptr, out._colors.ptr, n,
+                                                      float(radius), int(max_nn), grad.ptr, None))
+    out._color_gradient = grad
+    return out
+
+
+def registration_colored_icp(source, target, max_correspondence_distance, init=None, criteria=None,
+                             lambda_geometric=0.968, det_thresh=1e-6, nccl_comm=None, return_correspondences=True):
+    """registration::RegistrationColoredICP (colored_icp.cu:329-342)."""
+    target_c = initialize_pointcloud_for_colored_icp(target, max_correspondence_distance * 2.0, 30)
+    return registration_icp(source, target_c, max_correspondence_distance, init,
+                            TransformationEstimationForColoredICP(lambda_geometric, det_thresh), criteria, nccl_comm,
+                            return_correspondences)
+
+
+class IcpContext:
+    """Reusable RegistrationICP state (index + Hilbert-ordered source), for repeated runs and
+    the per-step test hook.  Thin wrapper over cphb_icp_create / _run / _step."""
+
+    def __init__(self, source, target, max_correspondence_distance, estimation_method=None, criteria=None):
+        _lib.require_gpu()
+        self.source, self.target = source, target  # keep device buffers alive
+        estimation_method = estimation_method or TransformationEstimationPointToPoint()
+        criteria = criteria or ICPConvergenceCriteria()
+        self._p = _params(estimation_method, max_correspondence_distance, criteria)
+        sc, tc = source._cloud(), target._cloud()
+        self._h = C.c_void_p()
+        _lib.check(_lib.lib().cphb_icp_create(C.byref(sc), C.byref(tc), C.byref(self._p), None, C.byref(self._h)))
+        self._corr = DeviceArray((max(len(source), 1), 2), np.int32)
+        self._ci = DeviceArray((max(len(source), 1),), np.int32)
+
+    def run(self, init=None, nccl_comm=None, return_correspondences=True):
+        init = np.eye(4, dtype=np.float32) if init is None else init
+        res = _lib.IcpResult()
+        _lib.check(_lib.lib().cphb_icp_run(self._h, as_f16(init), nccl_comm, C.byref(res),
+                                           self._corr.ptr if return_correspondences else None, None))
+        return _result(res, self._corr, return_correspondences)
+
+    def step(self, T):
+        """-> (sums[32] float64, corr_index[n] int32) at pose T applied to the pristine source."""
+        sums = (C.c_double * 32)()
+        _lib.check(_lib.lib().cphb_icp_step(self._h, as_f16(T), sums, self._ci.ptr, None))
+        return np.array(sums, np.float64), self._ci.cpu()[:len(self.source)]
+
+    def close(self):
+        if self._h:
+            _lib.lib().cphb_stream_synchronize(None)
+            _lib.lib().cphb_icp_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -1,0 +1,103 @@
+"""Device containers mirroring cupoch's utility vectors (device_vector_wrapper.h:34-58):
+Vector3fVector(numpy) uploads; .cpu() downloads.  Also borrows torch CUDA tensors /
+anything with __cuda_array_interface__ without copying (the reference does this through
+DLPack, utility/dl_converter.h:32-40)."""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+
+
+class DeviceArray:
+    """A typed, shaped view of device memory.  Owns it unless it borrows from `base`."""
+
+    def __init__(self, shape, dtype, ptr=None, base=None):
+        self.shape = tuple(int(s) for s in shape)
+        self.dtype = np.dtype(dtype)
+        self.nbytes = int(np.prod(self.shape, dtype=np.int64)) * self.dtype.itemsize
+        self._base = base
+        if ptr is None:
+            _lib.require_gpu()
+            ptr = _lib.lib().cphb_malloc(max(self.nbytes, 16))
+            if not ptr:
+                _lib.check(-2)
+            self._owned = True
+        else:
+            self._owned = False
+        self.ptr = int(ptr)
+
+    # -- construction ------------------------------------------------------
+    @classmethod
+    def from_numpy(cls, a, dtype=np.float32):
+        a = np.ascontiguousarray(a, dtype=dtype)
+        d = cls(a.shape, dtype)
+        if a.nbytes:
+            _lib.check(_lib.lib().cphb_memcpy_h2d(d.ptr, a.ctypes.data, a.nbytes, None))
+            _lib.check(_lib.lib().cphb_stream_synchronize(None))
+        return d
+
+    @classmethod
+    def borrow(cls, obj):
+        """Zero-copy view of a torch CUDA tensor / CuPy array (must be contiguous)."""
+        if hasattr(obj, "data_ptr") and hasattr(obj, "is_cuda"):
+            if not obj.is_cuda or not obj.is_contiguous():
+                raise ValueError("need a contiguous CUDA tensor")
+            dt = {"torch.float32": np.float32, "torch.int32": np.int32, "torch.float64": np.float64}[str(obj.dtype)]
+            return cls(tuple(obj.shape), dt, ptr=obj.data_ptr(), base=obj)
+        cai = obj.__cuda_array_interface__
+        return cls(cai["shape"], np.dtype(cai["typestr"]), ptr=cai["data"][0], base=obj)
+
+    @classmethod
+    def wrap(cls, obj, dtype=np.float32):
+        if obj is None or isinstance(obj, DeviceArray):
+            return obj
+        if hasattr(obj, "is_cuda") and obj.is_cuda:
+            return cls.borrow(obj)
+        if hasattr(obj, "__cuda_array_interface__"):
+            return cls.borrow(obj)
+        if hasattr(obj, "numpy") and not isinstance(obj, np.ndarray):
+            obj = obj.numpy()
+        return cls.from_numpy(np.asarray(obj), dtype)
+
+    # -- access --------------------------------------------------------------
+    def cpu(self):
+        out = np.empty(self.shape, self.dtype)
+        if self.nbytes:
+            _lib.check(_lib.lib().cphb_memcpy_d2h(out.ctypes.data, self.ptr, self.nbytes, None))
+            _lib.check(_lib.lib().cphb_stream_synchronize(None))
+        return out
+
+    def __len__(self):
+        return self.shape[0] if self.shape else 0
+
+    def __del__(self):
+        if getattr(self, "_owned", False) and self.ptr:
+            try:
+                _lib.lib().cphb_free(self.ptr)
+            except Exception:
+                pass
+            self.ptr = 0
+
+
+def Vector3fVector(a=None):
+    if a is None:
+        return None
+    d = DeviceArray.wrap(a, np.float32)
+    if len(d.shape) != 2 or d.shape[1] != 3:
+        raise ValueError("expected (n,3) float32")
+    return d
+
+
+def Matrix3fVector(a=None):
+    if a is None:
+        return None
+    d = DeviceArray.wrap(a, np.float32)
+    if d.shape[1:] not in ((3, 3), (9,)):
+        raise ValueError("expected (n,3,3) float32")
+    return d
+
+
+def as_f16(T):
+    T = np.ascontiguousarray(np.asarray(T, dtype=np.float32).reshape(4, 4))
+    return (C.c_float * 16)(*T.reshape(16).tolist())

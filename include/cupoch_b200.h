@@ -1,0 +1,237 @@
+/*
+ * cupoch_b200.h -- C ABI of the B200-native ICP / kNN / voxel-grid engine.
+ *
+ * This is the drop-in boundary for cupoch's hot path.
+ * cupoch has no FFI/plugin registry: its boundary is the public C++ headers
+ * (and the pybind11 module built on them).  Each entry point below names the
+ * reference interface it replaces; include/cupoch/ holds the header-compatible
+ * C++ facade that forwards to these symbols, cupoch_b200/ the Python mirror,
+ * and INTEGRATION.md the binding a cupoch maintainer would add.
+ *
+ * Conventions
+ *   - extern "C", plain pointers + sizes, no torch / thrust / Eigen types.
+ *   - all data pointers are DEVICE pointers unless the name starts with h_;
+ *     they are borrowed for the duration of the call (never retained, except
+ *     cphb_icp_create which documents it), outputs are caller-allocated.
+ *   - points / normals / colors: packed float32 xyz, 12-byte stride (the
+ *     layout of cupoch's device_vector<Eigen::Vector3f>, pointcloud.h:259-262).
+ *   - covariances: 9 float32 per point; cov_col_major=1 for Eigen's default
+ *     column-major Matrix3f (pointcloud.h:262), 0 for row-major (numpy).
+ *   - 4x4 transforms: float32[16], ROW-major.  (Eigen::Matrix4f is column-major:
+ *     the facade transposes 16 floats on the host.)
+ *   - sizes are 64-bit; indices are int32 like the reference.
+ *   - return value: 0 = CPHB_OK, <0 = error (message via cphb_last_error()).
+ *     Nothing here calls exit() (the reference's cudaSafeCall does,
+ *     platform.cu:60-67).
+ *   - stream: a cudaStream_t passed as void* (NULL = default stream).  Calls
+ *     are asynchronous on that stream unless they return host values, in which
+ *     case they synchronise the stream before returning (documented per call).
+ */
+#ifndef CUPOCH_B200_H
+#define CUPOCH_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CPHB_VERSION 100 /* 0.1.0 */
+
+enum cphb_status {
+    CPHB_OK = 0,
+    CPHB_ERR_INVALID = -1,  /* bad argument (the reference logs and continues / returns -1) */
+    CPHB_ERR_CUDA = -2,     /* CUDA runtime error */
+    CPHB_ERR_NO_DEVICE = -3,
+    CPHB_ERR_NCCL = -4,
+    CPHB_ERR_UNSUPPORTED = -5
+};
+
+/* registration::TransformationEstimationType, transformation_estimation.h:40-47 */
+enum cphb_estimation {
+    CPHB_EST_UNSPECIFIED = 0,
+    CPHB_EST_POINT_TO_POINT = 1,
+    CPHB_EST_POINT_TO_PLANE = 2,
+    CPHB_EST_SYMMETRIC = 3,
+    CPHB_EST_COLORED_ICP = 4,
+    CPHB_EST_GENERALIZED_ICP = 5
+};
+
+int cphb_version(void);
+const char *cphb_last_error(void);
+/* number of kernels launched by this library since load (bench.py's gpu_launches) */
+uint64_t cphb_launch_count(void);
+/* cudaGetDeviceCount / properties without torch */
+int cphb_device_count(void);
+int cphb_set_device(int device);
+
+/* ------------------------------------------------------------------------ *
+ * Spatial index  (replaces knn::KDTreeFlann + the vendored FLANN CUDA kd-tree,
+ * kdtree_flann.h:43-124, kdtree_flann.inl:125-144, kdtree_cuda_builder.h)
+ * ------------------------------------------------------------------------ */
+typedef struct cphb_index cphb_index;
+
+/* KDTreeFlann::SetRawData (kdtree_flann.inl:125-144).  Like the reference the
+ * index owns a private re-packed copy of the points: xyz may be freed after
+ * the call returns (the call is stream-ordered; no host sync). n may be 0. */
+int cphb_index_create(const float *xyz, size_t n, void *stream, cphb_index **out);
+void cphb_index_destroy(cphb_index *index);
+size_t cphb_index_size(const cphb_index *index);
+
+/* KDTreeFlann::SearchRadius(query, radius, max_nn, indices, distance2)
+ * (kdtree_flann.h:66-72, .inl:97-122; result set result_set.h:372-474):
+ * for each query the <= max_nn nearest points with d2 < radius*radius (strict,
+ * radius squared in float), ascending by (d2, index).  idx / d2 are
+ * [n_query * max_nn]; unfilled slots idx=-1, d2=+inf.  1 <= max_nn <= 100
+ * (NUM_MAX_NN, kdtree_search_param.h:26) else CPHB_ERR_INVALID (reference: -1).
+ * h_count (optional, host): number of filled slots = the reference's return
+ * value; requesting it synchronises the stream. */
+int cphb_search_radius(const cphb_index *index, const float *query, size_t n_query,
+                       float radius, int max_nn, int32_t *idx, float *d2,
+                       int64_t *h_count, void *stream);
+/* KDTreeFlann::SearchKNN (kdtree_flann.h:60-65, .inl:70-95). */
+int cphb_search_knn(const cphb_index *index, const float *query, size_t n_query,
+                    int knn, int32_t *idx, float *d2, int64_t *h_count, void *stream);
+/* north_star's name for the same operation. */
+int cphb_search_hybrid(const cphb_index *index, const float *query, size_t n_query,
+                       float radius, int max_nn, int32_t *idx, float *d2,
+                       int64_t *h_count, void *stream);
+
+/* ------------------------------------------------------------------------ *
+ * geometry::PointCloud operations (pointcloud.h)
+ * ------------------------------------------------------------------------ */
+typedef struct cphb_cloud {
+    const float *points;         /* n x 3 */
+    const float *normals;        /* n x 3 or NULL  (HasNormals, pointcloud.h:82-94) */
+    const float *colors;         /* n x 3 or NULL */
+    const float *covariances;    /* n x 9 or NULL */
+    const float *color_gradient; /* n x 3 or NULL (PointCloudForColoredICP, colored_icp.cu:36-40) */
+    size_t n;
+    int cov_col_major;
+} cphb_cloud;
+
+/* PointCloud::Transform (pointcloud.cu:293-299): in place p<-Rp+t, n<-Rn,
+ * C<-R C R^T; any of normals/covariances may be NULL. */
+int cphb_transform(float *points, float *normals, float *covariances, int cov_col_major,
+                   size_t n, const float h_T[16], void *stream);
+/* PointCloud::GetMinBound / GetMaxBound (eigen.inl:197-221). Synchronises. */
+int cphb_min_max_bound(const float *points, size_t n, float h_min[3], float h_max[3], void *stream);
+
+/* PointCloud::VoxelDownSample (down_sample.cu:170-273).  normals / colors in
+ * and out may be NULL (together).  out_* must hold n elements; *h_n_out gets
+ * the voxel count (synchronises).  Output order: lexicographic by voxel
+ * (x,y,z) like the reference's sort.  voxel<=0 or voxel*INT_MAX < extent
+ * return CPHB_OK with *h_n_out = 0 (the reference warns and returns an empty
+ * cloud). */
+int cphb_voxel_down_sample(const float *points, const float *normals, const float *colors,
+                           size_t n, float voxel_size, float *out_points, float *out_normals,
+                           float *out_colors, size_t *h_n_out, void *stream);
+
+/* PointCloud::EstimateNormals (estimate_normals.cu:82-127).  knn>0: KNN search
+ * (k includes the point itself, default 30); knn<=0: radius + max_nn. */
+int cphb_estimate_normals(const float *points, size_t n, int knn, float radius, int max_nn,
+                          float *out_normals, void *stream);
+/* InitializePointCloudForGeneralizedICP covariance step (generalized_icp.cu:53-60). */
+int cphb_covariances_from_normals(const float *normals, size_t n, float epsilon,
+                                  float *out_cov, int cov_col_major, void *stream);
+/* InitializePointCloudForColoredICP (colored_icp.cu:120-148): radius search
+ * (radius, max_nn) + per-point intensity-gradient fit. */
+int cphb_color_gradient(const float *points, const float *normals, const float *colors, size_t n,
+                        float radius, int max_nn, float *out_gradient, void *stream);
+
+/* ------------------------------------------------------------------------ *
+ * registration  (registration.h:35-91, transformation_estimation.h:36-143,
+ * generalized_icp.h, colored_icp.h)
+ * ------------------------------------------------------------------------ */
+typedef struct cphb_icp_params {
+    int estimation;               /* enum cphb_estimation */
+    float max_correspondence_distance;
+    float relative_fitness;       /* ICPConvergenceCriteria, registration.h:35-49 */
+    float relative_rmse;
+    int max_iteration;
+    float det_thresh;             /* PointToPlane / Symmetric / Colored: 1e-6; ignored for GICP */
+    float lambda_geometric;       /* Colored ICP, default 0.968 */
+    int flags;                    /* CPHB_ICP_* */
+} cphb_icp_params;
+
+#define CPHB_ICP_CUMULATIVE_TRANSFORM 1 /* "fast" mode: apply the cumulative T to the pristine source
+                                           instead of transforming the working copy in place each
+                                           iteration (registration.cu:160).  Not bit-compatible. */
+
+typedef struct cphb_icp_result {
+    float transformation[16];     /* row-major */
+    float fitness;
+    float inlier_rmse;
+    int64_t n_correspondences;
+    int iterations;               /* updates applied */
+    int converged;
+    float loop_ms;                /* device time of the launch loop (CUDA events on `stream`) */
+    int loop_launches;            /* kernels launched inside that region */
+} cphb_icp_result;
+
+typedef struct cphb_icp cphb_icp;
+
+/* Build the per-call state of RegistrationICP (registration.cu:146-147): the
+ * spatial index over target.points and a Hilbert-ordered working copy of the
+ * source.  The target attribute pointers (normals, colors, gradient,
+ * covariances) are RETAINED until cphb_icp_destroy; points are copied. */
+int cphb_icp_create(const cphb_cloud *source, const cphb_cloud *target,
+                    const cphb_icp_params *params, void *stream, cphb_icp **out);
+void cphb_icp_destroy(cphb_icp *icp);
+
+/* Run the loop of RegistrationICP (registration.cu:148-172) from init.  One
+ * fused kernel per iteration, no host round trip inside the loop.
+ * nccl_comm: NULL (single GPU) or an ncclComm_t whose ranks each hold a
+ * contiguous shard of the source; the 32 partial sums are all-reduced once
+ * per iteration.  corr_out (device, optional): 2*source.n int32 receiving the
+ * final correspondence set (i, j) ascending in i (local shard indices).
+ * Synchronises the stream before returning h_result. */
+int cphb_icp_run(cphb_icp *icp, const float h_init[16], void *nccl_comm,
+                 cphb_icp_result *h_result, int32_t *corr_out, void *stream);
+
+/* Debug / test hook: one GetRegistrationResultAndCorrespondences +
+ * ComputeJTJandJTr step at pose h_T applied to the pristine source:
+ * h_sums[32] doubles = 21 JTJ upper | 6 JTr | sum r^2 | sum d^2 | count | 0 0
+ * (P2P: sum s(3) sum t(3) sum s t^T(9) ... | sum d^2 | count); corr_index
+ * (device, optional, source.n int32): matched target index per source point
+ * or -1.  Synchronises. */
+int cphb_icp_step(cphb_icp *icp, const float h_T[16], double h_sums[32],
+                  int32_t *corr_index, void *stream);
+
+/* One-shot registration::RegistrationICP / RegistrationGeneralizedICP /
+ * RegistrationColoredICP on device-resident clouds.  For GICP the clouds must
+ * carry covariances, for Colored ICP the target must carry color_gradient
+ * (use cphb_covariances_from_normals / cphb_color_gradient, as the reference's
+ * Initialize* helpers do). */
+int cphb_registration_icp(const cphb_cloud *source, const cphb_cloud *target,
+                          const float h_init[16], const cphb_icp_params *params,
+                          void *nccl_comm, cphb_icp_result *h_result, int32_t *corr_out,
+                          void *stream);
+
+/* registration::EvaluateRegistration (registration.cu:106-119). */
+int cphb_evaluate_registration(const cphb_cloud *source, const cphb_cloud *target,
+                               float max_correspondence_distance, const float h_T[16],
+                               cphb_icp_result *h_result, int32_t *corr_out, void *stream);
+
+/* ------------------------------------------------------------------------ *
+ * Host-buffer convenience used by bench.py's e2e leg and the Python mirror:
+ * thin wrappers that cudaMalloc/cudaMemcpyAsync around the calls above.
+ * ------------------------------------------------------------------------ */
+void *cphb_malloc(size_t bytes);              /* cudaMalloc, NULL on failure */
+void cphb_free(void *p);
+void *cphb_malloc_host(size_t bytes);         /* pinned */
+void cphb_free_host(void *p);
+int cphb_memcpy_h2d(void *dst, const void *src, size_t bytes, void *stream);
+int cphb_memcpy_d2h(void *dst, const void *src, size_t bytes, void *stream);
+int cphb_memset(void *dst, int value, size_t bytes, void *stream);
+int cphb_stream_synchronize(void *stream);
+/* NCCL bootstrap without torch types: unique id is 128 bytes. */
+int cphb_nccl_unique_id(char h_id[128]);
+int cphb_nccl_comm_init(const char h_id[128], int world_size, int rank, void **out_comm);
+int cphb_nccl_comm_destroy(void *comm);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CUPOCH_B200_H */
