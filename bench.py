@@ -1,0 +1,309 @@
+#!/usr/bin/env python3
+"""bench.py -- headline benchmark of the ICP hot path (BASELINE.json config 2).
+
+Workload: point-to-plane ICP, 1M -> 1M synthetic points + analytic
+normals (surface z = 0.1 sin 4pi x cos 4pi y), max_correspondence_distance 0.02,
+ICPConvergenceCriteria(0, 0, 30): exactly 30 updates / 31 searches per registration.
+
+  step            = one RegistrationICP call (index build + source ordering + 31 fused launches)
+  value           = ICP iterations / s, clouds resident in HBM when the timed region starts
+  e2e.value       = the same through the public API with HOST (pinned) buffers: H2D of both clouds
+                    and D2H of the result inside the timed region
+  roofline        = algorithmic bytes of the fused iteration kernel (36 B / source point,
+                    SURVEY.md 8d) / its mean device time (CUDA events around the launch loop)
+  cpu_baseline    = the CPU oracle port (kd-tree + OpenMP, all host cores) on the same workload
+  --impl reference= that CPU implementation timed as its own arm
+
+N > 1 (torchrun): the source is split into contiguous blocks, one per rank, the target and its
+index are replicated, and the 32 partial sums are all-reduced (NCCL) once per iteration: strong
+scaling of the same 1M -> 1M problem.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+ALG_BYTES_PER_POINT = 36  # src xyz 12 + matched target xyz 12 + matched normal 12
+MAX_DIST = 0.02
+ITERS = 30
+
+
+def peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler(threading.Thread):
+    def __init__(self, index=0):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.reasons, self.stop_flag = index, [], set(), False
+        self.maxclk = None
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q,
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                f = [x.strip() for x in out.strip().split(",")]
+                self.samples.append(float(f[0]))
+                self.maxclk = float(f[1])
+                for nme, v in zip(names, f[2:]):
+                    if v.lower().startswith("active"):
+                        self.reasons.add(nme)
+            except Exception:
+                pass
+            time.sleep(0.2)
+
+    def summary(self):
+        s = sorted(self.samples)
+        return {"sm_mhz": s[len(s) // 2] if s else None, "sm_max_mhz": self.maxclk, "reasons": sorted(self.reasons),
+                "samples": len(s)}
+
+
+def make_workload(n):
+    from cupoch_b200.testing import datagen
+    tgt, tn = datagen.surface(n, 11)
+    src = datagen.make_source(tgt, datagen.gt_transform(), 13, 14, 5e-4)
+    return src, tgt, tn
+
+
+def run_reference(args, rank):
+    """CPU arm: the oracle port of cupoch's RegistrationICP (kd-tree + OpenMP) on the host cores."""
+    if rank != 0:
+        return
+    from oracle import oracle_py as orc
+    src, tgt, tn = make_workload(args.points)
+    def step():
+        return orc.registration_icp(orc.P2PLANE, src, tgt, MAX_DIST, tgt_nrm=tn, relative_fitness=0,
+                                    relative_rmse=0, max_iteration=ITERS)
+    for _ in range(args.warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        r = step()
+    dt = time.perf_counter() - t0
+    v = ITERS * args.steps / dt
+    print(json.dumps({
+        "impl": "reference", "metric": "icp_iterations_per_sec", "value": v, "unit": "iter/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "config2: point-to-plane ICP 1M->1M, 30 iters, r=0.02", "points": args.points,
+                   "iterations": ITERS},
+        "cpu_baseline": {"value": v, "unit": "iter/s", "cores": orc.num_threads(), "kind": "port",
+                         "sample": "full workload: %d registrations x %d iterations, kd-tree build included" % (args.steps, ITERS)},
+        "e2e": {"value": v, "unit": "iter/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "final_fitness": r["fitness"], "final_rmse": r["inlier_rmse"],
+    }))
+
+
+def pinned_array(L, shape):
+    nbytes = int(np.prod(shape)) * 4
+    p = L.cphb_malloc_host(nbytes)
+    buf = (C.c_float * (nbytes // 4)).from_address(p)
+    return np.frombuffer(buf, dtype=np.float32).reshape(shape), p
+
+
+def run_native(args, rank, world):
+    import cupoch_b200 as cph
+    from cupoch_b200 import _lib
+    from cupoch_b200.utility import DeviceArray, as_f16
+    L = _lib.lib()
+    _lib.require_gpu()
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    _lib.check(L.cphb_set_device(local_rank))
+    comm = None
+    dist = None
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        uid = torch.zeros(128, dtype=torch.uint8)
+        if rank == 0:
+            b = C.create_string_buffer(128)
+            _lib.check(L.cphb_nccl_unique_id(b))
+            uid = torch.frombuffer(bytearray(b.raw), dtype=torch.uint8).clone()
+        uid = uid.cuda()
+        dist.broadcast(uid, 0)
+        h = C.c_void_p()
+        _lib.check(L.cphb_nccl_comm_init(bytes(uid.cpu().numpy().tobytes()), world, rank, C.byref(h)))
+        comm = h
+
+    n = args.points
+    src, tgt, tn = make_workload(n)
+    lo, hi = (n * rank) // world, (n * (rank + 1)) // world
+    src_local = np.ascontiguousarray(src[lo:hi])
+    R = cph.registration
+    est, crit = R.TransformationEstimationPointToPlane(), R.ICPConvergenceCriteria(0, 0, ITERS)
+    init = np.eye(4, dtype=np.float32)
+
+    # resident clouds
+    s_pc = cph.geometry.PointCloud(src_local)
+    t_pc = cph.geometry.PointCloud(tgt)
+    t_pc.normals = tn
+    flush = DeviceArray((256 << 20,), np.uint8)  # > 126 MB L2
+
+    def barrier():
+        _lib.check(L.cphb_stream_synchronize(None))
+        if dist is not None:
+            dist.barrier()
+            import torch
+            torch.cuda.synchronize()
+
+    def step_resident():
+        return R.registration_icp(s_pc, t_pc, MAX_DIST, init, est, crit, nccl_comm=comm)
+
+    ev = [L.cphb_event_create() for _ in range(2)]
+
+    def timed(fn, steps):
+        """sum of per-step device times (CUDA events), L2 flushed between steps outside the timed region"""
+        total_ms, last = 0.0, None
+        for _ in range(steps):
+            _lib.check(L.cphb_memset(flush.ptr, 0, flush.nbytes, None))
+            barrier()
+            _lib.check(L.cphb_event_record(ev[0], None))
+            last = fn()
+            _lib.check(L.cphb_event_record(ev[1], None))
+            ms = C.c_float(0)
+            _lib.check(L.cphb_event_elapsed_ms(ev[0], ev[1], C.byref(ms)))
+            total_ms += ms.value
+        return total_ms, last
+
+    for _ in range(args.warmup):
+        step_resident()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    launches0 = L.cphb_launch_count()
+    total_ms, res = timed(step_resident, args.steps)
+    launches = L.cphb_launch_count() - launches0
+    loop_ms, loop_launches = res.loop_ms, res.loop_launches
+
+    # ---- end-to-end through the public API with host (pinned) buffers ---------------------------
+    h_src, p1 = pinned_array(L, src_local.shape)
+    h_tgt, p2 = pinned_array(L, tgt.shape)
+    h_tn, p3 = pinned_array(L, tn.shape)
+    h_src[:], h_tgt[:], h_tn[:] = src_local, tgt, tn
+    d2h = [0]
+
+    def step_e2e():
+        s2 = cph.geometry.PointCloud(h_src)         # H2D (pinned)
+        t2 = cph.geometry.PointCloud(h_tgt)
+        t2.normals = h_tn
+        r = R.registration_icp(s2, t2, MAX_DIST, init, est, crit, nccl_comm=comm)  # D2H of T + correspondences
+        d2h[0] = 16 * 4 + 8 + r.correspondence_set.nbytes
+        return r
+    for _ in range(min(args.warmup, 2)):
+        step_e2e()
+    e2e_ms, res_e = timed(step_e2e, args.steps)
+    h2d_bytes = h_src.nbytes + h_tgt.nbytes + h_tn.nbytes
+
+    # ---- kNN leg of the metric: SearchRadius(k=1, r) of the 1M source against the 1M target ------
+    tree = cph.geometry.KDTreeFlann(t_pc)
+    for _ in range(2):
+        tree.search_radius(s_pc.points, MAX_DIST, 1)
+    knn_ms, _ = timed(lambda: tree.search_radius(s_pc.points, MAX_DIST, 1), max(args.steps, 3))
+    knn_steps = max(args.steps, 3)
+    if rank == 0:
+        sampler.stop_flag = True
+        sampler.join(timeout=2)
+
+    # max over ranks
+    if dist is not None:
+        import torch
+        t = torch.tensor([total_ms, e2e_ms, knn_ms, loop_ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total_ms, e2e_ms, knn_ms, loop_ms = [float(x) for x in t.tolist()]
+    if rank == 0:
+        peak, peak_src = peaks()
+        ms_step = total_ms / args.steps
+        value = ITERS * 1e3 / ms_step
+        kern_ms = loop_ms / max(loop_launches, 1)
+        units = (hi - lo)
+        achieved = ALG_BYTES_PER_POINT * units / (kern_ms * 1e-3) / 1e9
+        out = {
+            "metric": "icp_iterations_per_sec", "value": value, "unit": "iter/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "config2: point-to-plane ICP 1M->1M + normals, 30 iters, r=0.02 (SURVEY.md 8d)",
+                       "points": n, "iterations": ITERS, "step": "one RegistrationICP call incl. index build",
+                       "cache": "256 MiB memset between timed steps (L2 flush); working set ~60 MB",
+                       "parallelism": "source sharded x%d, target replicated, 1 all-reduce(32 f64)/iter" % world},
+            "e2e": {"value": ITERS * 1e3 / (e2e_ms / args.steps), "unit": "iter/s", "h2d_bytes_per_step": int(h2d_bytes),
+                    "d2h_bytes_per_step": int(d2h[0]), "ms_per_step": e2e_ms / args.steps},
+            "gpu_launches": int(launches),
+            "loop": {"iters_per_sec": ITERS * 1e3 / loop_ms, "ms_per_launch": kern_ms, "launches": loop_launches,
+                     "correspondences_per_sec": float(res.fitness) * n * (ITERS + 1) * 1e3 / loop_ms},
+            "knn": {"mqueries_per_sec": n / world / (knn_ms / knn_steps) * 1e-3, "k": 1, "radius": MAX_DIST,
+                    "ms": knn_ms / knn_steps, "note": "SearchRadius of the source shard incl. query ordering"},
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": None, "peak_source": peak_src, "kernel": "icp_iteration_kernel<PointToPlane>",
+                         "algorithmic_bytes_per_launch": ALG_BYTES_PER_POINT * units},
+            "clocks": sampler.summary(),
+            "final": {"fitness": res.fitness, "inlier_rmse": res.inlier_rmse, "iterations": res.iterations,
+                      "T": np.asarray(res.transformation).round(6).tolist()},
+        }
+        if world == 1 and not args.no_cpu:
+            out["cpu_baseline"] = cpu_baseline(src, tgt, tn)
+        print(json.dumps(out))
+    for p in (p1, p2, p3):
+        L.cphb_free_host(p)
+    if comm is not None:
+        L.cphb_nccl_comm_destroy(comm)
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def cpu_baseline(src, tgt, tn):
+    """Bounded CPU sample: the oracle port (kd-tree + OpenMP) with 1 and 4 iterations on the full clouds,
+    extrapolated to the 30-iteration job (search cost is flat once aligned)."""
+    from oracle import oracle_py as orc
+    def t(iters):
+        t0 = time.perf_counter()
+        orc.registration_icp(orc.P2PLANE, src, tgt, MAX_DIST, tgt_nrm=tn, relative_fitness=0, relative_rmse=0,
+                             max_iteration=iters)
+        return time.perf_counter() - t0
+    t1, t4 = t(1), t(4)
+    per_iter = max((t4 - t1) / 3, 1e-9)
+    job = t4 + (ITERS - 4) * per_iter
+    return {"value": ITERS / job, "unit": "iter/s", "cores": orc.num_threads(), "kind": "port",
+            "sample": "1M->1M, 1 and 4 iterations measured (%.2fs, %.2fs), extrapolated to 30 incl. kd-tree build" % (t1, t4)}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="native", choices=["native", "reference"])
+    ap.add_argument("--points", type=int, default=1_000_000)
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "native" else args.warmup
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        run_reference(args, rank)
+    else:
+        run_native(args, rank, world)
+
+
+if __name__ == "__main__":
+    main()

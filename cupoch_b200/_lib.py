@@ -72,6 +72,11 @@ _SIGNATURES = {
     "cphb_memcpy_d2h": (C.c_int, [_P, _P, C.c_size_t, _P]),
     "cphb_memset": (C.c_int, [_P, C.c_int, C.c_size_t, _P]),
     "cphb_stream_synchronize": (C.c_int, [_P]),
+    "cphb_memcpy_d2d": (C.c_int, [_P, _P, C.c_size_t, _P]),
+    "cphb_event_create": (_P, []),
+    "cphb_event_destroy": (None, [_P]),
+    "cphb_event_record": (C.c_int, [_P, _P]),
+    "cphb_event_elapsed_ms": (C.c_int, [_P, _P, C.POINTER(C.c_float)]),
     "cphb_nccl_unique_id": (C.c_int, [C.c_char_p]),
     "cphb_nccl_comm_init": (C.c_int, [C.c_char_p, C.c_int, C.c_int, C.POINTER(_P)]),
     "cphb_nccl_comm_destroy": (C.c_int, [_P]),

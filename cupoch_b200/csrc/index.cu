@@ -92,6 +92,30 @@ extern "C" int cphb_memset(void *dst, int value, size_t bytes, void *stream) {
     CPHB_CUDA(cudaMemsetAsync(dst, value, bytes, (cudaStream_t)stream));
     return CPHB_OK;
 }
+extern "C" int cphb_memcpy_d2d(void *dst, const void *src, size_t bytes, void *stream) {
+    CPHB_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+    return CPHB_OK;
+}
+extern "C" void *cphb_event_create(void) {
+    cudaEvent_t e = nullptr;
+    if (cudaEventCreate(&e) != cudaSuccess) {
+        cphb_set_error("cudaEventCreate: %s", cudaGetErrorString(cudaGetLastError()));
+        return nullptr;
+    }
+    return (void *)e;
+}
+extern "C" void cphb_event_destroy(void *e) {
+    if (e) cudaEventDestroy((cudaEvent_t)e);
+}
+extern "C" int cphb_event_record(void *e, void *stream) {
+    CPHB_CUDA(cudaEventRecord((cudaEvent_t)e, (cudaStream_t)stream));
+    return CPHB_OK;
+}
+extern "C" int cphb_event_elapsed_ms(void *start, void *stop, float *h_ms) {
+    CPHB_CUDA(cudaEventSynchronize((cudaEvent_t)stop));
+    CPHB_CUDA(cudaEventElapsedTime(h_ms, (cudaEvent_t)start, (cudaEvent_t)stop));
+    return CPHB_OK;
+}
 extern "C" int cphb_stream_synchronize(void *stream) {
     CPHB_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
     return CPHB_OK;

@@ -226,6 +226,12 @@ int cphb_memcpy_h2d(void *dst, const void *src, size_t bytes, void *stream);
 int cphb_memcpy_d2h(void *dst, const void *src, size_t bytes, void *stream);
 int cphb_memset(void *dst, int value, size_t bytes, void *stream);
 int cphb_stream_synchronize(void *stream);
+int cphb_memcpy_d2d(void *dst, const void *src, size_t bytes, void *stream);
+/* CUDA events on `stream` (bench.py times the hot path on the device, not by wall clock) */
+void *cphb_event_create(void);
+void cphb_event_destroy(void *event);
+int cphb_event_record(void *event, void *stream);
+int cphb_event_elapsed_ms(void *start, void *stop, float *h_ms); /* synchronises on stop */
 /* NCCL bootstrap without torch types: unique id is 128 bytes. */
 int cphb_nccl_unique_id(char h_id[128]);
 int cphb_nccl_comm_init(const char h_id[128], int world_size, int rank, void **out_comm);

@@ -91,7 +91,8 @@ def test_strict_radius_boundary(orc):
     qry = np.array([[0.5, 0, 0], [0, 1, 0]], np.float32)
     _check(orc, tgt, qry, 2, radius=0.5)    # d2 == r2 exactly -> excluded
     idx, _ = _check(orc, tgt, qry, 2, radius=1.0)
-    assert idx[1, 0] == 0 and idx[1, 1] == -1  # (0,2,0) at d2 == 1.0 is excluded
+    assert idx[0].tolist() == [0, 1]           # tie at d2 = 0.25: smaller index first
+    assert idx[1].tolist() == [-1, -1]         # both neighbours of (0,1,0) sit at d2 == r2 == 1.0: excluded
     _check(orc, tgt, qry, 1, radius=0.0)
 
 
