@@ -64,6 +64,11 @@ _SIGNATURES = {
                                         C.POINTER(IcpParams), _P, C.POINTER(IcpResult), _P, _P]),
     "cphb_evaluate_registration": (C.c_int, [C.POINTER(Cloud), C.POINTER(Cloud), C.c_float, C.POINTER(C.c_float),
                                              C.POINTER(IcpResult), _P, _P]),
+    "cphb_compute_transformation": (C.c_int, [C.c_int, C.POINTER(Cloud), C.POINTER(Cloud), _P, C.c_size_t,
+                                              C.POINTER(IcpParams), C.POINTER(C.c_float), _P]),
+    "cphb_compute_rmse": (C.c_int, [C.c_int, C.POINTER(Cloud), C.POINTER(Cloud), _P, C.c_size_t, C.POINTER(IcpParams),
+                                    C.POINTER(C.c_float), _P]),
+    "cphb_kabsch": (C.c_int, [_P, C.c_size_t, _P, _P, C.c_size_t, C.POINTER(C.c_float), _P]),
     "cphb_malloc": (_P, [C.c_size_t]),
     "cphb_free": (None, [_P]),
     "cphb_malloc_host": (_P, [C.c_size_t]),

@@ -215,19 +215,37 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, unsigned parity) {
 }
 
 // ---------------------------------------------------------------------------
-// Warp-cooperative exact nearest-neighbour traversal (k = 1).
-// best = (d2 bits << 32) | original index: one u64 min implements
-// "smaller d2, ties -> smaller index" (the oracle's rule).
+// Warp-cooperative exact nearest-neighbour traversal.
+//
+// A warp owns 32 queries (a compact cluster: queries are processed in Hilbert
+// order).  At every node one lane tests one child box:
+//   stage 1  box-vs-warp-AABB distance against the warp bound (max over lanes
+//            of their current worst accepted d2) -- one instruction stream for
+//            32 children;
+//   order    children are visited by increasing distance to the warp AABB's
+//            centre, so the bound tightens after the first leaves;
+//   stage 2  before a child is entered its box is broadcast and every lane
+//            tests its OWN query against it with its OWN bound; the child is
+//            skipped unless some lane can still improve.
+// Leaves are fetched by TMA bulk copies into a double-buffered shared-memory
+// tile: the copy of the next candidate leaf is in flight while the current one
+// is scanned.  Ties: key = (d2 bits << 32) | original index, so one u64 min
+// implements "smaller d2, then smaller index" (the oracle's rule); culling
+// uses <= so equal-distance candidates are never skipped.
 // ---------------------------------------------------------------------------
-struct WarpSearch {
-    float qx, qy, qz;           // this lane's query
-    float wlo[3], whi[3];       // warp-uniform AABB of the valid queries
-    unsigned long long best;    // this lane's best key
-    unsigned bound;             // warp-uniform max over valid lanes of (best >> 32)
-    unsigned phase;             // mbarrier parity (warp-uniform)
-    bool valid;                 // lane holds a real query
-    float4 *tile;               // per-warp smem leaf tile [CPHB_LEAF]
-    uint64_t *bar;              // per-warp mbarrier
+struct WarpSearchBase {
+    float qx, qy, qz;      // this lane's query
+    float wlo[3], whi[3];  // warp-uniform AABB of the valid queries
+    float wc[3];           // its centre
+    unsigned bound;        // warp-uniform cull bound (d2 bits)
+    unsigned phase;        // bit b = parity of mbarrier b
+    bool valid;            // lane holds a real query
+    float4 *tile;          // per-warp smem: 2 leaf tiles [2][CPHB_LEAF]
+    uint64_t *bar;         // per-warp smem: 2 mbarriers
+};
+struct WarpSearch : WarpSearchBase {
+    unsigned long long best;  // this lane's best key
+    __device__ __forceinline__ unsigned lane_bound() const { return (unsigned)(best >> 32); }
 };
 
 // key strictly below (r2, idx 0): accepts exactly d2 < r2
@@ -245,55 +263,103 @@ __device__ __forceinline__ void warp_query_box(W &w) {
     for (int a = 0; a < 3; ++a) {
         w.wlo[a] = ord2f(__reduce_min_sync(CPHB_FULL, lo[a]));
         w.whi[a] = ord2f(__reduce_max_sync(CPHB_FULL, hi[a]));
+        w.wc[a] = 0.5f * w.wlo[a] + 0.5f * w.whi[a];
     }
 }
-
-// fetch one leaf tile by TMA into the warp's smem tile and wait for it
 template <class W>
-__device__ __forceinline__ void fetch_leaf(const IndexView &ix, unsigned leaf, W &w) {
-    if (lane_id() == 0) {
-        mbar_expect_tx(w.bar, CPHB_LEAF * 16);
-        tma_bulk_g2s(w.tile, ix.pts + (size_t)leaf * CPHB_LEAF, CPHB_LEAF * 16, w.bar);
-    }
-    while (!mbar_try_wait(w.bar, w.phase)) {
-    }
-    w.phase ^= 1u;
+__device__ __forceinline__ void warp_update_bound(W &w) {
+    w.bound = __reduce_max_sync(CPHB_FULL, w.valid ? w.lane_bound() : 0u);
 }
 
-__device__ __forceinline__ void scan_leaf(const IndexView &ix, unsigned leaf, WarpSearch &w) {
-    fetch_leaf(ix, leaf, w);
+__device__ __forceinline__ void issue_leaf(const IndexView &ix, unsigned leaf, float4 *tile, uint64_t *bar) {
+    if (lane_id() == 0) {
+        mbar_expect_tx(bar, CPHB_LEAF * 16);
+        tma_bulk_g2s(tile, ix.pts + (size_t)leaf * CPHB_LEAF, CPHB_LEAF * 16, bar);
+    }
+}
+template <class W>
+__device__ __forceinline__ void wait_leaf(W &w, int b) {
+    while (!mbar_try_wait(w.bar + b, (w.phase >> b) & 1u)) {
+    }
+    w.phase ^= (1u << b);
+}
+
+// k = 1 leaf scan
+__device__ __forceinline__ void scan_tile(const float4 *tile, WarpSearch &w) {
     unsigned long long best = w.best;
 #pragma unroll
     for (int j = 0; j < CPHB_LEAF; ++j) {
-        float4 p = w.tile[j];
+        float4 p = tile[j];
         float d2 = dist2(w.qx, w.qy, w.qz, p.x, p.y, p.z);
         unsigned long long key = ((unsigned long long)__float_as_uint(d2) << 32) | __float_as_uint(p.w);
         best = (key < best) ? key : best;
     }
     w.best = best;
-    __syncwarp();  // all lanes done with the tile before lane 0 re-arms it
-    w.bound = __reduce_max_sync(CPHB_FULL, w.valid ? (unsigned)(best >> 32) : 0u);
 }
 
-// W provides: wlo/whi (warp AABB), bound (warp-uniform cull bound, d2 bits) and
-// an overload scan_leaf(ix, leaf, W&) that updates bound.
+// lane index of the active child with the smallest order key, or -1
+__device__ __forceinline__ int pick_child(unsigned active, unsigned keybits) {
+    unsigned cand = ((active >> lane_id()) & 1u) ? keybits : 0xffffffffu;
+    unsigned m = __reduce_min_sync(CPHB_FULL, cand);
+    if (m == 0xffffffffu) return -1;
+    return __ffs(__ballot_sync(CPHB_FULL, cand == m)) - 1;
+}
+// stage 2: can any lane still improve inside box `bx`?  (uniform address: one broadcast load)
+template <class W>
+__device__ __forceinline__ bool any_lane_needs(const W &w, const Box *bx) {
+    const float4 lo = __ldg(&bx->lo), hi = __ldg(&bx->hi);
+    float dx = fmaxf(0.f, fmaxf(lo.x - w.qx, w.qx - hi.x));
+    float dy = fmaxf(0.f, fmaxf(lo.y - w.qy, w.qy - hi.y));
+    float dz = fmaxf(0.f, fmaxf(lo.z - w.qz, w.qz - hi.z));
+    float d = __fmaf_rn(dz, dz, __fmaf_rn(dy, dy, __fmul_rn(dx, dx)));
+    return __any_sync(CPHB_FULL, w.valid && __float_as_uint(d) <= w.lane_bound());
+}
+
 template <int LV, class W>
 struct Visit {
     static __device__ __forceinline__ void run(const IndexView &ix, unsigned group, W &w) {
-        const Box *b = ix.boxes[LV] + ((size_t)group * 32 + lane_id());
-        float4 lo = __ldg(&b->lo), hi = __ldg(&b->hi);
-        unsigned dbits = __float_as_uint(box_dist2(lo, hi, w.wlo, w.whi));
-        unsigned active = __ballot_sync(CPHB_FULL, dbits <= w.bound);
-        while (active) {
-            unsigned cand = ((active >> lane_id()) & 1u) ? dbits : 0xffffffffu;
-            unsigned dmin = __reduce_min_sync(CPHB_FULL, cand);
-            if (dmin > w.bound) break;  // everything left is farther than the current bound
-            unsigned who = __ballot_sync(CPHB_FULL, cand == dmin);
-            int src = __ffs(who) - 1;
-            active &= ~(1u << src);
-            unsigned child = group * 32 + src;
-            if constexpr (LV == 0) scan_leaf(ix, child, w);
-            else Visit<LV - 1, W>::run(ix, child, w);
+        const Box *gbox = ix.boxes[LV] + (size_t)group * 32;
+        unsigned dcull, dkey;
+        {
+            const float4 lo = __ldg(&gbox[lane_id()].lo), hi = __ldg(&gbox[lane_id()].hi);
+            dcull = __float_as_uint(box_dist2(lo, hi, w.wlo, w.whi));
+            // order key: distance of the box to the warp centre (+inf for empty boxes stays +inf)
+            const float c3[3] = {w.wc[0], w.wc[1], w.wc[2]};
+            dkey = __float_as_uint(box_dist2(lo, hi, c3, c3));
+        }
+        unsigned active = __ballot_sync(CPHB_FULL, dcull <= w.bound);
+        if constexpr (LV > 0) {
+            while (active) {
+                int src = pick_child(active, dkey);
+                if (src < 0) break;
+                active &= ~(1u << src);
+                if (any_lane_needs(w, gbox + src)) {
+                    Visit<LV - 1, W>::run(ix, group * 32 + src, w);
+                    active &= __ballot_sync(CPHB_FULL, dcull <= w.bound);
+                }
+            }
+        } else {
+            int b = 0;
+            int next = pick_child(active, dkey);
+            if (next >= 0) issue_leaf(ix, group * 32 + next, w.tile + b * CPHB_LEAF, w.bar + b);
+            while (next >= 0) {
+                const int cur = next;
+                active &= ~(1u << cur);
+                next = pick_child(active, dkey);
+                if (next >= 0) issue_leaf(ix, group * 32 + next, w.tile + (b ^ 1) * CPHB_LEAF, w.bar + (b ^ 1));
+                const bool need = any_lane_needs(w, gbox + cur);
+                wait_leaf(w, b);  // always consume the copy so the barrier phases stay in step
+                if (need) {
+                    scan_tile(w.tile + b * CPHB_LEAF, w);
+                    warp_update_bound(w);
+                    const unsigned still = __ballot_sync(CPHB_FULL, dcull <= w.bound);
+                    // the prefetched `next` stays queued even if it just got culled: it is consumed
+                    // (and skipped by stage 2) on the next trip
+                    active &= still;
+                }
+                __syncwarp();  // all lanes done with tile b before it is re-armed
+                b ^= 1;
+            }
         }
     }
 };
@@ -306,6 +372,7 @@ __device__ __forceinline__ void warp_nn_search(const IndexView &ix, W &w) {
     Visit<TOP, W>::run(ix, 0u, w);
 }
 
+// tile: 2*CPHB_LEAF float4, bar: 2 mbarriers (per warp)
 template <class W>
 __device__ __forceinline__ void warp_search_setup(W &w, float4 *tile, uint64_t *bar) {
     w.tile = tile;
@@ -313,6 +380,7 @@ __device__ __forceinline__ void warp_search_setup(W &w, float4 *tile, uint64_t *
     w.phase = 0;
     if (lane_id() == 0) {
         mbar_init(bar, 1);
+        mbar_init(bar + 1, 1);
         fence_mbar_init();
     }
     __syncwarp();

@@ -39,7 +39,7 @@ struct IcpState {
     int converged;
     int apply_u;
     unsigned ticket;
-    int pad;
+    unsigned tile_counter;
     long long n_corr;
 };
 
@@ -51,7 +51,9 @@ struct IcpArgs {
     const float4 *src_col;  // colors in Hilbert order (Colored) or null
     const float *tgt_xyz, *tgt_nrm, *tgt_col, *tgt_grad, *tgt_cov;
     IcpState *st;
-    double *partials;
+    double *partials;     // [reduce grid][32]
+    double *tile_sums;    // [n_pad/32][32]
+    int *prev;            // [n_pad] last iteration's match per Hilbert position (warm start) or null
     int32_t *corr_index;  // [n_src] matched target index per ORIGINAL source index, or null
     unsigned long long n_total;
     unsigned n_src, n_pad;
@@ -335,126 +337,19 @@ __device__ void icp_finalize(const IcpArgs &a, IcpState *st) {
 }
 
 // ===========================================================================
-// the fused per-iteration kernel
+// estimator rows for one correspondence (source point vs, target index j)
 // ===========================================================================
-template <int KIND, int TOP>
-__global__ void __launch_bounds__(ICP_BLOCK) icp_iteration_kernel(const __grid_constant__ IcpArgs a) {
-    __shared__ __align__(16) float4 s_tile[ICP_WARPS][CPHB_LEAF];
-    __shared__ uint64_t s_bar[ICP_WARPS];
-    __shared__ double s_rows[ICP_WARPS][32 * ROW_STRIDE];
-    __shared__ double s_acc[ICP_WARPS][32];
-    __shared__ unsigned s_last;
-
-    IcpState *st = a.st;
-    const int done = *(volatile int *)&st->done;
-    if (done == 2) return;
-    const bool materialize = (done == 1);
-    const bool apply = !materialize && !a.step_mode ? (*(volatile int *)&st->apply_u != 0) : (a.step_mode != 0);
-    const int warp = threadIdx.x >> 5, lane = lane_id();
-
-    WarpSearch w;
-    warp_search_setup(w, s_tile[warp], &s_bar[warp]);
-
-    const unsigned i = blockIdx.x * ICP_BLOCK + threadIdx.x;  // position in Hilbert order (< n_pad)
-    float4 s = a.src[i];
-    const unsigned orig = __float_as_uint(s.w);
-    w.valid = i < a.n_src;
-
-    // ---- PointCloud::Transform(update) on the working copy (pointcloud.cu:293-299) ----
-    float sn[3] = {0.f, 0.f, 0.f};
-    float Cs[9];
-    if (apply) {
-        float U[12];
-#pragma unroll
-        for (int k = 0; k < 12; ++k) U[k] = st->U[k];
-        float x = s.x, y = s.y, z = s.z;
-        s.x = __fadd_rn(dot3(U[0], U[1], U[2], x, y, z), U[3]);
-        s.y = __fadd_rn(dot3(U[4], U[5], U[6], x, y, z), U[7]);
-        s.z = __fadd_rn(dot3(U[8], U[9], U[10], x, y, z), U[11]);
-        if (!a.step_mode) a.src[i] = s;
-        if (KIND == CPHB_EST_SYMMETRIC && a.src_nrm) {
-            float4 n4 = a.src_nrm[i];
-            sn[0] = dot3(U[0], U[1], U[2], n4.x, n4.y, n4.z);
-            sn[1] = dot3(U[4], U[5], U[6], n4.x, n4.y, n4.z);
-            sn[2] = dot3(U[8], U[9], U[10], n4.x, n4.y, n4.z);
-            if (!a.step_mode) a.src_nrm[i] = make_float4(sn[0], sn[1], sn[2], 0.f);
-        }
-        if (KIND == CPHB_EST_GENERALIZED_ICP && a.src_cov) {
-            float C[9], tmp[9];
-#pragma unroll
-            for (int r = 0; r < 3; ++r) {
-                float4 c4 = a.src_cov[(size_t)r * a.n_pad + i];
-                C[3 * r] = c4.x; C[3 * r + 1] = c4.y; C[3 * r + 2] = c4.z;
-            }
-            const float R[9] = {U[0], U[1], U[2], U[4], U[5], U[6], U[8], U[9], U[10]};
-#pragma unroll
-            for (int r = 0; r < 3; ++r)
-#pragma unroll
-                for (int c = 0; c < 3; ++c)
-                    tmp[3 * r + c] = dot3(R[3 * r], R[3 * r + 1], R[3 * r + 2], C[c], C[3 + c], C[6 + c]);
-#pragma unroll
-            for (int r = 0; r < 3; ++r)
-#pragma unroll
-                for (int c = 0; c < 3; ++c)
-                    Cs[3 * r + c] = dot3(tmp[3 * r], tmp[3 * r + 1], tmp[3 * r + 2], R[3 * c], R[3 * c + 1], R[3 * c + 2]);
-            if (!a.step_mode)
-#pragma unroll
-                for (int r = 0; r < 3; ++r)
-                    a.src_cov[(size_t)r * a.n_pad + i] = make_float4(Cs[3 * r], Cs[3 * r + 1], Cs[3 * r + 2], 0.f);
-        }
-    } else {
-        if (KIND == CPHB_EST_SYMMETRIC && a.src_nrm) {
-            float4 n4 = a.src_nrm[i];
-            sn[0] = n4.x; sn[1] = n4.y; sn[2] = n4.z;
-        }
-        if (KIND == CPHB_EST_GENERALIZED_ICP && a.src_cov) {
-#pragma unroll
-            for (int r = 0; r < 3; ++r) {
-                float4 c4 = a.src_cov[(size_t)r * a.n_pad + i];
-                Cs[3 * r] = c4.x; Cs[3 * r + 1] = c4.y; Cs[3 * r + 2] = c4.z;
-            }
-        }
-    }
-
-    // ---- SearchRadius(.., max_nn = 1) (registration.cu:47) -----------------------------
-    w.qx = s.x; w.qy = s.y; w.qz = s.z;
-    const unsigned long long init = (a.r2 > 0.f) ? init_key(a.r2) : 0ull;
-    w.best = init;
-    w.bound = (unsigned)(init >> 32);
-    warp_query_box(w);
-    if (__any_sync(CPHB_FULL, w.valid)) warp_nn_search<TOP>(a.ix, w);
-    const bool found = w.valid && (w.best != init);
-    const unsigned j = (unsigned)(w.best & 0xffffffffull);
-    const float d2 = __uint_as_float((unsigned)(w.best >> 32));
-
-    if (a.corr_index && w.valid && (materialize || a.step_mode || a.launch_idx == a.max_iter))
-        a.corr_index[orig] = found ? (int32_t)j : -1;
-    if (materialize) {
-        // nothing to accumulate: fitness / rmse / T of this pose are already in the state
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            __threadfence();
-            unsigned t = atomicAdd(&st->ticket, 1u);
-            if (t == gridDim.x - 1) { st->ticket = 0; st->done = 2; }
-        }
-        return;
-    }
-
-    // ---- rows: J (6), r; staged as doubles, one row of 9 per lane -----------------------
-    double *rows = s_rows[warp];
-    const unsigned char(*pair)[2] = (KIND == CPHB_EST_POINT_TO_POINT) ? c_pair_p2p : c_pair_jtj;
-    const int ca = pair[lane][0], cb = pair[lane][1];
-    double acc = 0.0;
-    constexpr int NROWS = (KIND == CPHB_EST_COLORED_ICP) ? 2 : (KIND == CPHB_EST_GENERALIZED_ICP) ? 3 : 1;
-    float J[NROWS][6], r[NROWS];
-#pragma unroll
-    for (int q = 0; q < NROWS; ++q) {
-        r[q] = 0.f;
-#pragma unroll
-        for (int c = 0; c < 6; ++c) J[q][c] = 0.f;
-    }
-    bool use = found;
-    if (found) {
+struct TargetAttrs {
+    const float *tgt_xyz, *tgt_nrm, *tgt_col, *tgt_grad, *tgt_cov;
+    int tgt_cov_col_major;
+    float sg, sp;
+    bool src_nrm, src_col, src_cov;  // source attribute present
+};
+template <int KIND, int NROWS>
+__device__ __forceinline__ void build_rows(const TargetAttrs &a, const float s_x, const float s_y, const float s_z,
+                                           const float *sn, const float4 cs_in, const float *Cs, unsigned j,
+                                           float (&J)[NROWS][6], float (&r)[NROWS]) {
+    struct { float x, y, z; } s = {s_x, s_y, s_z};
         const float vs[3] = {s.x, s.y, s.z};
         const float vt[3] = {a.tgt_xyz[3 * (size_t)j], a.tgt_xyz[3 * (size_t)j + 1], a.tgt_xyz[3 * (size_t)j + 2]};
         if (KIND == CPHB_EST_POINT_TO_POINT) {
@@ -481,7 +376,7 @@ __global__ void __launch_bounds__(ICP_BLOCK) icp_iteration_kernel(const __grid_c
                 const size_t j3 = 3 * (size_t)j;
                 const float nt[3] = {a.tgt_nrm[j3], a.tgt_nrm[j3 + 1], a.tgt_nrm[j3 + 2]};
                 const float gt[3] = {a.tgt_grad[j3], a.tgt_grad[j3 + 1], a.tgt_grad[j3 + 2]};
-                const float4 cs = a.src_col[i];
+                const float4 cs = cs_in;
                 const float d[3] = {vs[0] - vt[0], vs[1] - vt[1], vs[2] - vt[2]};
                 const float dn = dot3(d[0], d[1], d[2], nt[0], nt[1], nt[2]);
                 float cr[3];
@@ -533,16 +428,300 @@ __global__ void __launch_bounds__(ICP_BLOCK) icp_iteration_kernel(const __grid_c
                 }
             }
         }
+}
+
+// ===========================================================================
+// the fused per-iteration kernel
+//
+// Persistent warps: each warp repeatedly claims a tile of 32 consecutive
+// (Hilbert-ordered) source points from an atomic counter, so per-tile cost
+// variation never idles a block.  Warps are fully independent (no
+// __syncthreads).  Per tile: apply the previous update in place -> warm-start
+// the search from last iteration's match -> exact NN search -> estimator rows
+// -> 32 column sums written to tile_sums[tile][32] (one coalesced 256-B store).
+// icp_reduce_kernel then adds the tile sums in a fixed order (bitwise
+// reproducible whatever the tile schedule was) and its last block runs the
+// solve / convergence logic.
+// ===========================================================================
+#define ICP_SEARCH_WARPS 4
+template <int KIND, int TOP>
+__global__ void __launch_bounds__(ICP_SEARCH_WARPS * 32) icp_iteration_kernel(const __grid_constant__ IcpArgs a) {
+    __shared__ __align__(16) float4 s_tile[ICP_SEARCH_WARPS][2 * CPHB_LEAF];
+    __shared__ uint64_t s_bar[ICP_SEARCH_WARPS][2];
+    __shared__ double s_rows[ICP_SEARCH_WARPS][32 * ROW_STRIDE];
+
+    IcpState *st = a.st;
+    const int done = *(volatile int *)&st->done;
+    if (done == 2) return;
+    const bool materialize = (done == 1);
+    const bool apply = a.step_mode ? true : (!materialize && *(volatile int *)&st->apply_u != 0);
+    const int warp = threadIdx.x >> 5, lane = lane_id();
+
+    WarpSearch w;
+    warp_search_setup(w, s_tile[warp], s_bar[warp]);
+    float U[12];
+#pragma unroll
+    for (int k = 0; k < 12; ++k) U[k] = apply ? st->U[k] : ((k % 5 == 0) ? 1.f : 0.f);
+    const unsigned n_tiles = a.n_pad / 32;
+    const unsigned long long init = (a.r2 > 0.f) ? init_key(a.r2) : 0ull;
+    const bool write_corr = a.corr_index && (materialize || a.step_mode || a.launch_idx == a.max_iter);
+    double *rows = s_rows[warp];
+    const unsigned char(*pair)[2] = (KIND == CPHB_EST_POINT_TO_POINT) ? c_pair_p2p : c_pair_jtj;
+    const int ca = pair[lane][0], cb = pair[lane][1];
+    const unsigned live = (KIND == CPHB_EST_POINT_TO_POINT) ? c_live_p2p : c_live_jtj;
+    constexpr int NROWS = (KIND == CPHB_EST_COLORED_ICP) ? 2 : (KIND == CPHB_EST_GENERALIZED_ICP) ? 3 : 1;
+
+    while (true) {
+        unsigned tile = 0;
+        if (lane == 0) tile = atomicAdd(&st->tile_counter, 1u);
+        tile = __shfl_sync(CPHB_FULL, tile, 0);
+        if (tile >= n_tiles) break;
+        const unsigned i = tile * 32 + lane;  // position in Hilbert order (< n_pad)
+        float4 s = a.src[i];
+        const unsigned orig = __float_as_uint(s.w);
+        w.valid = i < a.n_src;
+
+        // ---- PointCloud::Transform(update) on the working copy (pointcloud.cu:293-299) ----
+        float sn[3] = {0.f, 0.f, 0.f};
+        float Cs[9] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        if (apply) {
+            const float x = s.x, y = s.y, z = s.z;
+            s.x = __fadd_rn(dot3(U[0], U[1], U[2], x, y, z), U[3]);
+            s.y = __fadd_rn(dot3(U[4], U[5], U[6], x, y, z), U[7]);
+            s.z = __fadd_rn(dot3(U[8], U[9], U[10], x, y, z), U[11]);
+            if (!a.step_mode) a.src[i] = s;
+        }
+        if (KIND == CPHB_EST_SYMMETRIC && a.src_nrm) {
+            const float4 n4 = a.src_nrm[i];
+            if (apply) {
+                sn[0] = dot3(U[0], U[1], U[2], n4.x, n4.y, n4.z);
+                sn[1] = dot3(U[4], U[5], U[6], n4.x, n4.y, n4.z);
+                sn[2] = dot3(U[8], U[9], U[10], n4.x, n4.y, n4.z);
+                if (!a.step_mode) a.src_nrm[i] = make_float4(sn[0], sn[1], sn[2], 0.f);
+            } else {
+                sn[0] = n4.x; sn[1] = n4.y; sn[2] = n4.z;
+            }
+        }
+        if (KIND == CPHB_EST_GENERALIZED_ICP && a.src_cov) {
+            float C[9];
+#pragma unroll
+            for (int r = 0; r < 3; ++r) {
+                const float4 c4 = a.src_cov[(size_t)r * a.n_pad + i];
+                C[3 * r] = c4.x; C[3 * r + 1] = c4.y; C[3 * r + 2] = c4.z;
+            }
+            if (apply) {  // RotateCovariances (geometry_utils.cu:257-265): (R*C)*R^T
+                float tmp[9];
+                const float R[9] = {U[0], U[1], U[2], U[4], U[5], U[6], U[8], U[9], U[10]};
+#pragma unroll
+                for (int r = 0; r < 3; ++r)
+#pragma unroll
+                    for (int c = 0; c < 3; ++c)
+                        tmp[3 * r + c] = dot3(R[3 * r], R[3 * r + 1], R[3 * r + 2], C[c], C[3 + c], C[6 + c]);
+#pragma unroll
+                for (int r = 0; r < 3; ++r)
+#pragma unroll
+                    for (int c = 0; c < 3; ++c)
+                        Cs[3 * r + c] = dot3(tmp[3 * r], tmp[3 * r + 1], tmp[3 * r + 2], R[3 * c], R[3 * c + 1], R[3 * c + 2]);
+                if (!a.step_mode)
+#pragma unroll
+                    for (int r = 0; r < 3; ++r)
+                        a.src_cov[(size_t)r * a.n_pad + i] = make_float4(Cs[3 * r], Cs[3 * r + 1], Cs[3 * r + 2], 0.f);
+            } else {
+#pragma unroll
+                for (int r = 0; r < 9; ++r) Cs[r] = C[r];
+            }
+        }
+
+        // ---- SearchRadius(.., max_nn = 1) (registration.cu:47) ---------------------------
+        w.qx = s.x; w.qy = s.y; w.qz = s.z;
+        w.best = init;
+        if (a.prev && w.valid) {
+            // warm start: last iteration's match is a candidate like any other (same key
+            // arithmetic), so the result is unchanged; it only tightens the bounds early
+            const int pj = a.prev[i];
+            if (pj >= 0) {
+                const float d2p = dist2(s.x, s.y, s.z, a.tgt_xyz[3 * (size_t)pj], a.tgt_xyz[3 * (size_t)pj + 1],
+                                        a.tgt_xyz[3 * (size_t)pj + 2]);
+                const unsigned long long kp = ((unsigned long long)__float_as_uint(d2p) << 32) | (unsigned)pj;
+                if (kp < init) w.best = kp;
+            }
+        }
+        warp_update_bound(w);
+        if (!w.valid) w.best = init;
+        warp_query_box(w);
+        if (__any_sync(CPHB_FULL, w.valid)) warp_nn_search<TOP>(a.ix, w);
+        const bool found = w.valid && (w.best != init);
+        const unsigned j = (unsigned)(w.best & 0xffffffffull);
+        const float d2 = __uint_as_float((unsigned)(w.best >> 32));
+        if (a.prev && !a.step_mode) a.prev[i] = found ? (int)j : -1;
+        if (write_corr && w.valid) a.corr_index[orig] = found ? (int32_t)j : -1;
+        if (materialize) continue;  // fitness / rmse / T of this pose are already in the state
+
+        // ---- rows: J (6), r; staged as doubles, one row of 9 per lane ---------------------
+        float J[NROWS][6], r[NROWS];
+#pragma unroll
+        for (int q = 0; q < NROWS; ++q) {
+            r[q] = 0.f;
+#pragma unroll
+            for (int c = 0; c < 6; ++c) J[q][c] = 0.f;
+        }
+        if (found) {
+            TargetAttrs ta = {a.tgt_xyz, a.tgt_nrm, a.tgt_col, a.tgt_grad, a.tgt_cov, a.tgt_cov_col_major, a.sg, a.sp,
+                              a.src_nrm != nullptr, a.src_col != nullptr, a.src_cov != nullptr};
+            const float4 cs4 = (KIND == CPHB_EST_COLORED_ICP && a.src_col) ? a.src_col[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+            build_rows<KIND, NROWS>(ta, s.x, s.y, s.z, sn, cs4, Cs, j, J, r);
+        }
+        // stage + accumulate: lane L adds column pair (ca, cb) over the 32 staged rows, in row order
+        double acc = 0.0;
+#pragma unroll
+        for (int q = 0; q < NROWS; ++q) {
+            double *my = rows + lane * ROW_STRIDE;
+#pragma unroll
+            for (int c = 0; c < 6; ++c) my[c] = (double)J[q][c];
+            my[6] = (double)r[q];
+            my[7] = (q == 0 && found) ? (double)d2 : 0.0;
+            my[8] = (q == 0 && found) ? 1.0 : 0.0;
+            __syncwarp();
+#pragma unroll 8
+            for (int t = 0; t < 32; ++t) acc = fma(rows[t * ROW_STRIDE + ca], rows[t * ROW_STRIDE + cb], acc);
+            __syncwarp();
+        }
+        if (!((live >> lane) & 1u)) acc = 0.0;
+        a.tile_sums[(size_t)tile * 32 + lane] = acc;
     }
-    // stage + accumulate: lane L adds column pair (ca, cb) over the 32 staged rows, in row order
+}
+
+// Fixed-order grid sum of the tile sums, then (last block) the host-side part of the loop.
+// grid = R blocks; block b owns a contiguous chunk of tiles.
+#define ICP_REDUCE_BLOCK 256
+template <int KIND>
+__global__ void __launch_bounds__(ICP_REDUCE_BLOCK) icp_reduce_kernel(const __grid_constant__ IcpArgs a) {
+    __shared__ double s_acc[ICP_REDUCE_BLOCK / 32][32];
+    __shared__ unsigned s_last;
+    IcpState *st = a.st;
+    const int done = *(volatile int *)&st->done;
+    if (done == 2) return;
+    if (done == 1) {  // the search launch before this one only materialised correspondences
+        if (blockIdx.x == 0 && threadIdx.x == 0) { st->tile_counter = 0; st->done = 2; }
+        return;
+    }
+    const unsigned n_tiles = a.n_pad / 32;
+    const unsigned chunk = (n_tiles + gridDim.x - 1) / gridDim.x;
+    const unsigned t0 = blockIdx.x * chunk, t1 = min(n_tiles, t0 + chunk);
+    const int c = threadIdx.x & 31, g = threadIdx.x >> 5;
+    {
+        double t = 0.0;
+        for (unsigned k = t0 + g; k < t1; k += ICP_REDUCE_BLOCK / 32) t += __ldcg(&a.tile_sums[(size_t)k * 32 + c]);
+        s_acc[g][c] = t;
+    }
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        double t = 0.0;
+#pragma unroll
+        for (int k = 0; k < ICP_REDUCE_BLOCK / 32; ++k) t += s_acc[k][threadIdx.x];
+        a.partials[(size_t)blockIdx.x * 32 + threadIdx.x] = t;
+        __threadfence();
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned t = atomicAdd(&st->ticket, 1u);
+        s_last = (t == gridDim.x - 1) ? 1u : 0u;
+    }
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    if (threadIdx.x < 32) {
+        double t = 0.0;
+        for (unsigned b = 0; b < gridDim.x; ++b) t += __ldcg(&a.partials[(size_t)b * 32 + threadIdx.x]);
+        if (a.defer_finalize) st->local[threadIdx.x] = t;
+        else st->total[threadIdx.x] = t;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        st->ticket = 0;
+        st->tile_counter = 0;
+        if (!a.defer_finalize) icp_finalize<KIND>(a, st);
+        __threadfence();
+    }
+}
+
+// multi-GPU: runs after the all-reduce of st->local into st->total
+template <int KIND>
+__global__ void icp_finalize_kernel(const __grid_constant__ IcpArgs a) {
+    if (threadIdx.x == 0 && a.st->done != 2) icp_finalize<KIND>(a, a.st);
+}
+
+// ---------------------------------------------------------------------------
+// TransformationEstimation*::ComputeTransformation / ComputeRMSE on an explicit
+// correspondence list (transformation_estimation.cu:92-350, generalized_icp.cu:112-183,
+// colored_icp.cu:218-327, kabsch.cu:42-120): same rows and reduction as the fused kernel,
+// one thread per correspondence, packed (original-order) source attributes.
+// ---------------------------------------------------------------------------
+struct EstArgs {
+    TargetAttrs ta;
+    const float *src_xyz, *src_nrm, *src_col, *src_cov;
+    int src_cov_col_major;
+    const int32_t *corr;
+    unsigned n_corr;
+    double *partials;
+    double *total;     // [32]
+    unsigned *ticket;
+};
+template <int KIND>
+__global__ void __launch_bounds__(ICP_BLOCK) estimate_kernel(const __grid_constant__ EstArgs a) {
+    __shared__ double s_rows[ICP_WARPS][32 * ROW_STRIDE];
+    __shared__ double s_acc[ICP_WARPS][32];
+    __shared__ unsigned s_last;
+    const int warp = threadIdx.x >> 5, lane = lane_id();
+    const unsigned c = blockIdx.x * ICP_BLOCK + threadIdx.x;
+    const bool valid = c < a.n_corr;
+    constexpr int NROWS = (KIND == CPHB_EST_COLORED_ICP) ? 2 : (KIND == CPHB_EST_GENERALIZED_ICP) ? 3 : 1;
+    float J[NROWS][6], r[NROWS];
+#pragma unroll
+    for (int q = 0; q < NROWS; ++q) {
+        r[q] = 0.f;
+#pragma unroll
+        for (int k = 0; k < 6; ++k) J[q][k] = 0.f;
+    }
+    float term = 0.f;  // per-kind ComputeRMSE summand
+    if (valid) {
+        const size_t i = (size_t)a.corr[2 * (size_t)c];
+        const unsigned j = (unsigned)a.corr[2 * (size_t)c + 1];
+        const float vs[3] = {a.src_xyz[3 * i], a.src_xyz[3 * i + 1], a.src_xyz[3 * i + 2]};
+        float sn[3] = {0.f, 0.f, 0.f}, Cs[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+        float4 cs4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (KIND == CPHB_EST_SYMMETRIC && a.src_nrm) { sn[0] = a.src_nrm[3 * i]; sn[1] = a.src_nrm[3 * i + 1]; sn[2] = a.src_nrm[3 * i + 2]; }
+        if (KIND == CPHB_EST_COLORED_ICP && a.src_col) cs4 = make_float4(a.src_col[3 * i], a.src_col[3 * i + 1], a.src_col[3 * i + 2], 0.f);
+        if (KIND == CPHB_EST_GENERALIZED_ICP && a.src_cov)
+#pragma unroll
+            for (int p = 0; p < 3; ++p)
+#pragma unroll
+                for (int q = 0; q < 3; ++q) Cs[3 * p + q] = a.src_cov[9 * i + (a.src_cov_col_major ? 3 * q + p : 3 * p + q)];
+        build_rows<KIND, NROWS>(a.ta, vs[0], vs[1], vs[2], sn, cs4, Cs, j, J, r);
+        const float vt[3] = {a.ta.tgt_xyz[3 * (size_t)j], a.ta.tgt_xyz[3 * (size_t)j + 1], a.ta.tgt_xyz[3 * (size_t)j + 2]};
+        if (KIND == CPHB_EST_POINT_TO_POINT) {
+            term = dist2(vs[0], vs[1], vs[2], vt[0], vt[1], vt[2]);  // (lhs - rhs).squaredNorm()
+        } else if (KIND == CPHB_EST_SYMMETRIC) {
+            const float e = r[0] * r[0];  // ComputeErrorUsingNormals returns the squared residual ...
+            term = e * e;                 // ... which the caller squares again (transformation_estimation.cu:283-286)
+        } else if (KIND == CPHB_EST_GENERALIZED_ICP) {
+            // d^T W d with W = sqrt((Ct+Cs)^-1)  (generalized_icp.cu:121-130): rows hold W_i and r_i = W_i . d
+            const float d[3] = {vs[0] - vt[0], vs[1] - vt[1], vs[2] - vt[2]};
+            term = dot3(d[0], d[1], d[2], r[0], r[1 % NROWS], r[2 % NROWS]);
+        }
+    }
+    double *rows = s_rows[warp];
+    const unsigned char(*pair)[2] = (KIND == CPHB_EST_POINT_TO_POINT) ? c_pair_p2p : c_pair_jtj;
+    const int ca = pair[lane][0], cb = pair[lane][1];
+    double acc = 0.0;
 #pragma unroll
     for (int q = 0; q < NROWS; ++q) {
         double *my = rows + lane * ROW_STRIDE;
 #pragma unroll
-        for (int c = 0; c < 6; ++c) my[c] = (double)J[q][c];
+        for (int k = 0; k < 6; ++k) my[k] = (double)J[q][k];
         my[6] = (double)r[q];
-        my[7] = (q == 0 && use) ? (double)d2 : 0.0;
-        my[8] = (q == 0 && use) ? 1.0 : 0.0;
+        my[7] = (q == 0 && valid) ? (double)term : 0.0;
+        my[8] = (q == 0 && valid) ? 1.0 : 0.0;
         __syncwarp();
 #pragma unroll 8
         for (int t = 0; t < 32; ++t) acc = fma(rows[t * ROW_STRIDE + ca], rows[t * ROW_STRIDE + cb], acc);
@@ -552,8 +731,6 @@ __global__ void __launch_bounds__(ICP_BLOCK) icp_iteration_kernel(const __grid_c
         const unsigned live = (KIND == CPHB_EST_POINT_TO_POINT) ? c_live_p2p : c_live_jtj;
         if (!((live >> lane) & 1u)) acc = 0.0;
     }
-
-    // ---- block sum (fixed order) -> partials[block][32] ---------------------------------
     s_acc[warp][lane] = acc;
     __syncthreads();
     if (threadIdx.x < 32) {
@@ -565,40 +742,50 @@ __global__ void __launch_bounds__(ICP_BLOCK) icp_iteration_kernel(const __grid_c
     }
     __syncthreads();
     if (threadIdx.x == 0) {
-        unsigned t = atomicAdd(&st->ticket, 1u);
+        unsigned t = atomicAdd(a.ticket, 1u);
         s_last = (t == gridDim.x - 1) ? 1u : 0u;
     }
     __syncthreads();
     if (!s_last) return;
-
-    // ---- last block: grid sum in block order, then the host-side part of the loop ---------
     __threadfence();
     {
-        const int c = threadIdx.x & 31, g = threadIdx.x >> 5;
+        const int col = threadIdx.x & 31, g = threadIdx.x >> 5;
         double t = 0.0;
-        for (unsigned b = g; b < gridDim.x; b += ICP_WARPS) t += __ldcg(&a.partials[(size_t)b * 32 + c]);
-        s_acc[g][c] = t;
+        for (unsigned b = g; b < gridDim.x; b += ICP_WARPS) t += __ldcg(&a.partials[(size_t)b * 32 + col]);
+        s_acc[g][col] = t;
     }
     __syncthreads();
     if (threadIdx.x < 32) {
         double t = 0.0;
 #pragma unroll
         for (int k = 0; k < ICP_WARPS; ++k) t += s_acc[k][threadIdx.x];
-        if (a.defer_finalize) st->local[threadIdx.x] = t;
-        else st->total[threadIdx.x] = t;
+        a.total[threadIdx.x] = t;
     }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        st->ticket = 0;
-        if (!a.defer_finalize) icp_finalize<KIND>(a, st);
-        __threadfence();
-    }
+    if (threadIdx.x == 0) *a.ticket = 0;
 }
-
-// multi-GPU: runs after the all-reduce of st->local into st->total
+// sums -> 4x4 (one thread)
 template <int KIND>
-__global__ void icp_finalize_kernel(const __grid_constant__ IcpArgs a) {
-    if (threadIdx.x == 0 && a.st->done != 2) icp_finalize<KIND>(a, a.st);
+__global__ void estimate_solve_kernel(const double *S, unsigned long long n_model, float det_thresh, int have, float *T_out) {
+    if (threadIdx.x != 0) return;
+    float T[16];
+    identity4(T);
+    if (S[29] > 0 && have) {
+        if (KIND == CPHB_EST_POINT_TO_POINT) kabsch_from_sums(S, n_model, T);
+        else {
+            bool ok = solve_jtj(S, (KIND == CPHB_EST_GENERALIZED_ICP) ? -1.f : det_thresh, T);
+            if (ok && KIND == CPHB_EST_SYMMETRIC) {
+                double R[9], R2[9];
+                for (int i = 0; i < 3; ++i)
+                    for (int j = 0; j < 3; ++j) R[3 * i + j] = (double)T[4 * i + j];
+                for (int i = 0; i < 3; ++i)
+                    for (int j = 0; j < 3; ++j)
+                        R2[3 * i + j] = R[3 * i] * R[j] + R[3 * i + 1] * R[3 + j] + R[3 * i + 2] * R[6 + j];
+                for (int i = 0; i < 3; ++i)
+                    for (int j = 0; j < 3; ++j) T[4 * i + j] = (float)R2[3 * i + j];
+            }
+        }
+    }
+    for (int i = 0; i < 16; ++i) T_out[i] = T[i];
 }
 
 // ---------------------------------------------------------------------------
@@ -772,7 +959,9 @@ struct cphb_icp {
     int32_t *corr_index;
     unsigned *cmp_counts;
     unsigned *cmp_total;
-    unsigned grid;
+    double *tile_sums;
+    int *prev;
+    unsigned grid, reduce_grid;
     cudaStream_t stream;
 };
 
@@ -788,8 +977,9 @@ static bool is_identity4(const float *T) {  // Eigen isIdentity(1e-5), registrat
 
 template <int KIND>
 static void launch_iteration(const cphb_icp *icp, const IcpArgs &a, cudaStream_t s) {
-    if (icp->index->v.top <= 3) CPHB_LAUNCH((icp_iteration_kernel<KIND, 3>), icp->grid, ICP_BLOCK, 0, s, a);
-    else CPHB_LAUNCH((icp_iteration_kernel<KIND, 5>), icp->grid, ICP_BLOCK, 0, s, a);
+    if (icp->index->v.top <= 3) CPHB_LAUNCH((icp_iteration_kernel<KIND, 3>), icp->grid, ICP_SEARCH_WARPS * 32, 0, s, a);
+    else CPHB_LAUNCH((icp_iteration_kernel<KIND, 5>), icp->grid, ICP_SEARCH_WARPS * 32, 0, s, a);
+    CPHB_LAUNCH(icp_reduce_kernel<KIND>, icp->reduce_grid, ICP_REDUCE_BLOCK, 0, s, a);
 }
 static void launch_iteration_kind(const cphb_icp *icp, const IcpArgs &a, cudaStream_t s) {
     switch (icp->prm.estimation) {
@@ -837,7 +1027,17 @@ extern "C" int cphb_icp_create(const cphb_cloud *source, const cphb_cloud *targe
     const unsigned n_pad = (unsigned)cphb_align(n ? n : 1, ICP_BLOCK);
     icp->n_src = n;
     icp->n_pad = n_pad;
-    icp->grid = n_pad / ICP_BLOCK;
+    {
+        int dev = 0, sms = 148;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        const unsigned n_tiles = n_pad / 32;
+        unsigned want = (n_tiles + ICP_SEARCH_WARPS - 1) / ICP_SEARCH_WARPS;
+        unsigned cap = (unsigned)sms * 8u;  // 8 blocks x 4 warps = 32 resident warps / SM
+        icp->grid = want < cap ? want : cap;
+        unsigned rg = (n_tiles + 63) / 64;
+        icp->reduce_grid = rg < 1 ? 1 : (rg > (unsigned)sms ? (unsigned)sms : rg);
+    }
     const bool want_nrm = params->estimation == CPHB_EST_SYMMETRIC && source->normals;
     const bool want_col = params->estimation == CPHB_EST_COLORED_ICP && source->colors;
     const bool want_cov = params->estimation == CPHB_EST_GENERALIZED_ICP && source->covariances;
@@ -848,7 +1048,9 @@ extern "C" int cphb_icp_create(const cphb_cloud *source, const cphb_cloud *targe
     size_t o_pcov = want_cov ? take(sizeof(float4) * 3 * n_pad) : 0, o_wcov = want_cov ? take(sizeof(float4) * 3 * n_pad) : 0;
     size_t o_col = want_col ? take(sizeof(float4) * n_pad) : 0;
     size_t o_st = take(sizeof(IcpState));
-    size_t o_part = take(sizeof(double) * 32 * icp->grid);
+    size_t o_part = take(sizeof(double) * 32 * icp->reduce_grid);
+    size_t o_ts = take(sizeof(double) * n_pad);
+    size_t o_prev = take(sizeof(int) * n_pad);
     size_t o_ci = take(sizeof(int32_t) * n_pad);
     unsigned cmp_blocks = (n_pad + CMP_BLOCK - 1) / CMP_BLOCK;
     size_t o_cc = take(sizeof(unsigned) * (cmp_blocks + 1));
@@ -867,6 +1069,8 @@ extern "C" int cphb_icp_create(const cphb_cloud *source, const cphb_cloud *targe
     icp->src_col = want_col ? (float4 *)(b + o_col) : nullptr;
     icp->st = (IcpState *)(b + o_st);
     icp->partials = (double *)(b + o_part);
+    icp->tile_sums = (double *)(b + o_ts);
+    icp->prev = (int *)(b + o_prev);
     icp->corr_index = (int32_t *)(b + o_ci);
     icp->cmp_counts = (unsigned *)(b + o_cc);
     icp->cmp_total = (unsigned *)(b + o_ct);
@@ -911,6 +1115,8 @@ static void fill_args(const cphb_icp *icp, IcpArgs &a) {
     a.tgt_cov_col_major = icp->tgt.cov_col_major;
     a.st = icp->st;
     a.partials = icp->partials;
+    a.tile_sums = icp->tile_sums;
+    a.prev = icp->prev;
     a.n_src = icp->n_src;
     a.n_pad = icp->n_pad;
     a.n_total = icp->n_src;
@@ -928,6 +1134,7 @@ static void fill_args(const cphb_icp *icp, IcpArgs &a) {
 }
 
 static int reset_working_copy(cphb_icp *icp, cudaStream_t s) {
+    CPHB_CUDA(cudaMemsetAsync(icp->prev, 0xff, sizeof(int) * icp->n_pad, s));  // no warm start at launch 0
     CPHB_CUDA(cudaMemcpyAsync(icp->work_xyz, icp->pristine_xyz, sizeof(float4) * icp->n_pad, cudaMemcpyDeviceToDevice, s));
     if (icp->work_nrm)
         CPHB_CUDA(cudaMemcpyAsync(icp->work_nrm, icp->pristine_nrm, sizeof(float4) * icp->n_pad, cudaMemcpyDeviceToDevice, s));
@@ -1079,4 +1286,122 @@ extern "C" int cphb_transform(float *points, float *normals, float *covariances,
     CPHB_CHECK_LAUNCH();
     cphb_free_async(Td, s);
     return CPHB_OK;
+}
+
+// ---------------------------------------------------------------------------
+// standalone estimator entry points
+// ---------------------------------------------------------------------------
+static int run_estimate(int estimation, const cphb_cloud *source, const cphb_cloud *target, const int32_t *corr,
+                        size_t n_corr, const cphb_icp_params *params, double h_S[32], float h_T[16], cudaStream_t s) {
+    if (!source || !target || (n_corr && !corr)) {
+        cphb_set_error("estimate: null argument");
+        return CPHB_ERR_INVALID;
+    }
+    if (estimation < CPHB_EST_POINT_TO_POINT || estimation > CPHB_EST_GENERALIZED_ICP) {
+        cphb_set_error("estimate: estimation %d unsupported", estimation);
+        return CPHB_ERR_UNSUPPORTED;
+    }
+    for (int i = 0; i < 32; ++i) h_S[i] = 0.0;
+    if (h_T) for (int i = 0; i < 16; ++i) h_T[i] = (i % 5 == 0) ? 1.f : 0.f;
+    if (n_corr == 0) return CPHB_OK;
+    EstArgs a;
+    memset(&a, 0, sizeof(a));
+    float lg = params ? params->lambda_geometric : 0.968f;
+    if (lg < 0.f || lg > 1.0f) lg = 0.968f;
+    a.ta.tgt_xyz = target->points; a.ta.tgt_nrm = target->normals; a.ta.tgt_col = target->colors;
+    a.ta.tgt_grad = target->color_gradient; a.ta.tgt_cov = target->covariances;
+    a.ta.tgt_cov_col_major = target->cov_col_major;
+    a.ta.sg = (float)sqrt((double)lg);
+    a.ta.sp = (float)sqrt((double)(float)(1.0 - (double)lg));
+    a.ta.src_nrm = source->normals != nullptr; a.ta.src_col = source->colors != nullptr;
+    a.ta.src_cov = source->covariances != nullptr;
+    a.src_xyz = source->points; a.src_nrm = source->normals; a.src_col = source->colors;
+    a.src_cov = source->covariances; a.src_cov_col_major = source->cov_col_major;
+    a.corr = corr;
+    a.n_corr = (unsigned)n_corr;
+    unsigned grid = (unsigned)((n_corr + ICP_BLOCK - 1) / ICP_BLOCK);
+    char *buf = nullptr;
+    size_t bytes = cphb_align(sizeof(double) * 32 * grid, 256) + 256 + 256 + 64;
+    int rc = cphb_alloc_async((void **)&buf, bytes, s);
+    if (rc) return rc;
+    a.partials = (double *)buf;
+    a.total = (double *)(buf + cphb_align(sizeof(double) * 32 * grid, 256));
+    a.ticket = (unsigned *)((char *)a.total + 256);
+    float *Td = (float *)((char *)a.total + 512);
+    CPHB_CUDA(cudaMemsetAsync(a.ticket, 0, 4, s));
+    bool have = true;
+    switch (estimation) {
+        case CPHB_EST_POINT_TO_POINT: CPHB_LAUNCH(estimate_kernel<CPHB_EST_POINT_TO_POINT>, grid, ICP_BLOCK, 0, s, a); break;
+        case CPHB_EST_POINT_TO_PLANE: have = target->normals; CPHB_LAUNCH(estimate_kernel<CPHB_EST_POINT_TO_PLANE>, grid, ICP_BLOCK, 0, s, a); break;
+        case CPHB_EST_SYMMETRIC: have = target->normals && source->normals; CPHB_LAUNCH(estimate_kernel<CPHB_EST_SYMMETRIC>, grid, ICP_BLOCK, 0, s, a); break;
+        case CPHB_EST_COLORED_ICP: have = target->normals && target->colors && source->colors; CPHB_LAUNCH(estimate_kernel<CPHB_EST_COLORED_ICP>, grid, ICP_BLOCK, 0, s, a); break;
+        case CPHB_EST_GENERALIZED_ICP: have = target->covariances && source->covariances; CPHB_LAUNCH(estimate_kernel<CPHB_EST_GENERALIZED_ICP>, grid, ICP_BLOCK, 0, s, a); break;
+    }
+    if (h_T) {
+        float dt = params ? params->det_thresh : 1e-6f;
+        unsigned long long nm = source->n;
+        switch (estimation) {
+            case CPHB_EST_POINT_TO_POINT: CPHB_LAUNCH(estimate_solve_kernel<CPHB_EST_POINT_TO_POINT>, 1, 32, 0, s, a.total, nm, dt, have, Td); break;
+            case CPHB_EST_POINT_TO_PLANE: CPHB_LAUNCH(estimate_solve_kernel<CPHB_EST_POINT_TO_PLANE>, 1, 32, 0, s, a.total, nm, dt, have, Td); break;
+            case CPHB_EST_SYMMETRIC: CPHB_LAUNCH(estimate_solve_kernel<CPHB_EST_SYMMETRIC>, 1, 32, 0, s, a.total, nm, dt, have, Td); break;
+            case CPHB_EST_COLORED_ICP: CPHB_LAUNCH(estimate_solve_kernel<CPHB_EST_COLORED_ICP>, 1, 32, 0, s, a.total, nm, dt, have, Td); break;
+            case CPHB_EST_GENERALIZED_ICP: CPHB_LAUNCH(estimate_solve_kernel<CPHB_EST_GENERALIZED_ICP>, 1, 32, 0, s, a.total, nm, dt, have, Td); break;
+        }
+        CPHB_CUDA(cudaMemcpyAsync(h_T, Td, 64, cudaMemcpyDeviceToHost, s));
+    }
+    CPHB_CHECK_LAUNCH();
+    CPHB_CUDA(cudaMemcpyAsync(h_S, a.total, sizeof(double) * 32, cudaMemcpyDeviceToHost, s));
+    CPHB_CUDA(cudaStreamSynchronize(s));
+    cphb_free_async(buf, s);
+    return CPHB_OK;
+}
+
+extern "C" int cphb_compute_transformation(int estimation, const cphb_cloud *source, const cphb_cloud *target,
+                                           const int32_t *corr, size_t n_corr, const cphb_icp_params *params,
+                                           float h_T[16], void *stream) {
+    double S[32];
+    return run_estimate(estimation, source, target, corr, n_corr, params, S, h_T, (cudaStream_t)stream);
+}
+
+extern "C" int cphb_compute_rmse(int estimation, const cphb_cloud *source, const cphb_cloud *target, const int32_t *corr,
+                                 size_t n_corr, const cphb_icp_params *params, float *h_rmse, void *stream) {
+    double S[32];
+    *h_rmse = 0.f;
+    int rc = run_estimate(estimation, source, target, corr, n_corr, params, S, nullptr, (cudaStream_t)stream);
+    if (rc || n_corr == 0) return rc;
+    const float C = (float)n_corr;
+    switch (estimation) {
+        case CPHB_EST_POINT_TO_POINT: *h_rmse = sqrtf((float)S[28] / C); break;                      // transformation_estimation.cu:92-116
+        case CPHB_EST_POINT_TO_PLANE: *h_rmse = target->normals ? sqrtf((float)S[27] / C) : 0.f; break;  // :118-166
+        case CPHB_EST_SYMMETRIC: *h_rmse = (target->normals && source->normals) ? sqrtf((float)S[28] / C) : 0.f; break;  // :224-287
+        case CPHB_EST_GENERALIZED_ICP: *h_rmse = sqrtf((float)S[28] / C); break;                     // generalized_icp.cu:134-151
+        case CPHB_EST_COLORED_ICP: *h_rmse = (float)S[27]; break;  // colored_icp.cu:303-327 returns the plain sum (quirk)
+    }
+    return CPHB_OK;
+}
+
+// registration::Kabsch(model, target[, corres]) (kabsch.h:30-49); corr == NULL pairs i<->i
+__global__ void __launch_bounds__(256) iota_pairs_kernel(int32_t *p, unsigned n) {
+    unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) { p[2 * (size_t)i] = (int32_t)i; p[2 * (size_t)i + 1] = (int32_t)i; }
+}
+extern "C" int cphb_kabsch(const float *model, size_t n_model, const float *target, const int32_t *corr, size_t n_corr,
+                           float h_T[16], void *stream) {
+    cudaStream_t s = (cudaStream_t)stream;
+    cphb_cloud src, tgt;
+    memset(&src, 0, sizeof(src));
+    memset(&tgt, 0, sizeof(tgt));
+    src.points = model; src.n = n_model;
+    tgt.points = target; tgt.n = n_model;
+    int32_t *tmp = nullptr;
+    if (!corr) {
+        n_corr = n_model;
+        int rc = cphb_alloc_async((void **)&tmp, sizeof(int32_t) * 2 * (n_model ? n_model : 1), s);
+        if (rc) return rc;
+        if (n_model) CPHB_LAUNCH(iota_pairs_kernel, (unsigned)((n_model + 255) / 256), 256, 0, s, tmp, (unsigned)n_model);
+        corr = tmp;
+    }
+    int rc = cphb_compute_transformation(CPHB_EST_POINT_TO_POINT, &src, &tgt, corr, n_corr, nullptr, h_T, stream);
+    cphb_free_async(tmp, s);
+    return rc;
 }

@@ -17,25 +17,18 @@
 // key = (d2 bits, index).  Mirrors KnnRadiusResultSet (result_set.h:372-474):
 // strict d2 < r2, unfilled slots idx=-1 / d2=+inf.
 // ---------------------------------------------------------------------------
-struct WarpSearchK {
-    float qx, qy, qz;
-    float wlo[3], whi[3];
-    unsigned bound;
-    unsigned phase;
-    bool valid;
-    float4 *tile;
-    uint64_t *bar;
+struct WarpSearchK : WarpSearchBase {
     unsigned long long *list;  // this lane's column
     int k;
     unsigned long long worst;  // == list[(k-1)*32]
+    __device__ __forceinline__ unsigned lane_bound() const { return (unsigned)(worst >> 32); }
 };
 
-__device__ __forceinline__ void scan_leaf(const IndexView &ix, unsigned leaf, WarpSearchK &w) {
-    fetch_leaf(ix, leaf, w);
+__device__ __forceinline__ void scan_tile(const float4 *tile, WarpSearchK &w) {
     const int k = w.k;
 #pragma unroll 4
     for (int j = 0; j < CPHB_LEAF; ++j) {
-        float4 p = w.tile[j];
+        float4 p = tile[j];
         float d2 = dist2(w.qx, w.qy, w.qz, p.x, p.y, p.z);
         unsigned long long key = ((unsigned long long)__float_as_uint(d2) << 32) | __float_as_uint(p.w);
         if (key < w.worst) {
@@ -50,8 +43,6 @@ __device__ __forceinline__ void scan_leaf(const IndexView &ix, unsigned leaf, Wa
             w.worst = w.list[(k - 1) * 32];
         }
     }
-    __syncwarp();
-    w.bound = __reduce_max_sync(CPHB_FULL, w.valid ? (unsigned)(w.worst >> 32) : 0u);
 }
 
 template <int TOP>
@@ -59,11 +50,11 @@ __global__ void __launch_bounds__(256) search1_kernel(IndexView ix, const float 
                                                       const uint32_t *__restrict__ perm, size_t nq, float r2,
                                                       int32_t *__restrict__ out_idx, float *__restrict__ out_d2,
                                                       unsigned long long *count) {
-    __shared__ __align__(16) float4 s_tile[8][CPHB_LEAF];
-    __shared__ uint64_t s_bar[8];
+    __shared__ __align__(16) float4 s_tile[8][2 * CPHB_LEAF];
+    __shared__ uint64_t s_bar[8][2];
     const int warp = threadIdx.x >> 5;
     WarpSearch w;
-    warp_search_setup(w, s_tile[warp], &s_bar[warp]);
+    warp_search_setup(w, s_tile[warp], s_bar[warp]);
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     w.valid = i < nq;
     size_t pos = 0;
@@ -96,10 +87,10 @@ __global__ void searchk_kernel(IndexView ix, const float *__restrict__ qxyz, con
     const int nwarp = blockDim.x >> 5;
     const int warp = threadIdx.x >> 5;
     float4 *tiles = (float4 *)smem;
-    uint64_t *bars = (uint64_t *)(tiles + (size_t)nwarp * CPHB_LEAF);
-    unsigned long long *lists = (unsigned long long *)(bars + nwarp);
+    uint64_t *bars = (uint64_t *)(tiles + (size_t)nwarp * 2 * CPHB_LEAF);
+    unsigned long long *lists = (unsigned long long *)(bars + 2 * nwarp);
     WarpSearchK w;
-    warp_search_setup(w, tiles + (size_t)warp * CPHB_LEAF, &bars[warp]);
+    warp_search_setup(w, tiles + (size_t)warp * 2 * CPHB_LEAF, bars + 2 * warp);
     w.k = k;
     w.list = lists + (size_t)warp * k * 32 + lane_id();
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -175,7 +166,7 @@ static int search_impl(const cphb_index *index, const float *query, size_t nq, f
         else
             CPHB_LAUNCH(search1_kernel<5>, grid, 256, 0, s, index->v, query, perm, nq, r2, idx, d2, count);
     } else {
-        size_t per_warp = CPHB_LEAF * sizeof(float4) + sizeof(uint64_t) + (size_t)k * 32 * sizeof(unsigned long long);
+        size_t per_warp = 2 * CPHB_LEAF * sizeof(float4) + 2 * sizeof(uint64_t) + (size_t)k * 32 * sizeof(unsigned long long);
         int warps = (int)((96 * 1024) / per_warp);
         if (warps > 8) warps = 8;
         if (warps < 1) warps = 1;

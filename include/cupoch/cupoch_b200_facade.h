@@ -1,0 +1,570 @@
+// cupoch_b200_facade.h -- header-only C++17 facade that reproduces the cupoch
+// classes on the ICP / kNN / voxel-grid path on top of the C ABI
+// (include/cupoch_b200.h).  Names, argument meaning and error behaviour follow
+// the reference headers cited at each declaration; no thrust, no CUDA headers.
+//
+// Eigen: used when available (cupoch's API types are Eigen's); otherwise
+// layout-compatible PODs are declared in namespace Eigen so that the facade
+// still builds where Eigen is absent (it is absent in the build container).
+#pragma once
+#include <cmath>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <memory>
+#include <stdexcept>
+#include <tuple>
+#include <vector>
+
+#include "cupoch_b200.h"
+
+#if __has_include(<Eigen/Core>)
+#include <Eigen/Core>
+namespace Eigen {
+typedef Matrix<float, 4, 4, DontAlign> Matrix4f_u;
+}
+#else
+namespace Eigen {
+struct Vector3f {
+    float v[3];
+    Vector3f() : v{0, 0, 0} {}
+    Vector3f(float x, float y, float z) : v{x, y, z} {}
+    float &operator[](int i) { return v[i]; }
+    float operator[](int i) const { return v[i]; }
+    float &operator()(int i) { return v[i]; }
+    float operator()(int i) const { return v[i]; }
+    static Vector3f Zero() { return Vector3f(); }
+};
+struct Vector2i {
+    int v[2];
+    Vector2i() : v{0, 0} {}
+    Vector2i(int a, int b) : v{a, b} {}
+    int &operator[](int i) { return v[i]; }
+    int operator[](int i) const { return v[i]; }
+};
+struct Matrix3f {  // column-major like Eigen's default
+    float m[9];
+    Matrix3f() : m{0, 0, 0, 0, 0, 0, 0, 0, 0} {}
+    float &operator()(int r, int c) { return m[3 * c + r]; }
+    float operator()(int r, int c) const { return m[3 * c + r]; }
+};
+struct Matrix4f {  // column-major
+    float m[16];
+    Matrix4f() { std::memset(m, 0, sizeof(m)); }
+    float &operator()(int r, int c) { return m[4 * c + r]; }
+    float operator()(int r, int c) const { return m[4 * c + r]; }
+    static Matrix4f Identity() {
+        Matrix4f I;
+        for (int i = 0; i < 4; ++i) I(i, i) = 1.f;
+        return I;
+    }
+    bool isIdentity(float prec = 1e-5f) const {
+        for (int r = 0; r < 4; ++r)
+            for (int c = 0; c < 4; ++c)
+                if (std::fabs((*this)(r, c) - (r == c ? 1.f : 0.f)) > prec) return false;
+        return true;
+    }
+    Matrix4f operator*(const Matrix4f &o) const {
+        Matrix4f R;
+        for (int r = 0; r < 4; ++r)
+            for (int c = 0; c < 4; ++c)
+                R(r, c) = (((*this)(r, 0) * o(0, c) + (*this)(r, 1) * o(1, c)) + (*this)(r, 2) * o(2, c)) + (*this)(r, 3) * o(3, c);
+        return R;
+    }
+};
+typedef Matrix4f Matrix4f_u;
+}  // namespace Eigen
+#endif
+
+namespace cupoch {
+namespace utility {
+
+inline void LogError(const char *msg) { std::fprintf(stderr, "[cupoch_b200][error] %s\n", msg); }
+inline void LogWarning(const char *msg) { std::fprintf(stderr, "[cupoch_b200][warning] %s\n", msg); }
+inline void check(int rc) {
+    if (rc != CPHB_OK) throw std::runtime_error(std::string("cupoch_b200: ") + cphb_last_error());
+}
+
+/// RAII device array (stands in for rmm/thrust device_vector, device_vector.h:67-105).
+template <typename T>
+class device_vector {
+public:
+    device_vector() {}
+    explicit device_vector(size_t n) { resize(n); }
+    device_vector(const std::vector<T> &h) { *this = h; }
+    device_vector(const device_vector &o) { copy_from(o); }
+    device_vector(device_vector &&o) noexcept : p_(o.p_), n_(o.n_), cap_(o.cap_) { o.p_ = nullptr; o.n_ = o.cap_ = 0; }
+    ~device_vector() { cphb_free(p_); }
+    device_vector &operator=(const device_vector &o) { if (this != &o) copy_from(o); return *this; }
+    device_vector &operator=(device_vector &&o) noexcept {
+        if (this != &o) { cphb_free(p_); p_ = o.p_; n_ = o.n_; cap_ = o.cap_; o.p_ = nullptr; o.n_ = o.cap_ = 0; }
+        return *this;
+    }
+    device_vector &operator=(const std::vector<T> &h) {
+        resize(h.size());
+        if (n_) { check(cphb_memcpy_h2d(p_, h.data(), n_ * sizeof(T), nullptr)); check(cphb_stream_synchronize(nullptr)); }
+        return *this;
+    }
+    void resize(size_t n) {
+        if (n > cap_) {
+            T *q = static_cast<T *>(cphb_malloc(n * sizeof(T)));
+            if (!q) check(CPHB_ERR_CUDA);
+            if (n_) check(cphb_memcpy_d2d(q, p_, n_ * sizeof(T), nullptr));
+            check(cphb_stream_synchronize(nullptr));
+            cphb_free(p_);
+            p_ = q;
+            cap_ = n;
+        }
+        n_ = n;
+    }
+    void clear() { n_ = 0; }
+    size_t size() const { return n_; }
+    bool empty() const { return n_ == 0; }
+    T *data() { return p_; }
+    const T *data() const { return p_; }
+    std::vector<T> to_host() const {
+        std::vector<T> h(n_);
+        if (n_) { check(cphb_memcpy_d2h(h.data(), p_, n_ * sizeof(T), nullptr)); check(cphb_stream_synchronize(nullptr)); }
+        return h;
+    }
+
+private:
+    void copy_from(const device_vector &o) {
+        resize(o.n_);
+        if (n_) { check(cphb_memcpy_d2d(p_, o.p_, n_ * sizeof(T), nullptr)); check(cphb_stream_synchronize(nullptr)); }
+    }
+    T *p_ = nullptr;
+    size_t n_ = 0, cap_ = 0;
+};
+
+inline void to_row_major(const Eigen::Matrix4f &M, float out[16]) {
+    for (int r = 0; r < 4; ++r)
+        for (int c = 0; c < 4; ++c) out[4 * r + c] = M(r, c);
+}
+inline Eigen::Matrix4f from_row_major(const float in[16]) {
+    Eigen::Matrix4f M;
+    for (int r = 0; r < 4; ++r)
+        for (int c = 0; c < 4; ++c) M(r, c) = in[4 * r + c];
+    return M;
+}
+}  // namespace utility
+
+// --------------------------------------------------------------------------- knn
+namespace knn {
+static const int NUM_MAX_NN = 100;  // kdtree_search_param.h:26
+
+class KDTreeSearchParam {  // kdtree_search_param.h:28-66
+public:
+    enum class SearchType { Knn = 0, Radius = 1 };
+    virtual ~KDTreeSearchParam() {}
+    SearchType GetSearchType() const { return search_type_; }
+
+protected:
+    KDTreeSearchParam(SearchType t) : search_type_(t) {}
+
+private:
+    SearchType search_type_;
+};
+class KDTreeSearchParamKNN : public KDTreeSearchParam {
+public:
+    KDTreeSearchParamKNN(int knn = 30) : KDTreeSearchParam(SearchType::Knn), knn_(knn) {}
+    int knn_;
+};
+class KDTreeSearchParamRadius : public KDTreeSearchParam {
+public:
+    KDTreeSearchParamRadius(float radius, int max_nn) : KDTreeSearchParam(SearchType::Radius), radius_(radius), max_nn_(max_nn) {}
+    float radius_;
+    int max_nn_;
+};
+
+/// knn::KDTreeFlann (kdtree_flann.h:43-124).  Non-copyable; copies the data like the reference.
+class KDTreeFlann {
+public:
+    KDTreeFlann() {}
+    KDTreeFlann(const utility::device_vector<Eigen::Vector3f> &data) { SetRawData(data); }
+    ~KDTreeFlann() { release(); }
+    KDTreeFlann(const KDTreeFlann &) = delete;
+    KDTreeFlann &operator=(const KDTreeFlann &) = delete;
+
+    bool SetRawData(const utility::device_vector<Eigen::Vector3f> &data) {
+        release();
+        n_ = data.size();
+        if (n_ == 0) return false;  // kdtree_flann.inl:128-131
+        utility::check(cphb_index_create(reinterpret_cast<const float *>(data.data()), n_, nullptr, &ix_));
+        return true;
+    }
+    int Search(const utility::device_vector<Eigen::Vector3f> &query, const KDTreeSearchParam &param,
+               utility::device_vector<int> &indices, utility::device_vector<float> &distance2) const {
+        switch (param.GetSearchType()) {
+            case KDTreeSearchParam::SearchType::Knn:
+                return SearchKNN(query, static_cast<const KDTreeSearchParamKNN &>(param).knn_, indices, distance2);
+            case KDTreeSearchParam::SearchType::Radius: {
+                const auto &p = static_cast<const KDTreeSearchParamRadius &>(param);
+                return SearchRadius(query, p.radius_, p.max_nn_, indices, distance2);
+            }
+        }
+        return -1;
+    }
+    int SearchKNN(const utility::device_vector<Eigen::Vector3f> &query, int knn, utility::device_vector<int> &indices,
+                  utility::device_vector<float> &distance2) const {
+        if (!ix_ || n_ == 0 || query.empty() || knn < 0 || knn > NUM_MAX_NN) return -1;  // kdtree_flann.cu:46-48
+        indices.resize(query.size() * knn);
+        distance2.resize(query.size() * knn);
+        int64_t cnt = 0;
+        int rc = cphb_search_knn(ix_, reinterpret_cast<const float *>(query.data()), query.size(), knn, indices.data(),
+                                 distance2.data(), &cnt, nullptr);
+        return rc == CPHB_OK ? (int)cnt : -1;
+    }
+    int SearchRadius(const utility::device_vector<Eigen::Vector3f> &query, float radius, int max_nn,
+                     utility::device_vector<int> &indices, utility::device_vector<float> &distance2) const {
+        if (!ix_ || n_ == 0 || query.empty() || max_nn < 0) return -1;  // kdtree_flann.cu:70-72
+        indices.resize(query.size() * max_nn);
+        distance2.resize(query.size() * max_nn);
+        int64_t cnt = 0;
+        int rc = cphb_search_radius(ix_, reinterpret_cast<const float *>(query.data()), query.size(), radius, max_nn,
+                                    indices.data(), distance2.data(), &cnt, nullptr);
+        return rc == CPHB_OK ? (int)cnt : -1;
+    }
+    /// north_star's name for SearchRadius.
+    int SearchHybrid(const utility::device_vector<Eigen::Vector3f> &query, float radius, int max_nn,
+                     utility::device_vector<int> &indices, utility::device_vector<float> &distance2) const {
+        return SearchRadius(query, radius, max_nn, indices, distance2);
+    }
+    // single host query overloads (kdtree_flann.cu:88-129)
+    int SearchKNN(const Eigen::Vector3f &query, int knn, std::vector<int> &indices, std::vector<float> &distance2) const {
+        utility::device_vector<Eigen::Vector3f> q(std::vector<Eigen::Vector3f>{query});
+        utility::device_vector<int> i;
+        utility::device_vector<float> d;
+        int k = SearchKNN(q, knn, i, d);
+        indices = i.to_host();
+        distance2 = d.to_host();
+        return k;
+    }
+    int SearchRadius(const Eigen::Vector3f &query, float radius, int max_nn, std::vector<int> &indices,
+                     std::vector<float> &distance2) const {
+        utility::device_vector<Eigen::Vector3f> q(std::vector<Eigen::Vector3f>{query});
+        utility::device_vector<int> i;
+        utility::device_vector<float> d;
+        int k = SearchRadius(q, radius, max_nn, i, d);
+        indices = i.to_host();
+        distance2 = d.to_host();
+        return k;
+    }
+
+private:
+    void release() {
+        if (ix_) { cphb_stream_synchronize(nullptr); cphb_index_destroy(ix_); ix_ = nullptr; }
+    }
+    cphb_index *ix_ = nullptr;
+    size_t n_ = 0;
+};
+}  // namespace knn
+
+// --------------------------------------------------------------------------- geometry
+namespace geometry {
+/// geometry::PointCloud (pointcloud.h:43-263), hot-path subset.
+class PointCloud {
+public:
+    PointCloud() {}
+    PointCloud(const std::vector<Eigen::Vector3f> &points) : points_(points) {}
+    virtual ~PointCloud() {}
+    bool IsEmpty() const { return points_.empty(); }
+    bool HasPoints() const { return !points_.empty(); }
+    bool HasNormals() const { return !points_.empty() && normals_.size() == points_.size(); }          // pointcloud.h:82-94
+    bool HasColors() const { return !points_.empty() && colors_.size() == points_.size(); }
+    bool HasCovariances() const { return !points_.empty() && covariances_.size() == points_.size(); }
+    void SetPoints(const std::vector<Eigen::Vector3f> &p) { points_ = p; }
+    void SetNormals(const std::vector<Eigen::Vector3f> &p) { normals_ = p; }
+    void SetColors(const std::vector<Eigen::Vector3f> &p) { colors_ = p; }
+    std::vector<Eigen::Vector3f> GetPoints() const { return points_.to_host(); }
+    std::vector<Eigen::Vector3f> GetNormals() const { return normals_.to_host(); }
+    std::vector<Eigen::Vector3f> GetColors() const { return colors_.to_host(); }
+
+    Eigen::Vector3f GetMinBound() const { return bound(0); }  // pointcloud.cu:205
+    Eigen::Vector3f GetMaxBound() const { return bound(1); }
+
+    PointCloud &Transform(const Eigen::Matrix4f &T) {  // pointcloud.cu:293-299
+        float t[16];
+        utility::to_row_major(T, t);
+        if (!points_.empty())
+            utility::check(cphb_transform(fp(points_), HasNormals() ? fp(normals_) : nullptr,
+                                          HasCovariances() ? fp(covariances_) : nullptr, 1, points_.size(), t, nullptr));
+        utility::check(cphb_stream_synchronize(nullptr));
+        return *this;
+    }
+    std::shared_ptr<PointCloud> VoxelDownSample(float voxel_size) const {  // down_sample.cu:170-273
+        auto out = std::make_shared<PointCloud>();
+        if (voxel_size <= 0.0) { utility::LogWarning("[VoxelDownSample] voxel_size <= 0."); return out; }
+        const size_t n = points_.size();
+        if (n == 0) return out;
+        const bool hn = HasNormals(), hc = HasColors();
+        out->points_.resize(n);
+        if (hn) out->normals_.resize(n);
+        if (hc) out->colors_.resize(n);
+        size_t m = 0;
+        utility::check(cphb_voxel_down_sample(cfp(points_), hn ? cfp(normals_) : nullptr, hc ? cfp(colors_) : nullptr, n,
+                                              voxel_size, fp(out->points_), hn ? fp(out->normals_) : nullptr,
+                                              hc ? fp(out->colors_) : nullptr, &m, nullptr));
+        out->points_.resize(m);
+        if (hn) out->normals_.resize(m);
+        if (hc) out->colors_.resize(m);
+        return out;
+    }
+    bool EstimateNormals(const knn::KDTreeSearchParam &param = knn::KDTreeSearchParamKNN()) {  // estimate_normals.cu:82-127
+        if (!HasNormals()) normals_.resize(points_.size());
+        int knn = 0, max_nn = 0;
+        float radius = 0.f;
+        if (param.GetSearchType() == knn::KDTreeSearchParam::SearchType::Knn) knn = static_cast<const knn::KDTreeSearchParamKNN &>(param).knn_;
+        else { radius = static_cast<const knn::KDTreeSearchParamRadius &>(param).radius_; max_nn = static_cast<const knn::KDTreeSearchParamRadius &>(param).max_nn_; }
+        utility::check(cphb_estimate_normals(cfp(points_), points_.size(), knn, radius, max_nn, fp(normals_), nullptr));
+        return true;
+    }
+    cphb_cloud view() const {
+        cphb_cloud c;
+        std::memset(&c, 0, sizeof(c));
+        c.points = cfp(points_);
+        c.n = points_.size();
+        c.normals = HasNormals() ? cfp(normals_) : nullptr;
+        c.colors = HasColors() ? cfp(colors_) : nullptr;
+        c.covariances = HasCovariances() ? cfp(covariances_) : nullptr;
+        c.color_gradient = (!points_.empty() && color_gradient_.size() == points_.size()) ? cfp(color_gradient_) : nullptr;
+        c.cov_col_major = 1;  // Eigen::Matrix3f default storage
+        return c;
+    }
+
+public:
+    utility::device_vector<Eigen::Vector3f> points_, normals_, colors_;
+    utility::device_vector<Eigen::Matrix3f> covariances_;
+    utility::device_vector<Eigen::Vector3f> color_gradient_;  // PointCloudForColoredICP (colored_icp.cu:36-40)
+
+private:
+    template <class V> static float *fp(V &v) { return reinterpret_cast<float *>(v.data()); }
+    template <class V> static const float *cfp(const V &v) { return reinterpret_cast<const float *>(v.data()); }
+    Eigen::Vector3f bound(int which) const {
+        float mn[3] = {0, 0, 0}, mx[3] = {0, 0, 0};
+        if (!points_.empty()) utility::check(cphb_min_max_bound(cfp(points_), points_.size(), mn, mx, nullptr));
+        return which ? Eigen::Vector3f(mx[0], mx[1], mx[2]) : Eigen::Vector3f(mn[0], mn[1], mn[2]);
+    }
+};
+}  // namespace geometry
+
+// --------------------------------------------------------------------------- registration
+namespace registration {
+typedef utility::device_vector<Eigen::Vector2i> CorrespondenceSet;  // transformation_estimation.h:36
+
+enum class TransformationEstimationType {  // transformation_estimation.h:40-47
+    Unspecified = 0, PointToPoint = 1, PointToPlane = 2, SymmetricMethod = 3, ColoredICP = 4, GeneralizedICP = 5,
+};
+
+class ICPConvergenceCriteria {  // registration.h:35-49
+public:
+    ICPConvergenceCriteria(float relative_fitness = 1e-6, float relative_rmse = 1e-6, int max_iteration = 30)
+        : relative_fitness_(relative_fitness), relative_rmse_(relative_rmse), max_iteration_(max_iteration) {}
+    float relative_fitness_, relative_rmse_;
+    int max_iteration_;
+};
+
+class RegistrationResult {  // registration.h:51-67
+public:
+    RegistrationResult(const Eigen::Matrix4f &T = Eigen::Matrix4f::Identity()) : transformation_(T) {}
+    std::vector<Eigen::Vector2i> GetCorrespondenceSet() const { return correspondence_set_.to_host(); }
+    Eigen::Matrix4f_u transformation_;
+    CorrespondenceSet correspondence_set_;
+    float inlier_rmse_ = 0.0f;
+    float fitness_ = 0.0f;
+};
+
+inline cphb_icp_params make_params(int est, float max_dist, const ICPConvergenceCriteria &c, float det_thresh, float lambda) {
+    cphb_icp_params p;
+    std::memset(&p, 0, sizeof(p));
+    p.estimation = est;
+    p.max_correspondence_distance = max_dist;
+    p.relative_fitness = c.relative_fitness_;
+    p.relative_rmse = c.relative_rmse_;
+    p.max_iteration = c.max_iteration_;
+    p.det_thresh = det_thresh;
+    p.lambda_geometric = lambda;
+    return p;
+}
+
+/// transformation_estimation.h:49-77.  User subclasses (Unspecified) run through the generic loop below.
+class TransformationEstimation {
+public:
+    virtual ~TransformationEstimation() {}
+    virtual TransformationEstimationType GetTransformationEstimationType() const = 0;
+    virtual float ComputeRMSE(const geometry::PointCloud &source, const geometry::PointCloud &target, const CorrespondenceSet &corres) const = 0;
+    virtual Eigen::Matrix4f ComputeTransformation(const geometry::PointCloud &source, const geometry::PointCloud &target, const CorrespondenceSet &corres) const = 0;
+    virtual float det_thresh() const { return -1.f; }
+    virtual float lambda_geometric() const { return 0.968f; }
+
+protected:
+    float rmse_impl(const geometry::PointCloud &s, const geometry::PointCloud &t, const CorrespondenceSet &c) const {
+        cphb_cloud sc = s.view(), tc = t.view();
+        cphb_icp_params p = make_params((int)GetTransformationEstimationType(), 0.f, ICPConvergenceCriteria(), det_thresh(), lambda_geometric());
+        float r = 0.f;
+        utility::check(cphb_compute_rmse(p.estimation, &sc, &tc, reinterpret_cast<const int32_t *>(c.data()), c.size(), &p, &r, nullptr));
+        return r;
+    }
+    Eigen::Matrix4f transform_impl(const geometry::PointCloud &s, const geometry::PointCloud &t, const CorrespondenceSet &c) const {
+        cphb_cloud sc = s.view(), tc = t.view();
+        cphb_icp_params p = make_params((int)GetTransformationEstimationType(), 0.f, ICPConvergenceCriteria(), det_thresh(), lambda_geometric());
+        float T[16];
+        utility::check(cphb_compute_transformation(p.estimation, &sc, &tc, reinterpret_cast<const int32_t *>(c.data()), c.size(), &p, T, nullptr));
+        return utility::from_row_major(T);
+    }
+};
+#define CPHB_FACADE_ESTIMATOR_BODY(TYPE)                                                                        \
+    TransformationEstimationType GetTransformationEstimationType() const override { return TransformationEstimationType::TYPE; } \
+    float ComputeRMSE(const geometry::PointCloud &s, const geometry::PointCloud &t, const CorrespondenceSet &c) const override { return rmse_impl(s, t, c); } \
+    Eigen::Matrix4f ComputeTransformation(const geometry::PointCloud &s, const geometry::PointCloud &t, const CorrespondenceSet &c) const override { return transform_impl(s, t, c); }
+
+class TransformationEstimationPointToPoint : public TransformationEstimation {
+public:
+    CPHB_FACADE_ESTIMATOR_BODY(PointToPoint)
+};
+class TransformationEstimationPointToPlane : public TransformationEstimation {
+public:
+    TransformationEstimationPointToPlane(float det_thresh = 1.0e-6) : det_thresh_(det_thresh) {}
+    CPHB_FACADE_ESTIMATOR_BODY(PointToPlane)
+    float det_thresh() const override { return det_thresh_; }
+    float det_thresh_;
+};
+class TransformationEstimationSymmetricMethod : public TransformationEstimation {
+public:
+    TransformationEstimationSymmetricMethod(float det_thresh = 1.0e-6) : det_thresh_(det_thresh) {}
+    CPHB_FACADE_ESTIMATOR_BODY(SymmetricMethod)
+    float det_thresh() const override { return det_thresh_; }
+    float det_thresh_;
+};
+class TransformationEstimationForGeneralizedICP : public TransformationEstimation {  // generalized_icp.h:14-52
+public:
+    TransformationEstimationForGeneralizedICP(float epsilon = 1e-3) : epsilon_(epsilon) {}
+    CPHB_FACADE_ESTIMATOR_BODY(GeneralizedICP)
+    float epsilon_;
+};
+class TransformationEstimationForColoredICP : public TransformationEstimation {  // colored_icp.cu:42-71
+public:
+    TransformationEstimationForColoredICP(float lambda_geometric = 0.968, float det_thresh = 1.0e-6)
+        : lambda_geometric_(lambda_geometric), det_thresh_(det_thresh) {
+        if (lambda_geometric_ < 0 || lambda_geometric_ > 1.0) lambda_geometric_ = 0.968;
+    }
+    CPHB_FACADE_ESTIMATOR_BODY(ColoredICP)
+    float det_thresh() const override { return det_thresh_; }
+    float lambda_geometric() const override { return lambda_geometric_; }
+    float lambda_geometric_, det_thresh_;
+};
+
+inline RegistrationResult to_result(const cphb_icp_result &r, CorrespondenceSet &&corr) {
+    RegistrationResult out(utility::from_row_major(r.transformation));
+    corr.resize((size_t)r.n_correspondences);
+    out.correspondence_set_ = std::move(corr);
+    out.fitness_ = r.fitness;
+    out.inlier_rmse_ = r.inlier_rmse;
+    return out;
+}
+
+/// registration::EvaluateRegistration (registration.cu:106-119)
+inline RegistrationResult EvaluateRegistration(const geometry::PointCloud &source, const geometry::PointCloud &target,
+                                               float max_correspondence_distance,
+                                               const Eigen::Matrix4f &transformation = Eigen::Matrix4f::Identity()) {
+    cphb_cloud sc = source.view(), tc = target.view();
+    float T[16];
+    utility::to_row_major(transformation, T);
+    cphb_icp_result r;
+    CorrespondenceSet corr(source.points_.size() ? source.points_.size() : 1);
+    utility::check(cphb_evaluate_registration(&sc, &tc, max_correspondence_distance, T, &r, reinterpret_cast<int32_t *>(corr.data()), nullptr));
+    return to_result(r, std::move(corr));
+}
+
+/// registration::RegistrationICP (registration.cu:121-173).  Built-in estimators run the fused
+/// one-launch-per-iteration path; user-defined ones (Unspecified) the generic loop with the
+/// caller's virtual ComputeTransformation, exactly as the reference's loop is written.
+inline RegistrationResult RegistrationICP(const geometry::PointCloud &source, const geometry::PointCloud &target,
+                                          float max_correspondence_distance,
+                                          const Eigen::Matrix4f &init = Eigen::Matrix4f::Identity(),
+                                          const TransformationEstimation &estimation = TransformationEstimationPointToPoint(),
+                                          const ICPConvergenceCriteria &criteria = ICPConvergenceCriteria()) {
+    if (max_correspondence_distance <= 0.0) utility::LogError("Invalid max_correspondence_distance.");  // :130-132
+    const auto type = estimation.GetTransformationEstimationType();
+    if ((type == TransformationEstimationType::PointToPlane || type == TransformationEstimationType::ColoredICP) && !target.HasNormals())
+        utility::LogError("TransformationEstimationPointToPlane and TransformationEstimationColoredICP require pre-computed target normal vectors.");
+    if (type != TransformationEstimationType::Unspecified) {
+        cphb_cloud sc = source.view(), tc = target.view();
+        cphb_icp_params p = make_params((int)type, max_correspondence_distance, criteria, estimation.det_thresh(), estimation.lambda_geometric());
+        float T[16];
+        utility::to_row_major(init, T);
+        cphb_icp_result r;
+        CorrespondenceSet corr(source.points_.size() ? source.points_.size() : 1);
+        utility::check(cphb_registration_icp(&sc, &tc, T, &p, nullptr, &r, reinterpret_cast<int32_t *>(corr.data()), nullptr));
+        return to_result(r, std::move(corr));
+    }
+    // generic loop (registration.cu:145-172) for user-subclassed estimators
+    Eigen::Matrix4f transformation = init;
+    geometry::PointCloud pcd = source;
+    if (!init.isIdentity()) pcd.Transform(init);
+    RegistrationResult result = EvaluateRegistration(pcd, target, max_correspondence_distance);
+    result.transformation_ = transformation;
+    for (int i = 0; i < criteria.max_iteration_; ++i) {
+        Eigen::Matrix4f update = estimation.ComputeTransformation(pcd, target, result.correspondence_set_);
+        transformation = update * transformation;
+        pcd.Transform(update);
+        const float bf = result.fitness_, br = result.inlier_rmse_;
+        result = EvaluateRegistration(pcd, target, max_correspondence_distance);
+        result.transformation_ = transformation;
+        if (std::abs(bf - result.fitness_) < criteria.relative_fitness_ && std::abs(br - result.inlier_rmse_) < criteria.relative_rmse_) break;
+    }
+    return result;
+}
+
+/// InitializePointCloudForGeneralizedICP (generalized_icp.cu:37-61)
+inline std::shared_ptr<geometry::PointCloud> InitializePointCloudForGeneralizedICP(const geometry::PointCloud &pcd, float epsilon) {
+    auto out = std::make_shared<geometry::PointCloud>(pcd);
+    if (out->HasCovariances()) return out;
+    if (!out->HasNormals()) out->EstimateNormals(knn::KDTreeSearchParamKNN(20));
+    out->covariances_.resize(out->points_.size());
+    utility::check(cphb_covariances_from_normals(reinterpret_cast<const float *>(out->normals_.data()), out->points_.size(), epsilon,
+                                                 reinterpret_cast<float *>(out->covariances_.data()), 1, nullptr));
+    return out;
+}
+/// registration::RegistrationGeneralizedICP (generalized_icp.cu:185-198)
+inline RegistrationResult RegistrationGeneralizedICP(const geometry::PointCloud &source, const geometry::PointCloud &target,
+                                                     float max_correspondence_distance,
+                                                     const Eigen::Matrix4f &init = Eigen::Matrix4f::Identity(),
+                                                     const TransformationEstimationForGeneralizedICP &estimation = TransformationEstimationForGeneralizedICP(),
+                                                     const ICPConvergenceCriteria &criteria = ICPConvergenceCriteria()) {
+    return RegistrationICP(*InitializePointCloudForGeneralizedICP(source, estimation.epsilon_),
+                           *InitializePointCloudForGeneralizedICP(target, estimation.epsilon_), max_correspondence_distance,
+                           init, estimation, criteria);
+}
+/// registration::RegistrationColoredICP (colored_icp.cu:329-342)
+inline RegistrationResult RegistrationColoredICP(const geometry::PointCloud &source, const geometry::PointCloud &target,
+                                                 float max_distance, const Eigen::Matrix4f &init = Eigen::Matrix4f::Identity(),
+                                                 const ICPConvergenceCriteria &criteria = ICPConvergenceCriteria(),
+                                                 float lambda_geometric = 0.968, float det_thresh = 1.0e-6) {
+    geometry::PointCloud target_c = target;  // InitializePointCloudForColoredICP (colored_icp.cu:120-148)
+    target_c.color_gradient_.resize(target.points_.size());
+    if (target.HasNormals() && target.HasColors())
+        utility::check(cphb_color_gradient(reinterpret_cast<const float *>(target_c.points_.data()),
+                                           reinterpret_cast<const float *>(target_c.normals_.data()),
+                                           reinterpret_cast<const float *>(target_c.colors_.data()), target_c.points_.size(),
+                                           max_distance * 2.0f, 30, reinterpret_cast<float *>(target_c.color_gradient_.data()), nullptr));
+    else if (!target_c.color_gradient_.empty())
+        utility::check(cphb_memset(target_c.color_gradient_.data(), 0, target_c.color_gradient_.size() * 12, nullptr));
+    return RegistrationICP(source, target_c, max_distance, init, TransformationEstimationForColoredICP(lambda_geometric, det_thresh), criteria);
+}
+/// registration::Kabsch (kabsch.h:30-49)
+inline Eigen::Matrix4f_u Kabsch(const utility::device_vector<Eigen::Vector3f> &model, const utility::device_vector<Eigen::Vector3f> &target,
+                                const CorrespondenceSet &corres) {
+    float T[16];
+    utility::check(cphb_kabsch(reinterpret_cast<const float *>(model.data()), model.size(), reinterpret_cast<const float *>(target.data()),
+                               reinterpret_cast<const int32_t *>(corres.data()), corres.size(), T, nullptr));
+    return utility::from_row_major(T);
+}
+inline Eigen::Matrix4f_u Kabsch(const utility::device_vector<Eigen::Vector3f> &model, const utility::device_vector<Eigen::Vector3f> &target) {
+    float T[16];
+    utility::check(cphb_kabsch(reinterpret_cast<const float *>(model.data()), model.size(), reinterpret_cast<const float *>(target.data()),
+                               nullptr, 0, T, nullptr));
+    return utility::from_row_major(T);
+}
+}  // namespace registration
+}  // namespace cupoch

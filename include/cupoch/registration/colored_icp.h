@@ -1,0 +1,3 @@
+// Path-compatible with the reference header cupoch/registration/colored_icp.h; the declarations live in the single facade header.
+#pragma once
+#include "cupoch/cupoch_b200_facade.h"

@@ -209,6 +209,18 @@ int cphb_registration_icp(const cphb_cloud *source, const cphb_cloud *target,
                           void *nccl_comm, cphb_icp_result *h_result, int32_t *corr_out,
                           void *stream);
 
+/* TransformationEstimation*::ComputeTransformation / ComputeRMSE on an explicit correspondence list
+ * (transformation_estimation.h:49-77; corr = device (i, j) pairs).  Synchronise. */
+int cphb_compute_transformation(int estimation, const cphb_cloud *source, const cphb_cloud *target,
+                                const int32_t *corr, size_t n_corr, const cphb_icp_params *params,
+                                float h_T[16], void *stream);
+int cphb_compute_rmse(int estimation, const cphb_cloud *source, const cphb_cloud *target,
+                      const int32_t *corr, size_t n_corr, const cphb_icp_params *params,
+                      float *h_rmse, void *stream);
+/* registration::Kabsch(model, target[, corres]) (kabsch.h:30-49); corr NULL pairs i<->i. */
+int cphb_kabsch(const float *model, size_t n_model, const float *target, const int32_t *corr,
+                size_t n_corr, float h_T[16], void *stream);
+
 /* registration::EvaluateRegistration (registration.cu:106-119). */
 int cphb_evaluate_registration(const cphb_cloud *source, const cphb_cloud *target,
                                float max_correspondence_distance, const float h_T[16],

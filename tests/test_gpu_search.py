@@ -93,7 +93,10 @@ def test_strict_radius_boundary(orc):
     idx, _ = _check(orc, tgt, qry, 2, radius=1.0)
     assert idx[0].tolist() == [0, 1]           # tie at d2 = 0.25: smaller index first
     assert idx[1].tolist() == [-1, -1]         # both neighbours of (0,1,0) sit at d2 == r2 == 1.0: excluded
-    _check(orc, tgt, qry, 1, radius=0.0)
+    # radius 0: r2 == 0, nothing satisfies d2 < 0 (the oracle wrapper reserves radius<=0 for "no radius")
+    tree = cph.geometry.KDTreeFlann(cph.geometry.PointCloud(tgt))
+    cnt, idx, d2 = tree.search_radius(tgt, 0.0, 1)
+    assert cnt == 0 and (idx.cpu() == -1).all() and np.isinf(d2.cpu()).all()
 
 
 def test_error_codes():
