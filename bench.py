@@ -134,20 +134,13 @@ def run_native(args, rank, world):
         import torch.distributed as dist
         torch.cuda.set_device(local_rank)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-        uid = torch.zeros(128, dtype=torch.uint8)
-        if rank == 0:
-            b = C.create_string_buffer(128)
-            _lib.check(L.cphb_nccl_unique_id(b))
-            uid = torch.frombuffer(bytearray(b.raw), dtype=torch.uint8).clone()
-        uid = uid.cuda()
-        dist.broadcast(uid, 0)
-        h = C.c_void_p()
-        _lib.check(L.cphb_nccl_comm_init(bytes(uid.cpu().numpy().tobytes()), world, rank, C.byref(h)))
-        comm = h
+        from cupoch_b200.distributed import make_comm
+        comm = make_comm(dist, rank, world, device="cuda")
 
     n = args.points
     src, tgt, tn = make_workload(n)
-    lo, hi = (n * rank) // world, (n * (rank + 1)) // world
+    from cupoch_b200.distributed import shard_range
+    lo, hi = shard_range(n, rank, world)
     src_local = np.ascontiguousarray(src[lo:hi])
     R = cph.registration
     est, crit = R.TransformationEstimationPointToPlane(), R.ICPConvergenceCriteria(0, 0, ITERS)
@@ -207,8 +200,11 @@ def run_native(args, rank, world):
         s2 = cph.geometry.PointCloud(h_src)         # H2D (pinned)
         t2 = cph.geometry.PointCloud(h_tgt)
         t2.normals = h_tn
-        r = R.registration_icp(s2, t2, MAX_DIST, init, est, crit, nccl_comm=comm)  # D2H of T + correspondences
-        d2h[0] = 16 * 4 + 8 + r.correspondence_set.nbytes
+        r = R.registration_icp(s2, t2, MAX_DIST, init, est, crit, nccl_comm=comm)
+        # D2H: the RegistrationResult scalars (T, fitness, rmse, counts); correspondence_set_ stays on the
+        # device exactly as in the reference's RegistrationResult (registration.h:51-67)
+        _ = (r.transformation, r.fitness, r.inlier_rmse)
+        d2h[0] = C.sizeof(_lib.IcpResult)
         return r
     for _ in range(min(args.warmup, 2)):
         step_e2e()

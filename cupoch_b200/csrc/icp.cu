@@ -954,6 +954,7 @@ struct cphb_icp {
     float4 *src_col;
     IcpState *st;
     IcpState *h_st;  // pinned
+    bool owns_host;
     cudaEvent_t ev0, ev1;
     double *partials;
     int32_t *corr_index;
@@ -964,6 +965,15 @@ struct cphb_icp {
     unsigned grid, reduce_grid;
     cudaStream_t stream;
 };
+
+// per-thread cached pinned staging buffer + events: cudaMallocHost / cudaEventCreate cost milliseconds,
+// far more than a 1M-point registration's launch loop.
+struct HostCache {
+    IcpState *h_st = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    bool in_use = false;
+};
+static thread_local HostCache t_cache;
 
 static bool is_identity4(const float *T) {  // Eigen isIdentity(1e-5), registration.cu:148
     for (int i = 0; i < 4; ++i)
@@ -1075,9 +1085,23 @@ extern "C" int cphb_icp_create(const cphb_cloud *source, const cphb_cloud *targe
     icp->cmp_counts = (unsigned *)(b + o_cc);
     icp->cmp_total = (unsigned *)(b + o_ct);
     uint32_t *perm = (uint32_t *)(b + o_perm);
-    CPHB_CUDA(cudaMallocHost((void **)&icp->h_st, sizeof(IcpState)));
-    CPHB_CUDA(cudaEventCreate(&icp->ev0));
-    CPHB_CUDA(cudaEventCreate(&icp->ev1));
+    if (!t_cache.in_use) {
+        if (!t_cache.h_st) {
+            CPHB_CUDA(cudaMallocHost((void **)&t_cache.h_st, sizeof(IcpState)));
+            CPHB_CUDA(cudaEventCreate(&t_cache.ev0));
+            CPHB_CUDA(cudaEventCreate(&t_cache.ev1));
+        }
+        t_cache.in_use = true;
+        icp->owns_host = false;
+        icp->h_st = t_cache.h_st;
+        icp->ev0 = t_cache.ev0;
+        icp->ev1 = t_cache.ev1;
+    } else {  // a second live context on this thread gets its own
+        icp->owns_host = true;
+        CPHB_CUDA(cudaMallocHost((void **)&icp->h_st, sizeof(IcpState)));
+        CPHB_CUDA(cudaEventCreate(&icp->ev0));
+        CPHB_CUDA(cudaEventCreate(&icp->ev1));
+    }
     if (n) {
         rc = cphb_hilbert_order(source->points, n, perm, nullptr, 0, s);
         if (rc) { cphb_icp_destroy(icp); return rc; }
@@ -1093,9 +1117,13 @@ extern "C" int cphb_icp_create(const cphb_cloud *source, const cphb_cloud *targe
 extern "C" void cphb_icp_destroy(cphb_icp *icp) {
     if (!icp) return;
     if (icp->arena) cudaFreeAsync(icp->arena, icp->stream);
-    if (icp->h_st) cudaFreeHost(icp->h_st);
-    if (icp->ev0) cudaEventDestroy(icp->ev0);
-    if (icp->ev1) cudaEventDestroy(icp->ev1);
+    if (icp->owns_host) {
+        if (icp->h_st) cudaFreeHost(icp->h_st);
+        if (icp->ev0) cudaEventDestroy(icp->ev0);
+        if (icp->ev1) cudaEventDestroy(icp->ev1);
+    } else if (icp->h_st == t_cache.h_st) {
+        t_cache.in_use = false;
+    }
     cphb_index_destroy(icp->index);
     delete icp;
 }

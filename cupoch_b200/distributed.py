@@ -1,0 +1,55 @@
+"""Multi-GPU plumbing for the sharded ICP: one process per GPU, the source is split
+into contiguous blocks, the target is replicated, one all-reduce of 32 doubles per iteration.
+
+torch.distributed is used only for rendezvous (broadcasting the 128-byte NCCL unique id); the
+communicator itself is created inside libcupoch_b200.so (cphb_nccl_comm_init) and used by the fused
+loop (cphb_icp_run(..., nccl_comm))."""
+import ctypes as C
+
+from . import _lib
+
+
+def shard_range(n, rank, world):
+    """Contiguous block [lo, hi) of rank `rank`: sizes differ by at most one, blocks tile [0, n) in rank order,
+    so concatenating per-rank correspondence lists (with lo added to the source index) reproduces the
+    single-GPU ordering."""
+    if world <= 0 or not (0 <= rank < world):
+        raise ValueError("bad rank/world")
+    return (n * rank) // world, (n * (rank + 1)) // world
+
+
+def broadcast_unique_id(dist, rank, device=None):
+    """rank 0 creates an NCCL unique id; everybody returns the same 128 bytes (any torch backend)."""
+    import torch
+    buf = torch.zeros(128, dtype=torch.uint8)
+    if rank == 0:
+        b = C.create_string_buffer(128)
+        _lib.check(_lib.lib().cphb_nccl_unique_id(b))
+        buf = torch.frombuffer(bytearray(b.raw), dtype=torch.uint8).clone()
+    if device is not None:
+        buf = buf.to(device)
+    dist.broadcast(buf, 0)
+    return bytes(buf.cpu().numpy().tobytes())
+
+
+def make_comm(dist, rank, world, device=None):
+    """-> opaque ncclComm_t handle (ctypes.c_void_p) usable as `nccl_comm=` in cupoch_b200.registration."""
+    uid = broadcast_unique_id(dist, rank, device)
+    h = C.c_void_p()
+    _lib.check(_lib.lib().cphb_nccl_comm_init(uid, world, rank, C.byref(h)))
+    return h
+
+
+def destroy_comm(comm):
+    if comm:
+        _lib.check(_lib.lib().cphb_nccl_comm_destroy(comm))
+
+
+def gather_correspondences(dist, local_corr, lo, world):
+    """all-gather-v of the per-rank (i, j) lists into the single-GPU ordering (host side, once per call)."""
+    import numpy as np
+    mine = np.asarray(local_corr, np.int32).reshape(-1, 2).copy()
+    mine[:, 0] += lo
+    out = [None] * world
+    dist.all_gather_object(out, mine)
+    return np.concatenate(out, 0) if out else mine

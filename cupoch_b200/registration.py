@@ -8,7 +8,7 @@ import numpy as np
 
 from . import _lib
 from .geometry import KDTreeSearchParamKNN, PointCloud
-from .utility import DeviceArray, as_f16
+from .utility import DeviceArray, _DevicePool, as_f16
 
 
 class ICPConvergenceCriteria:  # registration.h:35-49
@@ -77,17 +77,40 @@ class TransformationEstimationForColoredICP(TransformationEstimation):  # colore
 
 
 class RegistrationResult:  # registration.h:51-67
+    """`correspondence_set` lives on the device like the reference's `correspondence_set_`; the host copy is
+    made on first access, as the reference's pybind property does (registration.cpp:338-343)."""
+
     def __init__(self, transformation=None):
         self.transformation = np.eye(4, dtype=np.float32) if transformation is None else np.asarray(transformation, np.float32)
-        self.correspondence_set = np.zeros((0, 2), np.int32)
+        self._corr_host = np.zeros((0, 2), np.int32)
+        self._corr_dev, self._n_corr = None, 0
         self.inlier_rmse = 0.0
         self.fitness = 0.0
         self.iterations = 0
         self.converged = False
 
+    @property
+    def correspondence_set(self):
+        if self._corr_dev is not None:
+            self._corr_host = self._corr_dev.cpu(self._n_corr) if self._n_corr else np.zeros((0, 2), np.int32)
+            _DevicePool.give(self._corr_dev)
+            self._corr_dev = None
+        return self._corr_host
+
+    @correspondence_set.setter
+    def correspondence_set(self, v):
+        self._corr_dev = None
+        self._corr_host = np.asarray(v, np.int32).reshape(-1, 2)
+
+    def __del__(self):
+        try:
+            _DevicePool.give(self._corr_dev)
+        except Exception:
+            pass
+
     def __repr__(self):
         return ("registration::RegistrationResult with fitness=%f, inlier_rmse=%f, and correspondence_set size of %d"
-                % (self.fitness, self.inlier_rmse, len(self.correspondence_set)))
+                % (self.fitness, self.inlier_rmse, self._n_corr if self._corr_dev is not None else len(self._corr_host)))
 
 
 def _params(estimation, max_distance, criteria):
@@ -112,8 +135,7 @@ def _result(res, corr, want_corr):
     out.loop_ms = float(res.loop_ms)
     out.loop_launches = int(res.loop_launches)
     if want_corr:
-        nc = int(res.n_correspondences)
-        out.correspondence_set = corr.cpu()[:nc].copy() if nc else np.zeros((0, 2), np.int32)
+        out._corr_dev, out._n_corr = corr, int(res.n_correspondences)
     return out
 
 
@@ -131,7 +153,7 @@ def registration_icp(source, target, max_correspondence_distance, init=None,
     sc, tc = source._cloud(), target._cloud()
     p = _params(estimation_method, max_correspondence_distance, criteria)
     res = _lib.IcpResult()
-    corr = DeviceArray((max(len(source), 1), 2), np.int32) if return_correspondences else None
+    corr = _DevicePool.take((max(len(source), 1), 2), np.int32) if return_correspondences else None
     _lib.check(_lib.lib().cphb_registration_icp(C.byref(sc), C.byref(tc), as_f16(init), C.byref(p), nccl_comm,
                                                 C.byref(res), corr.ptr if corr else None, None))
     return _result(res, corr, return_correspondences)
@@ -143,7 +165,7 @@ def evaluate_registration(source, target, max_correspondence_distance, transform
     _lib.require_gpu()
     sc, tc = source._cloud(False), target._cloud(False)
     res = _lib.IcpResult()
-    corr = DeviceArray((max(len(source), 1), 2), np.int32)
+    corr = _DevicePool.take((max(len(source), 1), 2), np.int32)
     _lib.check(_lib.lib().cphb_evaluate_registration(C.byref(sc), C.byref(tc), float(max_correspondence_distance),
                                                      as_f16(T), C.byref(res), corr.ptr, None))
     return _result(res, corr, True)
@@ -219,7 +241,10 @@ class IcpContext:
         res = _lib.IcpResult()
         _lib.check(_lib.lib().cphb_icp_run(self._h, as_f16(init), nccl_comm, C.byref(res),
                                            self._corr.ptr if return_correspondences else None, None))
-        return _result(res, self._corr, return_correspondences)
+        out = _result(res, None, False)
+        if return_correspondences:
+            out.correspondence_set = self._corr.cpu(int(res.n_correspondences)) if res.n_correspondences else np.zeros((0, 2), np.int32)
+        return out
 
     def step(self, T):
         """-> (sums[32] float64, corr_index[n] int32) at pose T applied to the pristine source."""

@@ -61,11 +61,20 @@ class DeviceArray:
         return cls.from_numpy(np.asarray(obj), dtype)
 
     # -- access --------------------------------------------------------------
-    def cpu(self):
-        out = np.empty(self.shape, self.dtype)
-        if self.nbytes:
-            _lib.check(_lib.lib().cphb_memcpy_d2h(out.ctypes.data, self.ptr, self.nbytes, None))
-            _lib.check(_lib.lib().cphb_stream_synchronize(None))
+    def cpu(self, count=None):
+        """download (optionally only the first `count` rows)"""
+        shape = self.shape if count is None else (int(count),) + self.shape[1:]
+        out = np.empty(shape, self.dtype)
+        if out.nbytes:
+            L = _lib.lib()
+            if out.nbytes >= (1 << 16):
+                stage = _PinnedStage.get(out.nbytes)
+                _lib.check(L.cphb_memcpy_d2h(stage, self.ptr, out.nbytes, None))
+                _lib.check(L.cphb_stream_synchronize(None))
+                C.memmove(out.ctypes.data, stage, out.nbytes)
+            else:
+                _lib.check(L.cphb_memcpy_d2h(out.ctypes.data, self.ptr, out.nbytes, None))
+                _lib.check(L.cphb_stream_synchronize(None))
         return out
 
     def __len__(self):
@@ -78,6 +87,42 @@ class DeviceArray:
             except Exception:
                 pass
             self.ptr = 0
+
+
+class _PinnedStage:
+    """One reusable pinned host buffer for D2H reads (pageable copies run at a few GB/s)."""
+    ptr, cap = 0, 0
+
+    @classmethod
+    def get(cls, nbytes):
+        if nbytes > cls.cap:
+            if cls.ptr:
+                _lib.lib().cphb_free_host(cls.ptr)
+            cls.cap = max(nbytes, 1 << 20)
+            cls.ptr = _lib.lib().cphb_malloc_host(cls.cap)
+            if not cls.ptr:
+                cls.cap = 0
+                _lib.check(-2)
+        return cls.ptr
+
+
+class _DevicePool:
+    """Tiny size-keyed free list so per-call result buffers do not hit cudaMalloc/cudaFree."""
+    free = {}
+
+    @classmethod
+    def take(cls, shape, dtype):
+        key = (tuple(shape), np.dtype(dtype).str)
+        lst = cls.free.get(key)
+        return lst.pop() if lst else DeviceArray(shape, dtype)
+
+    @classmethod
+    def give(cls, arr):
+        if arr is not None and arr._owned and arr.ptr:
+            key = (arr.shape, arr.dtype.str)
+            lst = cls.free.setdefault(key, [])
+            if len(lst) < 4:
+                lst.append(arr)
 
 
 def Vector3fVector(a=None):
