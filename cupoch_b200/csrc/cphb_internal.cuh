@@ -284,17 +284,38 @@ __device__ __forceinline__ void wait_leaf(W &w, int b) {
     w.phase ^= (1u << b);
 }
 
-// k = 1 leaf scan
-__device__ __forceinline__ void scan_tile(const float4 *tile, WarpSearch &w) {
-    unsigned long long best = w.best;
+// k = 1 leaf scan.  `need` = lanes whose own bound still reaches this leaf's box.
+//   many lanes  : every lane scans the 32 candidates against its own query (broadcast LDS.128);
+//   few lanes   : transposed -- lane L holds candidate L, the needing queries are broadcast one at a
+//                 time and the 32 distances are min-reduced with REDUX (d2 bits, then index among
+//                 equal d2: the same (d2, index) order as the sequential scan).
+#define CPHB_TRANSPOSE_MAX 14
+__device__ __forceinline__ void scan_tile(const float4 *tile, WarpSearch &w, unsigned need) {
+    if (__popc(need) > CPHB_TRANSPOSE_MAX) {
+        unsigned long long best = w.best;
 #pragma unroll
-    for (int j = 0; j < CPHB_LEAF; ++j) {
-        float4 p = tile[j];
-        float d2 = dist2(w.qx, w.qy, w.qz, p.x, p.y, p.z);
-        unsigned long long key = ((unsigned long long)__float_as_uint(d2) << 32) | __float_as_uint(p.w);
-        best = (key < best) ? key : best;
+        for (int j = 0; j < CPHB_LEAF; ++j) {
+            float4 p = tile[j];
+            float d2 = dist2(w.qx, w.qy, w.qz, p.x, p.y, p.z);
+            unsigned long long key = ((unsigned long long)__float_as_uint(d2) << 32) | __float_as_uint(p.w);
+            best = (key < best) ? key : best;
+        }
+        w.best = best;
+        return;
     }
-    w.best = best;
+    const float4 p = tile[lane_id()];
+    const unsigned pidx = __float_as_uint(p.w);
+    while (need) {
+        const int t = __ffs(need) - 1;
+        need &= need - 1;
+        const float qx = __shfl_sync(CPHB_FULL, w.qx, t), qy = __shfl_sync(CPHB_FULL, w.qy, t),
+                    qz = __shfl_sync(CPHB_FULL, w.qz, t);
+        const unsigned db = __float_as_uint(dist2(qx, qy, qz, p.x, p.y, p.z));
+        const unsigned m1 = __reduce_min_sync(CPHB_FULL, db);
+        const unsigned m2 = __reduce_min_sync(CPHB_FULL, db == m1 ? pidx : 0xffffffffu);
+        const unsigned long long key = ((unsigned long long)m1 << 32) | m2;
+        if (lane_id() == t && key < w.best) w.best = key;
+    }
 }
 
 // lane index of the active child with the smallest order key, or -1
@@ -304,15 +325,15 @@ __device__ __forceinline__ int pick_child(unsigned active, unsigned keybits) {
     if (m == 0xffffffffu) return -1;
     return __ffs(__ballot_sync(CPHB_FULL, cand == m)) - 1;
 }
-// stage 2: can any lane still improve inside box `bx`?  (uniform address: one broadcast load)
+// stage 2: which lanes can still improve inside box `bx`?  (uniform address: one broadcast load)
 template <class W>
-__device__ __forceinline__ bool any_lane_needs(const W &w, const Box *bx) {
+__device__ __forceinline__ unsigned lanes_needing(const W &w, const Box *bx) {
     const float4 lo = __ldg(&bx->lo), hi = __ldg(&bx->hi);
     float dx = fmaxf(0.f, fmaxf(lo.x - w.qx, w.qx - hi.x));
     float dy = fmaxf(0.f, fmaxf(lo.y - w.qy, w.qy - hi.y));
     float dz = fmaxf(0.f, fmaxf(lo.z - w.qz, w.qz - hi.z));
     float d = __fmaf_rn(dz, dz, __fmaf_rn(dy, dy, __fmul_rn(dx, dx)));
-    return __any_sync(CPHB_FULL, w.valid && __float_as_uint(d) <= w.lane_bound());
+    return __ballot_sync(CPHB_FULL, w.valid && __float_as_uint(d) <= w.lane_bound());
 }
 
 template <int LV, class W>
@@ -333,7 +354,7 @@ struct Visit {
                 int src = pick_child(active, dkey);
                 if (src < 0) break;
                 active &= ~(1u << src);
-                if (any_lane_needs(w, gbox + src)) {
+                if (lanes_needing(w, gbox + src)) {
                     Visit<LV - 1, W>::run(ix, group * 32 + src, w);
                     active &= __ballot_sync(CPHB_FULL, dcull <= w.bound);
                 }
@@ -347,10 +368,10 @@ struct Visit {
                 active &= ~(1u << cur);
                 next = pick_child(active, dkey);
                 if (next >= 0) issue_leaf(ix, group * 32 + next, w.tile + (b ^ 1) * CPHB_LEAF, w.bar + (b ^ 1));
-                const bool need = any_lane_needs(w, gbox + cur);
+                const unsigned need = lanes_needing(w, gbox + cur);
                 wait_leaf(w, b);  // always consume the copy so the barrier phases stay in step
                 if (need) {
-                    scan_tile(w.tile + b * CPHB_LEAF, w);
+                    scan_tile(w.tile + b * CPHB_LEAF, w, need);
                     warp_update_bound(w);
                     const unsigned still = __ballot_sync(CPHB_FULL, dcull <= w.bound);
                     // the prefetched `next` stays queued even if it just got culled: it is consumed

@@ -24,7 +24,7 @@ struct WarpSearchK : WarpSearchBase {
     __device__ __forceinline__ unsigned lane_bound() const { return (unsigned)(worst >> 32); }
 };
 
-__device__ __forceinline__ void scan_tile(const float4 *tile, WarpSearchK &w) {
+__device__ __forceinline__ void scan_tile(const float4 *tile, WarpSearchK &w, unsigned /*need*/) {
     const int k = w.k;
 #pragma unroll 4
     for (int j = 0; j < CPHB_LEAF; ++j) {

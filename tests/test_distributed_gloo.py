@@ -1,0 +1,87 @@
+"""N>1 host logic on CPU (gloo, world_size 2): shard partition, unique-id style broadcast, and the
+identity "all-reduce of per-shard sums == sums over the whole source" that the sharded ICP relies on
+(checked with the oracle's estimator on each rank's block).  No GPU, no product compute."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from cupoch_b200.distributed import gather_correspondences, shard_range
+
+
+def test_shard_range_tiles_exactly():
+    for n in (0, 1, 7, 1000, 1_000_003):
+        for world in (1, 2, 3, 8):
+            edges = [shard_range(n, r, world) for r in range(world)]
+            assert edges[0][0] == 0 and edges[-1][1] == n
+            for a, b in zip(edges, edges[1:]):
+                assert a[1] == b[0]
+            sizes = [hi - lo for lo, hi in edges]
+            assert max(sizes) - min(sizes) <= 1
+    with pytest.raises(ValueError):
+        shard_range(10, 2, 2)
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    from oracle import oracle_py as orc
+    from cupoch_b200.testing import datagen
+    n = 6000
+    tgt, tn = datagen.surface(n, 11)
+    src = datagen.make_source(tgt, datagen.gt_transform((-0.5, 0.7, 1.0), (0.004, -0.002, 0.003)), 13, 14, 3e-4)
+    # rank 0 "creates the id", everybody must end up with the same bytes (stand-in for the NCCL unique id)
+    buf = torch.zeros(128, dtype=torch.uint8)
+    if rank == 0:
+        buf = torch.arange(128, dtype=torch.uint8)
+    dist.broadcast(buf, 0)
+    assert buf.tolist() == list(range(128))
+    lo, hi = shard_range(n, rank, world)
+    corr, fit, rmse = orc.correspondences(src[lo:hi], tgt, 0.03)
+    sums = orc.jtj_jtr(orc.P2PLANE, src[lo:hi], tgt, corr, tgt_nrm=tn)
+    t = torch.from_numpy(np.concatenate([sums[:28], [float(len(corr))]]))
+    dist.all_reduce(t)                       # the one collective of the sharded loop
+    full_corr = gather_correspondences(dist, corr, lo, world)
+    if rank == 0:
+        q.put((t.numpy(), full_corr))
+    dist.destroy_process_group()
+
+
+def test_sharded_sums_equal_global_sums(orc):
+    from cupoch_b200.testing import datagen
+    world, port = 2, _free_port()
+    ctx = mp.get_context("spawn")
+    q = ctx.SimpleQueue()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    red, full_corr = q.get()
+    for p in procs:
+        p.join(60)
+        assert p.exitcode == 0
+    n = 6000
+    tgt, tn = datagen.surface(n, 11)
+    src = datagen.make_source(tgt, datagen.gt_transform((-0.5, 0.7, 1.0), (0.004, -0.002, 0.003)), 13, 14, 3e-4)
+    corr, _, _ = orc.correspondences(src, tgt, 0.03)
+    sums = orc.jtj_jtr(orc.P2PLANE, src, tgt, corr, tgt_nrm=tn)
+    np.testing.assert_array_equal(full_corr, corr)             # rank-order concatenation == single-GPU list
+    assert red[28] == len(corr)
+    np.testing.assert_allclose(red[:28], sums[:28], rtol=1e-12, atol=1e-14 * np.abs(sums[:28]).max())
+    # float64 sums agree to ~1e-16: the float32 system every rank solves is identical
+    a, b = red[:27].astype(np.float32), sums[:27].astype(np.float32)
+    assert (np.abs(a.view(np.int32) - b.view(np.int32)) <= 1).all()
