@@ -135,7 +135,7 @@ def run_native(args, rank, world):
         torch.cuda.set_device(local_rank)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
         from cupoch_b200.distributed import make_comm
-        comm = make_comm(dist, rank, world, device="cuda")
+        comm = make_comm(dist, rank, world, device="cuda", kind=args.comm)
 
     n = args.points
     src, tgt, tn = make_workload(n)
@@ -160,7 +160,7 @@ def run_native(args, rank, world):
             torch.cuda.synchronize()
 
     def step_resident():
-        return R.registration_icp(s_pc, t_pc, MAX_DIST, init, est, crit, nccl_comm=comm)
+        return R.registration_icp(s_pc, t_pc, MAX_DIST, init, est, crit, comm=comm)
 
     ev = [L.cphb_event_create() for _ in range(2)]
 
@@ -200,7 +200,7 @@ def run_native(args, rank, world):
         s2 = cph.geometry.PointCloud(h_src)         # H2D (pinned)
         t2 = cph.geometry.PointCloud(h_tgt)
         t2.normals = h_tn
-        r = R.registration_icp(s2, t2, MAX_DIST, init, est, crit, nccl_comm=comm)
+        r = R.registration_icp(s2, t2, MAX_DIST, init, est, crit, comm=comm)
         # D2H: the RegistrationResult scalars (T, fitness, rmse, counts); correspondence_set_ stays on the
         # device exactly as in the reference's RegistrationResult (registration.h:51-67)
         _ = (r.transformation, r.fitness, r.inlier_rmse)
@@ -241,7 +241,7 @@ def run_native(args, rank, world):
             "config": {"workload": "config2: point-to-plane ICP 1M->1M + normals, 30 iters, r=0.02 (SURVEY.md 8d)",
                        "points": n, "iterations": ITERS, "step": "one RegistrationICP call incl. index build",
                        "cache": "256 MiB memset between timed steps (L2 flush); working set ~60 MB",
-                       "parallelism": "source sharded x%d, target replicated, 1 all-reduce(32 f64)/iter" % world},
+                       "parallelism": "source sharded x%d, target replicated, 1 exchange(32 f64)/iter via %s" % (world, args.comm if world > 1 else "none")},
             "e2e": {"value": ITERS * 1e3 / (e2e_ms / args.steps), "unit": "iter/s", "h2d_bytes_per_step": int(h2d_bytes),
                     "d2h_bytes_per_step": int(d2h[0]), "ms_per_step": e2e_ms / args.steps},
             "gpu_launches": int(launches),
@@ -262,7 +262,8 @@ def run_native(args, rank, world):
     for p in (p1, p2, p3):
         L.cphb_free_host(p)
     if comm is not None:
-        L.cphb_nccl_comm_destroy(comm)
+        barrier()
+        L.cphb_comm_destroy(comm)
     if dist is not None:
         dist.destroy_process_group()
 
@@ -291,6 +292,8 @@ def main():
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--points", type=int, default=1_000_000)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--comm", default="p2p", choices=["p2p", "nccl"],
+                    help="N>1 exchange: p2p = peer-memory stores fused into the reduce kernel, nccl = ncclAllReduce")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "native" else args.warmup
     rank = int(os.environ.get("RANK", "0"))

@@ -83,8 +83,11 @@ _SIGNATURES = {
     "cphb_event_record": (C.c_int, [_P, _P]),
     "cphb_event_elapsed_ms": (C.c_int, [_P, _P, C.POINTER(C.c_float)]),
     "cphb_nccl_unique_id": (C.c_int, [C.c_char_p]),
-    "cphb_nccl_comm_init": (C.c_int, [C.c_char_p, C.c_int, C.c_int, C.POINTER(_P)]),
-    "cphb_nccl_comm_destroy": (C.c_int, [_P]),
+    "cphb_comm_nccl_create": (C.c_int, [C.c_char_p, C.c_int, C.c_int, C.POINTER(_P)]),
+    "cphb_comm_p2p_create": (C.c_int, [C.c_int, C.c_int, C.c_char_p, C.POINTER(_P)]),
+    "cphb_comm_p2p_connect": (C.c_int, [_P, C.c_char_p]),
+    "cphb_comm_destroy": (C.c_int, [_P]),
+    "cphb_comm_allreduce_f64": (C.c_int, [_P, _P, C.c_int, _P]),
 }
 EXPORTED_SYMBOLS = sorted(_SIGNATURES)
 

@@ -97,7 +97,67 @@ int cphb_sort_pairs_u64(const uint64_t *keys_in, uint64_t *keys_out, const uint3
 int cphb_hilbert_order(const float *xyz, size_t n, uint32_t *perm_out /*device n*/,
                        float *bounds_dev6 /*or NULL*/, int bounds_given, cudaStream_t s);
 
+// ---------------------------------------------------------------------------
+// communicator for the sharded ICP (comm.cu)
+// ---------------------------------------------------------------------------
+#define CPHB_COMM_NCCL 1
+#define CPHB_COMM_P2P 2
+#define CPHB_P2P_MAX_WORLD 16
+// mailbox layout per rank: data[2][MAX_WORLD][32] doubles, then flags[2][MAX_WORLD] u64
+#define CPHB_P2P_DATA_BYTES (2 * CPHB_P2P_MAX_WORLD * 32 * 8)
+#define CPHB_P2P_BOX_BYTES (CPHB_P2P_DATA_BYTES + 2 * CPHB_P2P_MAX_WORLD * 8)
+#define CPHB_P2P_ALLOC_BYTES (CPHB_P2P_BOX_BYTES + 64) /* + this rank's private exchange counter */
+struct P2pView {
+    char *box[CPHB_P2P_MAX_WORLD];  // box[q] = rank q's mailbox as mapped into THIS process
+    int rank, world;
+};
+struct cphb_comm {
+    int kind, rank, world, connected;
+    void *nccl;
+    void *box_local;
+    P2pView view;
+};
+int cphb_nccl_allreduce_f64(void *nccl_comm, const double *send, double *recv, size_t count, cudaStream_t s);
+
 #ifdef __CUDACC__
+// One warp (lanes = columns) of every rank calls this the same number of times: returns the sum over
+// ranks of `mine`, added in rank order (bit-identical on every rank).  Data and flag stores go straight
+// to the peers' HBM over NVLink; the wait spins on this rank's own memory.  The exchange number lives in
+// this rank's device memory (every rank executes the same sequence of exchanges, so the counters agree);
+// its parity selects one of two slot sets, which is what makes back-to-back exchanges safe: a peer can be
+// at most one exchange ahead.
+__device__ __forceinline__ double p2p_exchange_sum(const P2pView &v, double mine) {
+    const int c = threadIdx.x & 31;
+    unsigned long long *ctr = (unsigned long long *)(v.box[v.rank] + CPHB_P2P_BOX_BYTES);
+    const unsigned long long epoch = *(volatile unsigned long long *)ctr + 1ull;
+    __syncwarp();
+    if (c == 0) *(volatile unsigned long long *)ctr = epoch;
+    const int par = (int)(epoch & 1ull);
+    for (int q = 0; q < v.world; ++q) {
+        double *slot = (double *)v.box[q] + ((size_t)par * CPHB_P2P_MAX_WORLD + v.rank) * 32;
+        *((volatile double *)slot + c) = mine;
+    }
+    __threadfence_system();
+    __syncwarp();
+    if (c < v.world) {
+        volatile unsigned long long *f =
+            (volatile unsigned long long *)(v.box[c] + CPHB_P2P_DATA_BYTES) + (size_t)par * CPHB_P2P_MAX_WORLD + v.rank;
+        *f = epoch;  // lane c raises this rank's flag in peer c's mailbox
+        volatile unsigned long long *mine_f =
+            (volatile unsigned long long *)(v.box[v.rank] + CPHB_P2P_DATA_BYTES) + (size_t)par * CPHB_P2P_MAX_WORLD + c;
+        while (*mine_f < epoch) {
+        }
+    }
+    __syncwarp();
+    __threadfence_system();
+    double tot = 0.0;
+    for (int q = 0; q < v.world; ++q) {
+        const double *slot = (const double *)v.box[v.rank] + ((size_t)par * CPHB_P2P_MAX_WORLD + q) * 32;
+        tot += *((const volatile double *)slot + c);
+    }
+    return tot;
+}
+
 // ---------------------------------------------------------------------------
 // device helpers
 // ---------------------------------------------------------------------------

@@ -61,7 +61,9 @@ struct IcpArgs {
     float rel_fitness, rel_rmse, det_thresh, sg, sp;
     int launch_idx, max_iter;
     int tgt_cov_col_major;
-    int defer_finalize;  // multi-GPU: stop after writing st->local
+    int defer_finalize;  // multi-GPU over NCCL: stop after writing st->local
+    int use_p2p;         // multi-GPU over the fused peer-memory exchange
+    P2pView p2p;
     int step_mode;       // debug hook: one search + sums, no solve
 };
 
@@ -633,6 +635,7 @@ __global__ void __launch_bounds__(ICP_REDUCE_BLOCK) icp_reduce_kernel(const __gr
     if (threadIdx.x < 32) {
         double t = 0.0;
         for (unsigned b = 0; b < gridDim.x; ++b) t += __ldcg(&a.partials[(size_t)b * 32 + threadIdx.x]);
+        if (a.use_p2p) t = p2p_exchange_sum(a.p2p, t);  // the collective, fused: NVLink stores + flags
         if (a.defer_finalize) st->local[threadIdx.x] = t;
         else st->total[threadIdx.x] = t;
     }
@@ -940,7 +943,6 @@ __global__ void __launch_bounds__(256) transform_kernel(float *p, float *nrm, fl
 // ===========================================================================
 // host driver
 // ===========================================================================
-int cphb_nccl_allreduce_f64(void *comm, const double *send, double *recv, size_t count, cudaStream_t s);  // nccl_dyn.cu
 
 struct cphb_icp {
     cphb_index *index;
@@ -1182,7 +1184,7 @@ static int compact_correspondences(cphb_icp *icp, int32_t *corr_out, cudaStream_
     return CPHB_OK;
 }
 
-extern "C" int cphb_icp_run(cphb_icp *icp, const float h_init[16], void *nccl_comm, cphb_icp_result *h_result,
+extern "C" int cphb_icp_run(cphb_icp *icp, const float h_init[16], cphb_comm *comm, cphb_icp_result *h_result,
                             int32_t *corr_out, void *stream) {
     cudaStream_t s = (cudaStream_t)stream;
     if (!icp || !h_init || !h_result) {
@@ -1201,17 +1203,24 @@ extern "C" int cphb_icp_run(cphb_icp *icp, const float h_init[16], void *nccl_co
     fill_args(icp, a);
     a.corr_index = corr_out ? icp->corr_index : nullptr;
     unsigned long long n_total = icp->n_src;
-    if (nccl_comm) {
-        // global source size: one tiny all-reduce before the loop
+    void *nccl_comm = nullptr;
+    if (comm && comm->world > 1) {
+        // global source size: one tiny exchange before the loop
         double *tmp = icp->partials;  // scratch
         double hn = (double)icp->n_src;
         CPHB_CUDA(cudaMemcpyAsync(tmp, &hn, 8, cudaMemcpyHostToDevice, s));
-        rc = cphb_nccl_allreduce_f64(nccl_comm, tmp, tmp, 1, s);
+        rc = cphb_comm_allreduce_f64(comm, tmp, 1, s);
         if (rc) return rc;
         CPHB_CUDA(cudaMemcpyAsync(&hn, tmp, 8, cudaMemcpyDeviceToHost, s));
         CPHB_CUDA(cudaStreamSynchronize(s));
         n_total = (unsigned long long)hn;
-        a.defer_finalize = 1;
+        if (comm->kind == CPHB_COMM_NCCL) {
+            nccl_comm = comm->nccl;
+            a.defer_finalize = 1;
+        } else {
+            a.use_p2p = 1;
+            a.p2p = comm->view;
+        }
     }
     a.n_total = n_total;
     // launches 0..max_iter: search (+ update).  If the convergence test stops the loop at launch
@@ -1278,12 +1287,12 @@ extern "C" int cphb_icp_step(cphb_icp *icp, const float h_T[16], double h_sums[3
 }
 
 extern "C" int cphb_registration_icp(const cphb_cloud *source, const cphb_cloud *target, const float h_init[16],
-                                     const cphb_icp_params *params, void *nccl_comm, cphb_icp_result *h_result,
+                                     const cphb_icp_params *params, cphb_comm *comm, cphb_icp_result *h_result,
                                      int32_t *corr_out, void *stream) {
     cphb_icp *icp = nullptr;
     int rc = cphb_icp_create(source, target, params, stream, &icp);
     if (rc) return rc;
-    rc = cphb_icp_run(icp, h_init, nccl_comm, h_result, corr_out, stream);
+    rc = cphb_icp_run(icp, h_init, comm, h_result, corr_out, stream);
     cphb_icp_destroy(icp);
     return rc;
 }

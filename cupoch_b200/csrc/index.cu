@@ -58,16 +58,15 @@ void cphb_free_async(void *p, cudaStream_t s) {
     if (p) cudaFreeAsync(p, s);
 }
 
+// Stream-ordered pool allocation on the default stream: freed blocks stay in the pool (release threshold
+// = max), so repeated allocate/free cycles of the API layers cost microseconds instead of cudaMalloc/cudaFree.
 extern "C" void *cphb_malloc(size_t bytes) {
     void *p = nullptr;
-    if (cudaMalloc(&p, bytes ? bytes : 16) != cudaSuccess) {
-        cphb_set_error("cudaMalloc(%zu) failed: %s", bytes, cudaGetErrorString(cudaGetLastError()));
-        return nullptr;
-    }
+    if (cphb_alloc_async(&p, bytes ? bytes : 16, (cudaStream_t)0) != CPHB_OK) return nullptr;
     return p;
 }
 extern "C" void cphb_free(void *p) {
-    if (p) cudaFree(p);
+    if (p) cudaFreeAsync(p, (cudaStream_t)0);
 }
 extern "C" void *cphb_malloc_host(size_t bytes) {
     void *p = nullptr;

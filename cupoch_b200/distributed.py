@@ -1,9 +1,9 @@
 """Multi-GPU plumbing for the sharded ICP: one process per GPU, the source is split
 into contiguous blocks, the target is replicated, one all-reduce of 32 doubles per iteration.
 
-torch.distributed is used only for rendezvous (broadcasting the 128-byte NCCL unique id); the
-communicator itself is created inside libcupoch_b200.so (cphb_nccl_comm_init) and used by the fused
-loop (cphb_icp_run(..., nccl_comm))."""
+torch.distributed is used only for rendezvous (exchanging the CUDA IPC handles or the NCCL unique id);
+the communicator itself lives inside libcupoch_b200.so (cphb_comm_*) and is used by the fused loop
+(cphb_icp_run(..., comm))."""
 import ctypes as C
 
 from . import _lib
@@ -32,17 +32,33 @@ def broadcast_unique_id(dist, rank, device=None):
     return bytes(buf.cpu().numpy().tobytes())
 
 
-def make_comm(dist, rank, world, device=None):
-    """-> opaque ncclComm_t handle (ctypes.c_void_p) usable as `nccl_comm=` in cupoch_b200.registration."""
-    uid = broadcast_unique_id(dist, rank, device)
+def make_comm(dist, rank, world, device=None, kind="p2p"):
+    """-> opaque cphb_comm* (ctypes.c_void_p) usable as `comm=` in cupoch_b200.registration.
+    kind "p2p": CUDA-IPC mailboxes, the per-iteration exchange is fused into the reduce kernel (NVLink
+    stores + flags); kind "nccl": ncclAllReduce."""
+    import torch
+    L = _lib.lib()
     h = C.c_void_p()
-    _lib.check(_lib.lib().cphb_nccl_comm_init(uid, world, rank, C.byref(h)))
+    if kind == "nccl":
+        uid = broadcast_unique_id(dist, rank, device)
+        _lib.check(L.cphb_comm_nccl_create(uid, world, rank, C.byref(h)))
+        return h
+    mine = C.create_string_buffer(64)
+    _lib.check(L.cphb_comm_p2p_create(world, rank, mine, C.byref(h)))
+    t = torch.frombuffer(bytearray(mine.raw), dtype=torch.uint8).clone()
+    if device is not None:
+        t = t.to(device)
+    allh = [torch.zeros_like(t) for _ in range(world)]
+    dist.all_gather(allh, t)
+    blob = b"".join(bytes(x.cpu().numpy().tobytes()) for x in allh)
+    _lib.check(L.cphb_comm_p2p_connect(h, blob))
+    dist.barrier()
     return h
 
 
 def destroy_comm(comm):
     if comm:
-        _lib.check(_lib.lib().cphb_nccl_comm_destroy(comm))
+        _lib.check(_lib.lib().cphb_comm_destroy(comm))
 
 
 def gather_correspondences(dist, local_corr, lo, world):

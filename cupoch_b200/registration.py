@@ -140,7 +140,7 @@ def _result(res, corr, want_corr):
 
 
 def registration_icp(source, target, max_correspondence_distance, init=None,
-                     estimation_method=None, criteria=None, nccl_comm=None, return_correspondences=True):
+                     estimation_method=None, criteria=None, comm=None, return_correspondences=True):
     """registration::RegistrationICP (registration.cu:121-173)."""
     estimation_method = estimation_method or TransformationEstimationPointToPoint()
     criteria = criteria or ICPConvergenceCriteria()
@@ -154,7 +154,7 @@ def registration_icp(source, target, max_correspondence_distance, init=None,
     p = _params(estimation_method, max_correspondence_distance, criteria)
     res = _lib.IcpResult()
     corr = _DevicePool.take((max(len(source), 1), 2), np.int32) if return_correspondences else None
-    _lib.check(_lib.lib().cphb_registration_icp(C.byref(sc), C.byref(tc), as_f16(init), C.byref(p), nccl_comm,
+    _lib.check(_lib.lib().cphb_registration_icp(C.byref(sc), C.byref(tc), as_f16(init), C.byref(p), comm,
                                                 C.byref(res), corr.ptr if corr else None, None))
     return _result(res, corr, return_correspondences)
 
@@ -188,11 +188,11 @@ def _with_covariances(pcd, epsilon):
 
 
 def registration_generalized_icp(source, target, max_correspondence_distance, init=None, estimation=None,
-                                 criteria=None, nccl_comm=None, return_correspondences=True):
+                                 criteria=None, comm=None, return_correspondences=True):
     """registration::RegistrationGeneralizedICP (generalized_icp.cu:185-198)."""
     estimation = estimation or TransformationEstimationForGeneralizedICP()
     return registration_icp(_with_covariances(source, estimation.epsilon), _with_covariances(target, estimation.epsilon),
-                            max_correspondence_distance, init, estimation, criteria, nccl_comm, return_correspondences)
+                            max_correspondence_distance, init, estimation, criteria, comm, return_correspondences)
 
 
 def initialize_pointcloud_for_colored_icp(target, radius, max_nn=30):
@@ -212,11 +212,11 @@ def initialize_pointcloud_for_colored_icp(target, radius, max_nn=30):
 
 
 def registration_colored_icp(source, target, max_correspondence_distance, init=None, criteria=None,
-                             lambda_geometric=0.968, det_thresh=1e-6, nccl_comm=None, return_correspondences=True):
+                             lambda_geometric=0.968, det_thresh=1e-6, comm=None, return_correspondences=True):
     """registration::RegistrationColoredICP (colored_icp.cu:329-342)."""
     target_c = initialize_pointcloud_for_colored_icp(target, max_correspondence_distance * 2.0, 30)
     return registration_icp(source, target_c, max_correspondence_distance, init,
-                            TransformationEstimationForColoredICP(lambda_geometric, det_thresh), criteria, nccl_comm,
+                            TransformationEstimationForColoredICP(lambda_geometric, det_thresh), criteria, comm,
                             return_correspondences)
 
 
@@ -236,10 +236,10 @@ class IcpContext:
         self._corr = DeviceArray((max(len(source), 1), 2), np.int32)
         self._ci = DeviceArray((max(len(source), 1),), np.int32)
 
-    def run(self, init=None, nccl_comm=None, return_correspondences=True):
+    def run(self, init=None, comm=None, return_correspondences=True):
         init = np.eye(4, dtype=np.float32) if init is None else init
         res = _lib.IcpResult()
-        _lib.check(_lib.lib().cphb_icp_run(self._h, as_f16(init), nccl_comm, C.byref(res),
+        _lib.check(_lib.lib().cphb_icp_run(self._h, as_f16(init), comm, C.byref(res),
                                            self._corr.ptr if return_correspondences else None, None))
         out = _result(res, None, False)
         if return_correspondences:

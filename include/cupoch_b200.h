@@ -171,6 +171,7 @@ typedef struct cphb_icp_result {
 } cphb_icp_result;
 
 typedef struct cphb_icp cphb_icp;
+typedef struct cphb_comm cphb_comm; /* multi-GPU communicator, see the end of this header */
 
 /* Build the per-call state of RegistrationICP (registration.cu:146-147): the
  * spatial index over target.points and a Hilbert-ordered working copy of the
@@ -182,12 +183,12 @@ void cphb_icp_destroy(cphb_icp *icp);
 
 /* Run the loop of RegistrationICP (registration.cu:148-172) from init.  One
  * fused kernel per iteration, no host round trip inside the loop.
- * nccl_comm: NULL (single GPU) or an ncclComm_t whose ranks each hold a
- * contiguous shard of the source; the 32 partial sums are all-reduced once
- * per iteration.  corr_out (device, optional): 2*source.n int32 receiving the
+ * comm: NULL (single GPU) or a communicator whose ranks each hold a contiguous
+ * shard of the source; the 32 partial sums are exchanged once per iteration
+ * (NCCL all-reduce, or the peer-memory exchange fused into the reduce kernel).  corr_out (device, optional): 2*source.n int32 receiving the
  * final correspondence set (i, j) ascending in i (local shard indices).
  * Synchronises the stream before returning h_result. */
-int cphb_icp_run(cphb_icp *icp, const float h_init[16], void *nccl_comm,
+int cphb_icp_run(cphb_icp *icp, const float h_init[16], cphb_comm *comm,
                  cphb_icp_result *h_result, int32_t *corr_out, void *stream);
 
 /* Debug / test hook: one GetRegistrationResultAndCorrespondences +
@@ -206,7 +207,7 @@ int cphb_icp_step(cphb_icp *icp, const float h_T[16], double h_sums[32],
  * Initialize* helpers do). */
 int cphb_registration_icp(const cphb_cloud *source, const cphb_cloud *target,
                           const float h_init[16], const cphb_icp_params *params,
-                          void *nccl_comm, cphb_icp_result *h_result, int32_t *corr_out,
+                          cphb_comm *comm, cphb_icp_result *h_result, int32_t *corr_out,
                           void *stream);
 
 /* TransformationEstimation*::ComputeTransformation / ComputeRMSE on an explicit correspondence list
@@ -244,10 +245,22 @@ void *cphb_event_create(void);
 void cphb_event_destroy(void *event);
 int cphb_event_record(void *event, void *stream);
 int cphb_event_elapsed_ms(void *start, void *stop, float *h_ms); /* synchronises on stop */
-/* NCCL bootstrap without torch types: unique id is 128 bytes. */
+/* ------------------------------------------------------------------------ *
+ * Multi-GPU communicator (one process per GPU, one node).  Two kinds:
+ *  NCCL: rank 0 calls cphb_nccl_unique_id, the 128 bytes reach every rank by any means
+ *        (torch.distributed broadcast, MPI, a file), every rank calls cphb_comm_nccl_create.
+ *  P2P : every rank calls cphb_comm_p2p_create (allocates a mailbox in its HBM and returns a 64-byte
+ *        CUDA IPC handle), the handles are all-gathered in rank order by any means, every rank calls
+ *        cphb_comm_p2p_connect.  The per-iteration exchange is then fused into the ICP reduce kernel:
+ *        NVLink stores into the peers' mailboxes + flags, no collective library on the path.
+ * ------------------------------------------------------------------------ */
 int cphb_nccl_unique_id(char h_id[128]);
-int cphb_nccl_comm_init(const char h_id[128], int world_size, int rank, void **out_comm);
-int cphb_nccl_comm_destroy(void *comm);
+int cphb_comm_nccl_create(const char h_id[128], int world_size, int rank, cphb_comm **out);
+int cphb_comm_p2p_create(int world_size, int rank, char h_handle[64], cphb_comm **out);
+int cphb_comm_p2p_connect(cphb_comm *comm, const char *h_handles /* world_size * 64 bytes */);
+int cphb_comm_destroy(cphb_comm *comm);
+/* in-place sum over ranks of <= 32 doubles (device buffer); what the ICP loop uses, exposed for tests */
+int cphb_comm_allreduce_f64(cphb_comm *comm, double *buf, int count, void *stream);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,65 @@
+#!/usr/bin/env python3
+"""Run under torchrun (one rank per GPU): sharded ICP (peer-memory exchange and NCCL) vs the same
+registration on one GPU.  Rank 0 prints one JSON line.  usage:
+  python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P tools/multi_gpu_check.py
+"""
+import json
+import os
+import sys
+
+import numpy as np
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+
+
+def main():
+    import torch
+    import torch.distributed as dist
+    import cupoch_b200 as cph
+    from cupoch_b200 import _lib
+    from cupoch_b200.distributed import destroy_comm, gather_correspondences, make_comm, shard_range
+    from cupoch_b200.testing import datagen
+    rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+    lr = int(os.environ.get("LOCAL_RANK", rank))
+    torch.cuda.set_device(lr)
+    _lib.check(_lib.lib().cphb_set_device(lr))
+    dist.init_process_group("nccl", device_id=torch.device("cuda", lr))
+    n = int(os.environ.get("CHECK_POINTS", "300000"))
+    tgt, tn = datagen.surface(n, 11)
+    src = datagen.make_source(tgt, datagen.gt_transform(), 13, 14, 5e-4)
+    lo, hi = shard_range(n, rank, world)
+    R = cph.registration
+    est, crit = R.TransformationEstimationPointToPlane(), R.ICPConvergenceCriteria(0, 0, 20)
+    t_pc = cph.geometry.PointCloud(tgt)
+    t_pc.normals = tn
+    s_pc = cph.geometry.PointCloud(np.ascontiguousarray(src[lo:hi]))
+    out = {"world": world, "points": n}
+    for kind in ("p2p", "nccl"):
+        comm = make_comm(dist, rank, world, device="cuda", kind=kind)
+        res = R.registration_icp(s_pc, t_pc, 0.02, np.eye(4), est, crit, comm=comm)
+        res2 = R.registration_icp(s_pc, t_pc, 0.02, np.eye(4), est, crit, comm=comm)   # back-to-back runs on one comm
+        corr = gather_correspondences(dist, res.correspondence_set, lo, world)
+        Ts = [None] * world
+        dist.all_gather_object(Ts, res.transformation.tolist())
+        out[kind] = {"T": res.transformation.tolist(), "fitness": res.fitness, "rmse": res.inlier_rmse,
+                     "ranks_agree": all(t == Ts[0] for t in Ts),
+                     "rerun_identical": bool(np.array_equal(res.transformation, res2.transformation)),
+                     "loop_ms": res.loop_ms, "n_corr": int(len(corr))}
+        dist.barrier()
+        destroy_comm(comm)
+        if rank == 0:
+            out[kind]["_corr"] = corr
+    if rank == 0:
+        full = R.registration_icp(cph.geometry.PointCloud(src), t_pc, 0.02, np.eye(4), est, crit)
+        for kind in ("p2p", "nccl"):
+            c = out[kind].pop("_corr")
+            out[kind]["pose_diff_vs_1gpu"] = float(np.linalg.norm(np.array(out[kind]["T"], np.float64) - full.transformation))
+            out[kind]["corr_equal_1gpu"] = bool(np.array_equal(c, full.correspondence_set))
+            out[kind].pop("T")
+        out["single"] = {"fitness": full.fitness, "rmse": full.inlier_rmse, "loop_ms": full.loop_ms}
+        print(json.dumps(out))
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
