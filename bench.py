@@ -141,7 +141,9 @@ def run_native(args, rank, world):
     src, tgt, tn = make_workload(n)
     from cupoch_b200.distributed import shard_range
     lo, hi = shard_range(n, rank, world)
-    src_local = np.ascontiguousarray(src[lo:hi])
+    # every rank holds the full source; the library keeps this rank's Hilbert-contiguous block of it
+    src_local = src
+    shard = (rank, world) if world > 1 else None
     R = cph.registration
     est, crit = R.TransformationEstimationPointToPlane(), R.ICPConvergenceCriteria(0, 0, ITERS)
     init = np.eye(4, dtype=np.float32)
@@ -160,7 +162,7 @@ def run_native(args, rank, world):
             torch.cuda.synchronize()
 
     def step_resident():
-        return R.registration_icp(s_pc, t_pc, MAX_DIST, init, est, crit, comm=comm)
+        return R.registration_icp(s_pc, t_pc, MAX_DIST, init, est, crit, comm=comm, shard=shard)
 
     ev = [L.cphb_event_create() for _ in range(2)]
 
@@ -200,7 +202,7 @@ def run_native(args, rank, world):
         s2 = cph.geometry.PointCloud(h_src)         # H2D (pinned)
         t2 = cph.geometry.PointCloud(h_tgt)
         t2.normals = h_tn
-        r = R.registration_icp(s2, t2, MAX_DIST, init, est, crit, comm=comm)
+        r = R.registration_icp(s2, t2, MAX_DIST, init, est, crit, comm=comm, shard=shard)
         # D2H: the RegistrationResult scalars (T, fitness, rmse, counts); correspondence_set_ stays on the
         # device exactly as in the reference's RegistrationResult (registration.h:51-67)
         _ = (r.transformation, r.fitness, r.inlier_rmse)
@@ -213,9 +215,10 @@ def run_native(args, rank, world):
 
     # ---- kNN leg of the metric: SearchRadius(k=1, r) of the 1M source against the 1M target ------
     tree = cph.geometry.KDTreeFlann(t_pc)
+    q_pc = cph.geometry.PointCloud(np.ascontiguousarray(src[lo:hi]))   # queries: no collective, shard by index
     for _ in range(2):
-        tree.search_radius(s_pc.points, MAX_DIST, 1)
-    knn_ms, _ = timed(lambda: tree.search_radius(s_pc.points, MAX_DIST, 1), max(args.steps, 3))
+        tree.search_radius(q_pc.points, MAX_DIST, 1)
+    knn_ms, _ = timed(lambda: tree.search_radius(q_pc.points, MAX_DIST, 1), max(args.steps, 3))
     knn_steps = max(args.steps, 3)
     if rank == 0:
         sampler.stop_flag = True
@@ -241,7 +244,8 @@ def run_native(args, rank, world):
             "config": {"workload": "config2: point-to-plane ICP 1M->1M + normals, 30 iters, r=0.02 (SURVEY.md 8d)",
                        "points": n, "iterations": ITERS, "step": "one RegistrationICP call incl. index build",
                        "cache": "256 MiB memset between timed steps (L2 flush); working set ~60 MB",
-                       "parallelism": "source sharded x%d, target replicated, 1 exchange(32 f64)/iter via %s" % (world, args.comm if world > 1 else "none")},
+                       "parallelism": "source sharded x%d (Hilbert-contiguous blocks), target replicated, 1 exchange(32 f64)/iter via %s"
+                                      % (world, args.comm if world > 1 else "none")},
             "e2e": {"value": ITERS * 1e3 / (e2e_ms / args.steps), "unit": "iter/s", "h2d_bytes_per_step": int(h2d_bytes),
                     "d2h_bytes_per_step": int(d2h[0]), "ms_per_step": e2e_ms / args.steps},
             "gpu_launches": int(launches),

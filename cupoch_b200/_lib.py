@@ -27,12 +27,14 @@ class Cloud(C.Structure):
 class IcpParams(C.Structure):
     _fields_ = [("estimation", C.c_int), ("max_correspondence_distance", C.c_float),
                 ("relative_fitness", C.c_float), ("relative_rmse", C.c_float), ("max_iteration", C.c_int),
-                ("det_thresh", C.c_float), ("lambda_geometric", C.c_float), ("flags", C.c_int)]
+                ("det_thresh", C.c_float), ("lambda_geometric", C.c_float), ("flags", C.c_int),
+                ("shard_rank", C.c_int), ("shard_world", C.c_int)]
 
 
 class IcpResult(C.Structure):
     _fields_ = [("transformation", C.c_float * 16), ("fitness", C.c_float), ("inlier_rmse", C.c_float),
-                ("n_correspondences", C.c_int64), ("iterations", C.c_int), ("converged", C.c_int),
+                ("n_correspondences", C.c_int64), ("n_local_correspondences", C.c_int64), ("iterations", C.c_int),
+                ("converged", C.c_int),
                 ("loop_ms", C.c_float), ("loop_launches", C.c_int)]
 
 

@@ -31,6 +31,7 @@ struct Box {
 
 struct IndexView {
     const float4 *pts;
+    const uint32_t *inv;  // inv[original index] = position in Hilbert order
     const Box *boxes[CPHB_LEVELS];
     unsigned long long n;
     unsigned n_leaves;

@@ -19,6 +19,7 @@
 // float32 like the reference's host code.
 #include <float.h>
 #include <math.h>
+#include <stddef.h>
 #include <string.h>
 
 #include "cphb_internal.cuh"
@@ -41,6 +42,8 @@ struct IcpState {
     unsigned ticket;
     unsigned tile_counter;
     long long n_corr;
+    unsigned pad_local;  // host-side staging only (count of locally written correspondence pairs)
+    unsigned pad_;
 };
 
 struct IcpArgs {
@@ -796,11 +799,12 @@ __global__ void estimate_solve_kernel(const double *S, unsigned long long n_mode
 // ---------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) gather_source_kernel(const float *__restrict__ xyz, const float *__restrict__ nrm,
                                                             const float *__restrict__ col, const float *__restrict__ cov,
-                                                            int cov_col_major, const uint32_t *__restrict__ perm,
-                                                            unsigned n, unsigned n_pad, float4 *o_xyz, float4 *o_nrm,
-                                                            float4 *o_col, float4 *o_cov) {
+                                                            int cov_col_major, const uint32_t *__restrict__ perm_all,
+                                                            unsigned lo, unsigned n, unsigned n_pad, float4 *o_xyz,
+                                                            float4 *o_nrm, float4 *o_col, float4 *o_cov) {
     unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n_pad) return;
+    const uint32_t *perm = perm_all + lo;  // this rank's block of the Hilbert order
     if (i < n) {
         size_t j = perm[i];
         o_xyz[i] = make_float4(xyz[3 * j], xyz[3 * j + 1], xyz[3 * j + 2], __uint_as_float((unsigned)j));
@@ -823,6 +827,41 @@ __global__ void __launch_bounds__(256) gather_source_kernel(const float *__restr
         if (o_cov)
             for (int r = 0; r < 3; ++r) o_cov[(size_t)r * n_pad + i] = make_float4(0.f, 0.f, 0.f, 0.f);
     }
+}
+
+// ---------------------------------------------------------------------------
+// Re-tiling: once the clouds are roughly aligned, re-order the working copy by the Hilbert position of
+// each point's current match, so that a warp's 32 queries fall into one or two target leaves instead
+// of straddling a dozen.  Pure permutation of the working arrays (w / prev travel with the point): the
+// result set is unchanged, only the order in which exact products are added to the float64 sums.
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) retile_key_kernel(const int *__restrict__ prev, const uint32_t *__restrict__ inv,
+                                                         unsigned n_src, unsigned n_pad, uint32_t *keys, uint32_t *vals) {
+    unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_pad) return;
+    uint32_t k = 0xffffffffu;  // padding stays last
+    if (i < n_src) {
+        const int pj = prev[i];
+        k = (pj >= 0) ? inv[pj] : 0xfffffffeu;  // unmatched points after the matched ones
+    }
+    keys[i] = k;
+    vals[i] = i;
+}
+__global__ void __launch_bounds__(256) retile_gather_kernel(const uint32_t *__restrict__ order, unsigned n_pad,
+                                                            const float4 *__restrict__ xyz, const int *__restrict__ prev,
+                                                            const float4 *__restrict__ nrm, const float4 *__restrict__ col,
+                                                            const float4 *__restrict__ cov, float4 *o_xyz, int *o_prev,
+                                                            float4 *o_nrm, float4 *o_col, float4 *o_cov) {
+    unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_pad) return;
+    const unsigned s = order[i];
+    o_xyz[i] = xyz[s];
+    o_prev[i] = prev[s];
+    if (nrm) o_nrm[i] = nrm[s];
+    if (col) o_col[i] = col[s];
+    if (cov)
+#pragma unroll
+        for (int r = 0; r < 3; ++r) o_cov[(size_t)r * n_pad + i] = cov[(size_t)r * n_pad + s];
 }
 
 // stable compaction of (i, corr_index[i]) with corr_index[i] >= 0 (registration.cu:54-69)
@@ -949,11 +988,15 @@ struct cphb_icp {
     cphb_icp_params prm;
     cphb_cloud tgt;
     unsigned n_src, n_pad;
+    unsigned n_full;   // size of the source as passed (== n_src unless the library shards it)
     void *arena;
     size_t arena_bytes;
     float4 *pristine_xyz, *pristine_nrm, *pristine_cov;  // Hilbert-ordered source as given
     float4 *work_xyz, *work_nrm, *work_cov;
     float4 *src_col;
+    float4 *alt_xyz, *alt_nrm, *alt_cov, *alt_col, *cur_col;  // re-tiling ping-pong buffers
+    int *alt_prev;
+    uint32_t *rt_keys, *rt_keys2, *rt_vals, *rt_order;
     IcpState *st;
     IcpState *h_st;  // pinned
     bool owns_host;
@@ -1035,7 +1078,20 @@ extern "C" int cphb_icp_create(const cphb_cloud *source, const cphb_cloud *targe
     icp->stream = s;
     int rc = cphb_index_create(target->points, target->n, s, &icp->index);
     if (rc) { delete icp; return rc; }
-    const unsigned n = (unsigned)source->n;
+    const unsigned n_full = (unsigned)source->n;
+    unsigned lo = 0, n = n_full;
+    if (params->shard_world > 1) {
+        if (params->shard_rank < 0 || params->shard_rank >= params->shard_world) {
+            cphb_set_error("cphb_icp_create: shard_rank %d outside [0,%d)", params->shard_rank, params->shard_world);
+            cphb_index_destroy(icp->index);
+            delete icp;
+            return CPHB_ERR_INVALID;
+        }
+        lo = (unsigned)(((unsigned long long)n_full * params->shard_rank) / params->shard_world);
+        unsigned hi = (unsigned)(((unsigned long long)n_full * (params->shard_rank + 1)) / params->shard_world);
+        n = hi - lo;
+    }
+    icp->n_full = n_full;
     const unsigned n_pad = (unsigned)cphb_align(n ? n : 1, ICP_BLOCK);
     icp->n_src = n;
     icp->n_pad = n_pad;
@@ -1063,11 +1119,16 @@ extern "C" int cphb_icp_create(const cphb_cloud *source, const cphb_cloud *targe
     size_t o_part = take(sizeof(double) * 32 * icp->reduce_grid);
     size_t o_ts = take(sizeof(double) * n_pad);
     size_t o_prev = take(sizeof(int) * n_pad);
-    size_t o_ci = take(sizeof(int32_t) * n_pad);
-    unsigned cmp_blocks = (n_pad + CMP_BLOCK - 1) / CMP_BLOCK;
+    size_t o_axyz = take(sizeof(float4) * n_pad), o_aprev = take(sizeof(int) * n_pad);
+    size_t o_anrm = want_nrm ? take(sizeof(float4) * n_pad) : 0, o_acov = want_cov ? take(sizeof(float4) * 3 * n_pad) : 0;
+    size_t o_acol = want_col ? take(sizeof(float4) * n_pad) : 0, o_ccol = want_col ? take(sizeof(float4) * n_pad) : 0;
+    size_t o_rt = take(sizeof(uint32_t) * 4 * n_pad);
+    const unsigned nf_pad = (unsigned)cphb_align(n_full ? n_full : 1, ICP_BLOCK);
+    size_t o_ci = take(sizeof(int32_t) * nf_pad);
+    unsigned cmp_blocks = (nf_pad + CMP_BLOCK - 1) / CMP_BLOCK;
     size_t o_cc = take(sizeof(unsigned) * (cmp_blocks + 1));
     size_t o_ct = take(16);
-    size_t o_perm = take(sizeof(uint32_t) * n_pad);
+    size_t o_perm = take(sizeof(uint32_t) * nf_pad);
     icp->arena_bytes = off;
     rc = cphb_alloc_async(&icp->arena, off, s);
     if (rc) { cphb_index_destroy(icp->index); delete icp; return rc; }
@@ -1083,6 +1144,16 @@ extern "C" int cphb_icp_create(const cphb_cloud *source, const cphb_cloud *targe
     icp->partials = (double *)(b + o_part);
     icp->tile_sums = (double *)(b + o_ts);
     icp->prev = (int *)(b + o_prev);
+    icp->alt_xyz = (float4 *)(b + o_axyz);
+    icp->alt_prev = (int *)(b + o_aprev);
+    icp->alt_nrm = want_nrm ? (float4 *)(b + o_anrm) : nullptr;
+    icp->alt_cov = want_cov ? (float4 *)(b + o_acov) : nullptr;
+    icp->alt_col = want_col ? (float4 *)(b + o_acol) : nullptr;
+    icp->cur_col = want_col ? (float4 *)(b + o_ccol) : nullptr;
+    icp->rt_keys = (uint32_t *)(b + o_rt);
+    icp->rt_keys2 = icp->rt_keys + n_pad;
+    icp->rt_vals = icp->rt_keys + 2 * (size_t)n_pad;
+    icp->rt_order = icp->rt_keys + 3 * (size_t)n_pad;
     icp->corr_index = (int32_t *)(b + o_ci);
     icp->cmp_counts = (unsigned *)(b + o_cc);
     icp->cmp_total = (unsigned *)(b + o_ct);
@@ -1104,12 +1175,12 @@ extern "C" int cphb_icp_create(const cphb_cloud *source, const cphb_cloud *targe
         CPHB_CUDA(cudaEventCreate(&icp->ev0));
         CPHB_CUDA(cudaEventCreate(&icp->ev1));
     }
-    if (n) {
-        rc = cphb_hilbert_order(source->points, n, perm, nullptr, 0, s);
+    if (n_full) {
+        rc = cphb_hilbert_order(source->points, n_full, perm, nullptr, 0, s);
         if (rc) { cphb_icp_destroy(icp); return rc; }
     }
     CPHB_LAUNCH(gather_source_kernel, n_pad / 256, 256, 0, s, source->points, source->normals, source->colors,
-                source->covariances, source->cov_col_major, perm, n, n_pad, icp->pristine_xyz, icp->pristine_nrm,
+                source->covariances, source->cov_col_major, perm, lo, n, n_pad, icp->pristine_xyz, icp->pristine_nrm,
                 icp->src_col, icp->pristine_cov);
     CPHB_CHECK_LAUNCH();
     *out = icp;
@@ -1174,13 +1245,37 @@ static int reset_working_copy(cphb_icp *icp, cudaStream_t s) {
 }
 
 static int compact_correspondences(cphb_icp *icp, int32_t *corr_out, cudaStream_t s) {
-    unsigned n = icp->n_src;
+    unsigned n = icp->n_full;
     unsigned nb = (n + CMP_BLOCK - 1) / CMP_BLOCK;
     if (nb == 0) nb = 1;
     CPHB_LAUNCH(compact_count_kernel, nb, CMP_BLOCK, 0, s, icp->corr_index, n, icp->cmp_counts);
     CPHB_LAUNCH(compact_scan_kernel, 1, 1024, 0, s, icp->cmp_counts, nb, icp->cmp_total);
     CPHB_LAUNCH(compact_write_kernel, nb, CMP_BLOCK, 0, s, icp->corr_index, n, icp->cmp_counts, corr_out);
     CPHB_CHECK_LAUNCH();
+    return CPHB_OK;
+}
+
+// permute the working arrays referenced by `a` into the alt buffers and swap
+static int retile(cphb_icp *icp, IcpArgs &a, cudaStream_t s) {
+    const unsigned n_pad = icp->n_pad, grid = n_pad / 256;
+    CPHB_LAUNCH(retile_key_kernel, grid, 256, 0, s, a.prev, icp->index->v.inv, icp->n_src, n_pad, icp->rt_keys, icp->rt_vals);
+    CPHB_CHECK_LAUNCH();
+    // keys are target positions or the sentinels 0xfffffffe / 0xffffffff: 32-bit radix sort, 4 onesweep passes
+    int rc = cphb_sort_pairs_u32(icp->rt_keys, icp->rt_keys2, icp->rt_vals, icp->rt_order, n_pad, 32, s);
+    if (rc) return rc;
+    float4 *o_xyz = (a.src == icp->work_xyz) ? icp->alt_xyz : icp->work_xyz;
+    int *o_prev = (a.prev == icp->prev) ? icp->alt_prev : icp->prev;
+    float4 *o_nrm = a.src_nrm ? ((a.src_nrm == icp->work_nrm) ? icp->alt_nrm : icp->work_nrm) : nullptr;
+    float4 *o_cov = a.src_cov ? ((a.src_cov == icp->work_cov) ? icp->alt_cov : icp->work_cov) : nullptr;
+    float4 *o_col = a.src_col ? ((a.src_col == icp->alt_col) ? icp->cur_col : icp->alt_col) : nullptr;
+    CPHB_LAUNCH(retile_gather_kernel, grid, 256, 0, s, icp->rt_order, n_pad, a.src, a.prev, a.src_nrm, a.src_col, a.src_cov,
+                o_xyz, o_prev, o_nrm, o_col, o_cov);
+    CPHB_CHECK_LAUNCH();
+    a.src = o_xyz;
+    a.prev = o_prev;
+    a.src_nrm = o_nrm;
+    a.src_cov = o_cov;
+    a.src_col = o_col;
     return CPHB_OK;
 }
 
@@ -1202,10 +1297,22 @@ extern "C" int cphb_icp_run(cphb_icp *icp, const float h_init[16], cphb_comm *co
     IcpArgs a;
     fill_args(icp, a);
     a.corr_index = corr_out ? icp->corr_index : nullptr;
+    if (corr_out && icp->n_full != icp->n_src)  // points owned by other ranks have no entry here
+        CPHB_CUDA(cudaMemsetAsync(icp->corr_index, 0xff, sizeof(int32_t) * icp->n_full, s));
     unsigned long long n_total = icp->n_src;
+    const bool lib_sharded = icp->prm.shard_world > 1;
+    if (lib_sharded) n_total = icp->n_full;
     void *nccl_comm = nullptr;
-    if (comm && comm->world > 1) {
-        // global source size: one tiny exchange before the loop
+    if (comm && comm->world > 1 && lib_sharded) {
+        if (comm->kind == CPHB_COMM_NCCL) {
+            nccl_comm = comm->nccl;
+            a.defer_finalize = 1;
+        } else {
+            a.use_p2p = 1;
+            a.p2p = comm->view;
+        }
+    } else if (comm && comm->world > 1) {
+        // caller-sharded source: global source size by one tiny exchange before the loop
         double *tmp = icp->partials;  // scratch
         double hn = (double)icp->n_src;
         CPHB_CUDA(cudaMemcpyAsync(tmp, &hn, 8, cudaMemcpyHostToDevice, s));
@@ -1236,6 +1343,10 @@ extern "C" int cphb_icp_run(cphb_icp *icp, const float h_init[16], cphb_comm *co
             if (rc) return rc;
             launch_finalize_kind(icp, a, s);
         }
+        if (!(icp->prm.flags & CPHB_ICP_NO_RETILE) && it < a.max_iter && (it == 1 || it == 4 || it == 10) && icp->n_src >= 4096) {
+            rc = retile(icp, a, s);
+            if (rc) return rc;
+        }
     }
     CPHB_CUDA(cudaEventRecord(icp->ev1, s));
     const int loop_launches = (int)(g_cphb_launches - launches0);
@@ -1244,12 +1355,16 @@ extern "C" int cphb_icp_run(cphb_icp *icp, const float h_init[16], cphb_comm *co
         rc = compact_correspondences(icp, corr_out, s);
         if (rc) return rc;
     }
-    CPHB_CUDA(cudaMemcpyAsync(h, icp->st, sizeof(IcpState), cudaMemcpyDeviceToHost, s));
+    unsigned h_local = 0;
+    if (corr_out) CPHB_CUDA(cudaMemcpyAsync(&h->pad_local, icp->cmp_total, 4, cudaMemcpyDeviceToHost, s));
+    CPHB_CUDA(cudaMemcpyAsync(h, icp->st, offsetof(IcpState, pad_local), cudaMemcpyDeviceToHost, s));
     CPHB_CUDA(cudaStreamSynchronize(s));
+    h_local = h->pad_local;
     memcpy(h_result->transformation, h->T, 64);
     h_result->fitness = h->fitness;
     h_result->inlier_rmse = h->rmse;
     h_result->n_correspondences = h->n_corr;
+    h_result->n_local_correspondences = corr_out ? (long long)h_local : 0;
     h_result->iterations = h->iterations;
     h_result->converged = h->converged;
     h_result->loop_ms = 0.f;
@@ -1276,10 +1391,11 @@ extern "C" int cphb_icp_step(cphb_icp *icp, const float h_T[16], double h_sums[3
     fill_args(icp, a);
     a.step_mode = 1;
     a.corr_index = icp->corr_index;
+    CPHB_CUDA(cudaMemsetAsync(icp->corr_index, 0xff, sizeof(int32_t) * icp->n_full, s));
     launch_iteration_kind(icp, a, s);
     CPHB_CHECK_LAUNCH();
     if (corr_index)
-        CPHB_CUDA(cudaMemcpyAsync(corr_index, icp->corr_index, sizeof(int32_t) * icp->n_src, cudaMemcpyDeviceToDevice, s));
+        CPHB_CUDA(cudaMemcpyAsync(corr_index, icp->corr_index, sizeof(int32_t) * icp->n_full, cudaMemcpyDeviceToDevice, s));
     CPHB_CUDA(cudaMemcpyAsync(h, icp->st, sizeof(IcpState), cudaMemcpyDeviceToHost, s));
     CPHB_CUDA(cudaStreamSynchronize(s));
     memcpy(h_sums, h->total, sizeof(double) * 32);

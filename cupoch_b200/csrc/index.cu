@@ -171,15 +171,16 @@ __global__ void __launch_bounds__(256) hilbert_key_kernel(const float *__restric
     vals[i] = (uint32_t)i;
 }
 
-// pts[pos] = (xyz[perm[pos]], perm[pos]); tail padding = (FLT_MAX x3, -1)
+// pts[pos] = (xyz[perm[pos]], perm[pos]); tail padding = (FLT_MAX x3, -1); inv[perm[pos]] = pos
 __global__ void __launch_bounds__(256) gather_points_kernel(const float *__restrict__ xyz,
                                                             const uint32_t *__restrict__ perm, size_t n,
-                                                            size_t n_pad, float4 *pts) {
+                                                            size_t n_pad, float4 *pts, uint32_t *inv) {
     size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
     if (i >= n_pad) return;
     float4 p;
     if (i < n) {
         uint32_t j = perm[i];
+        inv[j] = (uint32_t)i;
         p.x = xyz[3 * (size_t)j];
         p.y = xyz[3 * (size_t)j + 1];
         p.z = xyz[3 * (size_t)j + 2];
@@ -318,6 +319,8 @@ extern "C" int cphb_index_create(const float *xyz, size_t n, void *stream, cphb_
     off += 256;
     size_t off_perm = off;
     off = cphb_align(off + sizeof(uint32_t) * (n ? n : 1), 256);
+    size_t off_inv = off;
+    off = cphb_align(off + sizeof(uint32_t) * (n ? n : 1), 256);
     ix->arena_bytes = off;
     int rc = cphb_alloc_async(&ix->arena, off, s);
     if (rc) {
@@ -330,6 +333,7 @@ extern "C" int cphb_index_create(const float *xyz, size_t n, void *stream, cphb_
     for (int l = 0; l < CPHB_LEVELS; ++l) boxes[l] = (Box *)(base + off_box[l]);
     ix->bounds = (float *)(base + off_bounds);
     uint32_t *perm = (uint32_t *)(base + off_perm);
+    uint32_t *inv = (uint32_t *)(base + off_inv);
 
     if (n) {
         rc = cphb_hilbert_order(xyz, n, perm, ix->bounds, 0, s);
@@ -341,7 +345,7 @@ extern "C" int cphb_index_create(const float *xyz, size_t n, void *stream, cphb_
     } else {
         CPHB_LAUNCH(bounds_init_kernel, 1, 32, 0, s, (unsigned *)ix->bounds);
     }
-    CPHB_LAUNCH(gather_points_kernel, (unsigned)((n_pad + 255) / 256), 256, 0, s, xyz, perm, n, n_pad, pts);
+    CPHB_LAUNCH(gather_points_kernel, (unsigned)((n_pad + 255) / 256), 256, 0, s, xyz, perm, n, n_pad, pts, inv);
     CPHB_LAUNCH(leaf_box_kernel, (unsigned)((pad[0] * 32 + 255) / 256), 256, 0, s, pts, n, pad[0], boxes[0]);
     for (int l = 1; l < CPHB_LEVELS; ++l)
         CPHB_LAUNCH(upper_box_kernel, (unsigned)((pad[l] * 32 + 255) / 256), 256, 0, s, boxes[l - 1], count[l - 1],
@@ -349,6 +353,7 @@ extern "C" int cphb_index_create(const float *xyz, size_t n, void *stream, cphb_
     CPHB_CHECK_LAUNCH();
 
     ix->v.pts = pts;
+    ix->v.inv = inv;
     for (int l = 0; l < CPHB_LEVELS; ++l) ix->v.boxes[l] = boxes[l];
     ix->v.n = n;
     ix->v.n_leaves = (unsigned)count[0];

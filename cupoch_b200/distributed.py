@@ -62,10 +62,13 @@ def destroy_comm(comm):
 
 
 def gather_correspondences(dist, local_corr, lo, world):
-    """all-gather-v of the per-rank (i, j) lists into the single-GPU ordering (host side, once per call)."""
+    """all-gather-v of the per-rank (i, j) lists into the single-GPU list, ascending in i (host side, once
+    per call).  `lo` is added to the local source indices (0 when the library did the sharding: indices
+    are global already)."""
     import numpy as np
     mine = np.asarray(local_corr, np.int32).reshape(-1, 2).copy()
     mine[:, 0] += lo
     out = [None] * world
     dist.all_gather_object(out, mine)
-    return np.concatenate(out, 0) if out else mine
+    allc = np.concatenate(out, 0) if out else mine
+    return allc[np.argsort(allc[:, 0], kind="stable")]

@@ -113,8 +113,13 @@ class RegistrationResult:  # registration.h:51-67
                 % (self.fitness, self.inlier_rmse, self._n_corr if self._corr_dev is not None else len(self._corr_host)))
 
 
-def _params(estimation, max_distance, criteria):
+ICP_NO_RETILE = 2   # CPHB_ICP_NO_RETILE
+DEFAULT_FLAGS = 0   # OR of ICP_* flags applied to every registration (ablation / debugging)
+
+
+def _params(estimation, max_distance, criteria, shard=None):
     p = _lib.IcpParams()
+    p.shard_rank, p.shard_world = (int(shard[0]), int(shard[1])) if shard else (0, 0)
     p.estimation = estimation.get_transformation_estimation_type()
     p.max_correspondence_distance = float(max_distance)
     p.relative_fitness = criteria.relative_fitness
@@ -122,7 +127,7 @@ def _params(estimation, max_distance, criteria):
     p.max_iteration = criteria.max_iteration
     p.det_thresh = getattr(estimation, "det_thresh", -1.0)
     p.lambda_geometric = getattr(estimation, "lambda_geometric", 0.968)
-    p.flags = 0
+    p.flags = DEFAULT_FLAGS
     return p
 
 
@@ -135,13 +140,16 @@ def _result(res, corr, want_corr):
     out.loop_ms = float(res.loop_ms)
     out.loop_launches = int(res.loop_launches)
     if want_corr:
-        out._corr_dev, out._n_corr = corr, int(res.n_correspondences)
+        out._corr_dev, out._n_corr = corr, int(res.n_local_correspondences)
     return out
 
 
 def registration_icp(source, target, max_correspondence_distance, init=None,
-                     estimation_method=None, criteria=None, comm=None, return_correspondences=True):
-    """registration::RegistrationICP (registration.cu:121-173)."""
+                     estimation_method=None, criteria=None, comm=None, return_correspondences=True, shard=None):
+    """registration::RegistrationICP (registration.cu:121-173).
+    Multi-GPU: pass `comm` (cupoch_b200.distributed.make_comm) and `shard=(rank, world)` with the FULL source on
+    every rank; the library keeps this rank's Hilbert-contiguous block.  correspondence_set then holds this
+    rank's pairs with global source indices."""
     estimation_method = estimation_method or TransformationEstimationPointToPoint()
     criteria = criteria or ICPConvergenceCriteria()
     init = np.eye(4, dtype=np.float32) if init is None else init
@@ -151,7 +159,7 @@ def registration_icp(source, target, max_correspondence_distance, init=None,
         raise NotImplementedError("user-defined TransformationEstimation: use the generic loop in the C++ facade")
     _lib.require_gpu()
     sc, tc = source._cloud(), target._cloud()
-    p = _params(estimation_method, max_correspondence_distance, criteria)
+    p = _params(estimation_method, max_correspondence_distance, criteria, shard)
     res = _lib.IcpResult()
     corr = _DevicePool.take((max(len(source), 1), 2), np.int32) if return_correspondences else None
     _lib.check(_lib.lib().cphb_registration_icp(C.byref(sc), C.byref(tc), as_f16(init), C.byref(p), comm,
@@ -188,11 +196,11 @@ def _with_covariances(pcd, epsilon):
 
 
 def registration_generalized_icp(source, target, max_correspondence_distance, init=None, estimation=None,
-                                 criteria=None, comm=None, return_correspondences=True):
+                                 criteria=None, comm=None, return_correspondences=True, shard=None):
     """registration::RegistrationGeneralizedICP (generalized_icp.cu:185-198)."""
     estimation = estimation or TransformationEstimationForGeneralizedICP()
     return registration_icp(_with_covariances(source, estimation.epsilon), _with_covariances(target, estimation.epsilon),
-                            max_correspondence_distance, init, estimation, criteria, comm, return_correspondences)
+                            max_correspondence_distance, init, estimation, criteria, comm, return_correspondences, shard)
 
 
 def initialize_pointcloud_for_colored_icp(target, radius, max_nn=30):
@@ -212,12 +220,12 @@ def initialize_pointcloud_for_colored_icp(target, radius, max_nn=30):
 
 
 def registration_colored_icp(source, target, max_correspondence_distance, init=None, criteria=None,
-                             lambda_geometric=0.968, det_thresh=1e-6, comm=None, return_correspondences=True):
+                             lambda_geometric=0.968, det_thresh=1e-6, comm=None, return_correspondences=True, shard=None):
     """registration::RegistrationColoredICP (colored_icp.cu:329-342)."""
     target_c = initialize_pointcloud_for_colored_icp(target, max_correspondence_distance * 2.0, 30)
     return registration_icp(source, target_c, max_correspondence_distance, init,
                             TransformationEstimationForColoredICP(lambda_geometric, det_thresh), criteria, comm,
-                            return_correspondences)
+                            return_correspondences, shard)
 
 
 class IcpContext:
@@ -243,7 +251,8 @@ class IcpContext:
                                            self._corr.ptr if return_correspondences else None, None))
         out = _result(res, None, False)
         if return_correspondences:
-            out.correspondence_set = self._corr.cpu(int(res.n_correspondences)) if res.n_correspondences else np.zeros((0, 2), np.int32)
+            nl = int(res.n_local_correspondences)
+            out.correspondence_set = self._corr.cpu(nl) if nl else np.zeros((0, 2), np.int32)
         return out
 
     def step(self, T):

@@ -456,7 +456,7 @@ public:
 
 inline RegistrationResult to_result(const cphb_icp_result &r, CorrespondenceSet &&corr) {
     RegistrationResult out(utility::from_row_major(r.transformation));
-    corr.resize((size_t)r.n_correspondences);
+    corr.resize((size_t)r.n_local_correspondences);
     out.correspondence_set_ = std::move(corr);
     out.fitness_ = r.fitness;
     out.inlier_rmse_ = r.inlier_rmse;

@@ -153,17 +153,22 @@ typedef struct cphb_icp_params {
     float det_thresh;             /* PointToPlane / Symmetric / Colored: 1e-6; ignored for GICP */
     float lambda_geometric;       /* Colored ICP, default 0.968 */
     int flags;                    /* CPHB_ICP_* */
+    /* Multi-GPU: with shard_world > 1 every rank passes the FULL source; the library orders it along the
+     * Hilbert curve and keeps the shard_rank-th contiguous block of that order (a spatially compact
+     * shard at full density).  correspondence indices stay global.  0/0 or 1 = no library-side sharding
+     * (a caller may still pass its own shard together with a communicator). */
+    int shard_rank;
+    int shard_world;
 } cphb_icp_params;
 
-#define CPHB_ICP_CUMULATIVE_TRANSFORM 1 /* "fast" mode: apply the cumulative T to the pristine source
-                                           instead of transforming the working copy in place each
-                                           iteration (registration.cu:160).  Not bit-compatible. */
+#define CPHB_ICP_NO_RETILE 2 /* keep the source in its initial Hilbert order for the whole run (debug/ablation) */
 
 typedef struct cphb_icp_result {
     float transformation[16];     /* row-major */
     float fitness;
     float inlier_rmse;
-    int64_t n_correspondences;
+    int64_t n_correspondences;    /* global count (all ranks) */
+    int64_t n_local_correspondences; /* pairs written to corr_out by this rank (== global on one GPU) */
     int iterations;               /* updates applied */
     int converged;
     float loop_ms;                /* device time of the launch loop (CUDA events on `stream`) */

@@ -199,3 +199,20 @@ def test_icp_1m_properties():
     i, j = a.correspondence_set[:, 0], a.correspondence_set[:, 1]
     assert (np.diff(i) > 0).all() and j.min() >= 0 and j.max() < n          # ascending in i, valid j
     ctx.close()
+
+
+def test_retiling_does_not_change_results(orc):
+    """Re-ordering the working copy by matched target position is a pure permutation: same pose bits,
+    same correspondence set, with and without it (and both equal the oracle)."""
+    src, sn, tgt, tn = small_pair(n=30000)
+    crit = R.ICPConvergenceCriteria(0, 0, 14)
+    a = R.registration_icp(cloud(src), cloud(tgt, tn), 0.03, np.eye(4), R.TransformationEstimationPointToPlane(), crit)
+    R.DEFAULT_FLAGS = R.ICP_NO_RETILE
+    try:
+        b = R.registration_icp(cloud(src), cloud(tgt, tn), 0.03, np.eye(4), R.TransformationEstimationPointToPlane(), crit)
+    finally:
+        R.DEFAULT_FLAGS = 0
+    np.testing.assert_array_equal(a.transformation, b.transformation)
+    np.testing.assert_array_equal(a.correspondence_set, b.correspondence_set)
+    ref = orc.registration_icp(orc.P2PLANE, src, tgt, 0.03, tgt_nrm=tn, relative_fitness=0, relative_rmse=0, max_iteration=14)
+    _compare(a, ref)

@@ -32,13 +32,19 @@ def main():
     est, crit = R.TransformationEstimationPointToPlane(), R.ICPConvergenceCriteria(0, 0, 20)
     t_pc = cph.geometry.PointCloud(tgt)
     t_pc.normals = tn
-    s_pc = cph.geometry.PointCloud(np.ascontiguousarray(src[lo:hi]))
+    s_pc = cph.geometry.PointCloud(src)          # full source on every rank; the library shards it spatially
+    s_own = cph.geometry.PointCloud(np.ascontiguousarray(src[lo:hi]))   # caller-sharded variant
     out = {"world": world, "points": n}
-    for kind in ("p2p", "nccl"):
-        comm = make_comm(dist, rank, world, device="cuda", kind=kind)
-        res = R.registration_icp(s_pc, t_pc, 0.02, np.eye(4), est, crit, comm=comm)
-        res2 = R.registration_icp(s_pc, t_pc, 0.02, np.eye(4), est, crit, comm=comm)   # back-to-back runs on one comm
-        corr = gather_correspondences(dist, res.correspondence_set, lo, world)
+    for kind in ("p2p", "nccl", "p2p_caller_sharded"):
+        comm = make_comm(dist, rank, world, device="cuda", kind=kind.split("_")[0])
+        if kind.endswith("caller_sharded"):
+            res = R.registration_icp(s_own, t_pc, 0.02, np.eye(4), est, crit, comm=comm)
+            res2 = R.registration_icp(s_own, t_pc, 0.02, np.eye(4), est, crit, comm=comm)
+            corr = gather_correspondences(dist, res.correspondence_set, lo, world)
+        else:
+            res = R.registration_icp(s_pc, t_pc, 0.02, np.eye(4), est, crit, comm=comm, shard=(rank, world))
+            res2 = R.registration_icp(s_pc, t_pc, 0.02, np.eye(4), est, crit, comm=comm, shard=(rank, world))  # back to back
+            corr = gather_correspondences(dist, res.correspondence_set, 0, world)
         Ts = [None] * world
         dist.all_gather_object(Ts, res.transformation.tolist())
         out[kind] = {"T": res.transformation.tolist(), "fitness": res.fitness, "rmse": res.inlier_rmse,
@@ -51,7 +57,7 @@ def main():
             out[kind]["_corr"] = corr
     if rank == 0:
         full = R.registration_icp(cph.geometry.PointCloud(src), t_pc, 0.02, np.eye(4), est, crit)
-        for kind in ("p2p", "nccl"):
+        for kind in ("p2p", "nccl", "p2p_caller_sharded"):
             c = out[kind].pop("_corr")
             out[kind]["pose_diff_vs_1gpu"] = float(np.linalg.norm(np.array(out[kind]["T"], np.float64) - full.transformation))
             out[kind]["corr_equal_1gpu"] = bool(np.array_equal(c, full.correspondence_set))
