@@ -192,6 +192,99 @@ __global__ void __launch_bounds__(256) gather_points_kernel(const float *__restr
     pts[i] = p;
 }
 
+// ---------------------------------------------------------------------------
+// kd refinement of the Hilbert order.  Runs of 32 Hilbert-consecutive points are compact but irregular,
+// so their AABBs overlap heavily (a query typically lies inside 2-3 leaf boxes and every one of them has
+// to be scanned).  Each group of 1024 consecutive points (= one level-1 node) is therefore re-partitioned
+// in shared memory by 5 exact median splits along the widest axis of each segment: the 32 leaves of a
+// group become kd cells with pairwise disjoint boxes.  Implicit layout, leaf size and upper levels are
+// unchanged; only the order of points inside a group changes.
+// One block per group; segmented bitonic sorts (segment = 1024 >> level) of (key, point) pairs.
+// ---------------------------------------------------------------------------
+#define KD_GROUP 1024
+#define KD_THREADS 256
+__global__ void __launch_bounds__(KD_THREADS) kd_refine_kernel(float4 *pts, size_t n_pad) {
+    __shared__ float4 s_p[KD_GROUP];
+    __shared__ unsigned s_k[KD_GROUP];
+    __shared__ unsigned s_lo[32][3], s_hi[32][3];
+    __shared__ int s_axis[32];
+    const size_t base = (size_t)blockIdx.x * KD_GROUP;
+    const int tid = threadIdx.x;
+    for (int e = tid; e < KD_GROUP; e += KD_THREADS) {
+        size_t i = base + e;
+        s_p[e] = (i < n_pad) ? pts[i] : make_float4(FLT_MAX, FLT_MAX, FLT_MAX, __uint_as_float(0xffffffffu));
+    }
+    __syncthreads();
+    for (int level = 0; level < 5; ++level) {
+        const int S = KD_GROUP >> level;  // segment size (>= 64), n_seg = 1 << level
+        const int n_seg = 1 << level;
+        if (tid < n_seg) {
+#pragma unroll
+            for (int a = 0; a < 3; ++a) { s_lo[tid][a] = 0xffffffffu; s_hi[tid][a] = 0u; }
+        }
+        __syncthreads();
+        for (int e = tid; e < KD_GROUP; e += KD_THREADS) {
+            const float4 p = s_p[e];
+            if (__float_as_uint(p.w) != 0xffffffffu) {  // padding does not stretch the boxes
+                const int sg = e / S;
+                atomicMin(&s_lo[sg][0], f2ord(p.x)); atomicMax(&s_hi[sg][0], f2ord(p.x));
+                atomicMin(&s_lo[sg][1], f2ord(p.y)); atomicMax(&s_hi[sg][1], f2ord(p.y));
+                atomicMin(&s_lo[sg][2], f2ord(p.z)); atomicMax(&s_hi[sg][2], f2ord(p.z));
+            }
+        }
+        __syncthreads();
+        if (tid < n_seg) {
+            float ex[3];
+#pragma unroll
+            for (int a = 0; a < 3; ++a)
+                ex[a] = (s_lo[tid][a] <= s_hi[tid][a]) ? ord2f(s_hi[tid][a]) - ord2f(s_lo[tid][a]) : 0.f;
+            int ax = 0;
+            if (ex[1] > ex[ax]) ax = 1;
+            if (ex[2] > ex[ax]) ax = 2;
+            s_axis[tid] = ax;
+        }
+        __syncthreads();
+        for (int e = tid; e < KD_GROUP; e += KD_THREADS) {
+            const float4 p = s_p[e];
+            const int ax = s_axis[e / S];
+            const float c = (ax == 0) ? p.x : (ax == 1) ? p.y : p.z;
+            // padding sorts last; ties broken by original index so the order is deterministic
+            s_k[e] = (__float_as_uint(p.w) == 0xffffffffu) ? 0xffffffffu : f2ord(c);
+        }
+        __syncthreads();
+        // sort every aligned segment of S elements ascending
+        for (int k = 2; k <= S; k <<= 1) {
+            for (int j = k >> 1; j > 0; j >>= 1) {
+                for (int t = tid; t < KD_GROUP / 2; t += KD_THREADS) {
+                    const int i = 2 * t - (t & (j - 1));  // lower index of the pair (i, i + j)
+                    const int l = i + j;
+                    const bool up = (k == S) ? true : ((i & k) == 0);
+                    const unsigned ki = s_k[i], kl = s_k[l];
+                    const unsigned wi = __float_as_uint(s_p[i].w), wl = __float_as_uint(s_p[l].w);
+                    const bool gt = (ki > kl) || (ki == kl && wi > wl);
+                    if (gt == up) {
+                        s_k[i] = kl; s_k[l] = ki;
+                        const float4 tmp = s_p[i]; s_p[i] = s_p[l]; s_p[l] = tmp;
+                    }
+                }
+                __syncthreads();
+            }
+        }
+    }
+    for (int e = tid; e < KD_GROUP; e += KD_THREADS) {
+        size_t i = base + e;
+        if (i < n_pad) pts[i] = s_p[e];
+    }
+}
+
+// inv[original index] = final position
+__global__ void __launch_bounds__(256) inverse_perm_kernel(const float4 *__restrict__ pts, size_t n_pad, uint32_t *inv) {
+    size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (i >= n_pad) return;
+    const unsigned j = __float_as_uint(pts[i].w);
+    if (j != 0xffffffffu) inv[j] = (uint32_t)i;
+}
+
 // one warp per leaf (CPHB_LEAF == 32): AABB of its real points
 __global__ void __launch_bounds__(256) leaf_box_kernel(const float4 *__restrict__ pts, size_t n,
                                                        size_t n_boxes_pad, Box *boxes) {
@@ -199,7 +292,7 @@ __global__ void __launch_bounds__(256) leaf_box_kernel(const float4 *__restrict_
     if (leaf >= n_boxes_pad) return;
     size_t i = leaf * CPHB_LEAF + lane_id();
     unsigned lo[3] = {0xffffffffu, 0xffffffffu, 0xffffffffu}, hi[3] = {0u, 0u, 0u};
-    if (i < n) {
+    if (i < n) {  // real points are a prefix of pts (padding sorts last at every refinement level)
         float4 p = pts[i];
         lo[0] = hi[0] = f2ord(p.x);
         lo[1] = hi[1] = f2ord(p.y);
@@ -346,6 +439,10 @@ extern "C" int cphb_index_create(const float *xyz, size_t n, void *stream, cphb_
         CPHB_LAUNCH(bounds_init_kernel, 1, 32, 0, s, (unsigned *)ix->bounds);
     }
     CPHB_LAUNCH(gather_points_kernel, (unsigned)((n_pad + 255) / 256), 256, 0, s, xyz, perm, n, n_pad, pts, inv);
+    if (n > KD_GROUP / 2) {  // tiny clouds: nothing to gain
+        CPHB_LAUNCH(kd_refine_kernel, (unsigned)((n_pad + KD_GROUP - 1) / KD_GROUP), KD_THREADS, 0, s, pts, n_pad);
+        CPHB_LAUNCH(inverse_perm_kernel, (unsigned)((n_pad + 255) / 256), 256, 0, s, pts, n_pad, inv);
+    }
     CPHB_LAUNCH(leaf_box_kernel, (unsigned)((pad[0] * 32 + 255) / 256), 256, 0, s, pts, n, pad[0], boxes[0]);
     for (int l = 1; l < CPHB_LEVELS; ++l)
         CPHB_LAUNCH(upper_box_kernel, (unsigned)((pad[l] * 32 + 255) / 256), 256, 0, s, boxes[l - 1], count[l - 1],

@@ -212,7 +212,9 @@ def test_retiling_does_not_change_results(orc):
         b = R.registration_icp(cloud(src), cloud(tgt, tn), 0.03, np.eye(4), R.TransformationEstimationPointToPlane(), crit)
     finally:
         R.DEFAULT_FLAGS = 0
-    np.testing.assert_array_equal(a.transformation, b.transformation)
+    # the float64 sums are added in a different order (1e-16 relative), so the float32 systems are the same
+    # except on a rounding boundary: allow one ulp-level wobble of the pose, demand identical correspondences
+    assert np.linalg.norm(a.transformation.astype(np.float64) - b.transformation) <= 1e-6
     np.testing.assert_array_equal(a.correspondence_set, b.correspondence_set)
     ref = orc.registration_icp(orc.P2PLANE, src, tgt, 0.03, tgt_nrm=tn, relative_fitness=0, relative_rmse=0, max_iteration=14)
     _compare(a, ref)
