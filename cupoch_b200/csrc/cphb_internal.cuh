@@ -421,23 +421,34 @@ struct Visit {
                 }
             }
         } else {
+            // leaf level.  A candidate is fetched only if stage 2 says some lane can still improve in it
+            // (bounds only tighten, so a leaf rejected now stays rejected); the copy of the next accepted
+            // leaf is in flight while the current one is scanned.
             int b = 0;
-            int next = pick_child(active, dkey);
+            int next = -1;
+            while (active) {
+                const int c = pick_child(active, dkey);
+                if (c < 0) { active = 0; break; }
+                active &= ~(1u << c);
+                if (lanes_needing(w, gbox + c)) { next = c; break; }
+            }
             if (next >= 0) issue_leaf(ix, group * 32 + next, w.tile + b * CPHB_LEAF, w.bar + b);
             while (next >= 0) {
                 const int cur = next;
-                active &= ~(1u << cur);
-                next = pick_child(active, dkey);
+                next = -1;
+                while (active) {
+                    const int c = pick_child(active, dkey);
+                    if (c < 0) { active = 0; break; }
+                    active &= ~(1u << c);
+                    if (lanes_needing(w, gbox + c)) { next = c; break; }
+                }
                 if (next >= 0) issue_leaf(ix, group * 32 + next, w.tile + (b ^ 1) * CPHB_LEAF, w.bar + (b ^ 1));
-                const unsigned need = lanes_needing(w, gbox + cur);
-                wait_leaf(w, b);  // always consume the copy so the barrier phases stay in step
+                wait_leaf(w, b);
+                const unsigned need = lanes_needing(w, gbox + cur);  // bounds may have tightened since the pick
                 if (need) {
                     scan_tile(w.tile + b * CPHB_LEAF, w, need);
                     warp_update_bound(w);
-                    const unsigned still = __ballot_sync(CPHB_FULL, dcull <= w.bound);
-                    // the prefetched `next` stays queued even if it just got culled: it is consumed
-                    // (and skipped by stage 2) on the next trip
-                    active &= still;
+                    active &= __ballot_sync(CPHB_FULL, dcull <= w.bound);
                 }
                 __syncwarp();  // all lanes done with tile b before it is re-armed
                 b ^= 1;
