@@ -198,10 +198,16 @@ def run_native(args, rank, world):
     h_src[:], h_tgt[:], h_tn[:] = src_local, tgt, tn
     d2h = [0]
 
+    dbg = os.environ.get("BENCH_DEBUG")
+
     def step_e2e():
+        t0 = time.perf_counter()
         s2 = cph.geometry.PointCloud(h_src)         # H2D (pinned)
         t2 = cph.geometry.PointCloud(h_tgt)
         t2.normals = h_tn
+        if dbg:
+            L.cphb_stream_synchronize(None)
+            sys.stderr.write("e2e upload %.3f ms\n" % (1e3 * (time.perf_counter() - t0)))
         r = R.registration_icp(s2, t2, MAX_DIST, init, est, crit, comm=comm, shard=shard)
         # D2H: the RegistrationResult scalars (T, fitness, rmse, counts); correspondence_set_ stays on the
         # device exactly as in the reference's RegistrationResult (registration.h:51-67)

@@ -408,6 +408,14 @@ struct Visit {
             // order key: distance of the box to the warp centre (+inf for empty boxes stays +inf)
             const float c3[3] = {w.wc[0], w.wc[1], w.wc[2]};
             dkey = __float_as_uint(box_dist2(lo, hi, c3, c3));
+            // boxes containing the centre all have key 0: break those ties by the distance of the box
+            // centre so the box "around" the warp comes first
+            if (dkey == 0u) {
+                const float mx = 0.5f * lo.x + 0.5f * hi.x - c3[0], my = 0.5f * lo.y + 0.5f * hi.y - c3[1],
+                            mz = 0.5f * lo.z + 0.5f * hi.z - c3[2];
+                // scaled far below any non-zero box distance of interest: only an ordering hint
+                dkey = __float_as_uint(1e-30f * __fmaf_rn(mz, mz, __fmaf_rn(my, my, mx * mx)));
+            }
         }
         unsigned active = __ballot_sync(CPHB_FULL, dcull <= w.bound);
         if constexpr (LV > 0) {

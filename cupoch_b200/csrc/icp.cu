@@ -635,9 +635,17 @@ __global__ void __launch_bounds__(ICP_REDUCE_BLOCK) icp_reduce_kernel(const __gr
     __syncthreads();
     if (!s_last) return;
     __threadfence();
+    {   // all 8 warps share the grid sum (fixed order: row groups of 8, then the 8 group sums)
+        double t = 0.0;
+#pragma unroll 4
+        for (unsigned b = g; b < gridDim.x; b += ICP_REDUCE_BLOCK / 32) t += __ldcg(&a.partials[(size_t)b * 32 + c]);
+        s_acc[g][c] = t;
+    }
+    __syncthreads();
     if (threadIdx.x < 32) {
         double t = 0.0;
-        for (unsigned b = 0; b < gridDim.x; ++b) t += __ldcg(&a.partials[(size_t)b * 32 + threadIdx.x]);
+#pragma unroll
+        for (int k = 0; k < ICP_REDUCE_BLOCK / 32; ++k) t += s_acc[k][threadIdx.x];
         if (a.use_p2p) t = p2p_exchange_sum(a.p2p, t);  // the collective, fused: NVLink stores + flags
         if (a.defer_finalize) st->local[threadIdx.x] = t;
         else st->total[threadIdx.x] = t;
