@@ -36,6 +36,7 @@ if ROOT not in sys.path:
 ALG_BYTES_PER_POINT = 36  # src xyz 12 + matched target xyz 12 + matched normal 12
 MAX_DIST = 0.02
 ITERS = 30
+WORKLOAD = "config2: point-to-plane ICP 1M->1M + normals, 30 iters, r=0.02 (SURVEY.md 8d)"
 
 
 def peaks():
@@ -103,8 +104,8 @@ def run_reference(args, rank):
         "impl": "reference", "metric": "icp_iterations_per_sec", "value": v, "unit": "iter/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "config2: point-to-plane ICP 1M->1M, 30 iters, r=0.02", "points": args.points,
-                   "iterations": ITERS},
+        "config": {"workload": WORKLOAD, "points": args.points, "iterations": ITERS,
+                   "step": "one RegistrationICP call incl. index (kd-tree) build"},
         "cpu_baseline": {"value": v, "unit": "iter/s", "cores": orc.num_threads(), "kind": "port",
                          "sample": "full workload: %d registrations x %d iterations, kd-tree build included" % (args.steps, ITERS)},
         "e2e": {"value": v, "unit": "iter/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -247,7 +248,7 @@ def run_native(args, rank, world):
             "metric": "icp_iterations_per_sec", "value": value, "unit": "iter/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "config2: point-to-plane ICP 1M->1M + normals, 30 iters, r=0.02 (SURVEY.md 8d)",
+            "config": {"workload": WORKLOAD,
                        "points": n, "iterations": ITERS, "step": "one RegistrationICP call incl. index build",
                        "cache": "256 MiB memset between timed steps (L2 flush); working set ~60 MB",
                        "parallelism": "source sharded x%d (Hilbert-contiguous blocks), target replicated, 1 exchange(32 f64)/iter via %s"
@@ -257,8 +258,9 @@ def run_native(args, rank, world):
             "gpu_launches": int(launches),
             "loop": {"iters_per_sec": ITERS * 1e3 / loop_ms, "ms_per_launch": kern_ms, "launches": loop_launches,
                      "correspondences_per_sec": float(res.fitness) * n * (ITERS + 1) * 1e3 / loop_ms},
-            "knn": {"mqueries_per_sec": n / world / (knn_ms / knn_steps) * 1e-3, "k": 1, "radius": MAX_DIST,
-                    "ms": knn_ms / knn_steps, "note": "SearchRadius of the source shard incl. query ordering"},
+            "knn": {"mqueries_per_sec": n / (knn_ms / knn_steps) * 1e-3, "k": 1, "radius": MAX_DIST,
+                    "ms": knn_ms / knn_steps,
+                    "note": "SearchRadius of all %d source points (sharded by index over the ranks, no collective) incl. query ordering; aggregate rate" % n},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": None, "peak_source": peak_src, "kernel": "icp_iteration_kernel<PointToPlane>",
                          "algorithmic_bytes_per_launch": ALG_BYTES_PER_POINT * units},

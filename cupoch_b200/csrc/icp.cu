@@ -435,6 +435,25 @@ __device__ __forceinline__ void build_rows(const TargetAttrs &a, const float s_x
         }
 }
 
+// Deliberate deviation from the reference (parity hazard 8): a row with a non-finite entry is
+// dropped instead of poisoning the whole sum.  The reference's FastEigen3x3 computes x/|x| (eigenvalue.inl:28)
+// which is 0/0 when an off-diagonal projection vanishes exactly; with millions of GICP rows per iteration that
+// happens, and the reference then returns an all-NaN transformation.
+template <int NROWS>
+__device__ __forceinline__ void drop_nonfinite_rows(float (&J)[NROWS][6], float (&r)[NROWS]) {
+#pragma unroll
+    for (int q = 0; q < NROWS; ++q) {
+        float s = r[q];
+#pragma unroll
+        for (int c = 0; c < 6; ++c) s += J[q][c];  // NaN/inf propagate into s
+        if (!(fabsf(s) <= FLT_MAX)) {  // NaN or inf
+            r[q] = 0.f;
+#pragma unroll
+            for (int c = 0; c < 6; ++c) J[q][c] = 0.f;
+        }
+    }
+}
+
 // ===========================================================================
 // the fused per-iteration kernel
 //
@@ -575,6 +594,7 @@ __global__ void __launch_bounds__(ICP_SEARCH_WARPS * 32) icp_iteration_kernel(co
                               a.src_nrm != nullptr, a.src_col != nullptr, a.src_cov != nullptr};
             const float4 cs4 = (KIND == CPHB_EST_COLORED_ICP && a.src_col) ? a.src_col[i] : make_float4(0.f, 0.f, 0.f, 0.f);
             build_rows<KIND, NROWS>(ta, s.x, s.y, s.z, sn, cs4, Cs, j, J, r);
+            drop_nonfinite_rows<NROWS>(J, r);
         }
         // stage + accumulate: lane L adds column pair (ca, cb) over the 32 staged rows, in row order
         double acc = 0.0;
@@ -712,6 +732,7 @@ __global__ void __launch_bounds__(ICP_BLOCK) estimate_kernel(const __grid_consta
 #pragma unroll
                 for (int q = 0; q < 3; ++q) Cs[3 * p + q] = a.src_cov[9 * i + (a.src_cov_col_major ? 3 * q + p : 3 * p + q)];
         build_rows<KIND, NROWS>(a.ta, vs[0], vs[1], vs[2], sn, cs4, Cs, j, J, r);
+        drop_nonfinite_rows<NROWS>(J, r);
         const float vt[3] = {a.ta.tgt_xyz[3 * (size_t)j], a.ta.tgt_xyz[3 * (size_t)j + 1], a.ta.tgt_xyz[3 * (size_t)j + 2]};
         if (KIND == CPHB_EST_POINT_TO_POINT) {
             term = dist2(vs[0], vs[1], vs[2], vt[0], vt[1], vt[2]);  // (lhs - rhs).squaredNorm()

@@ -28,6 +28,32 @@ class TransformationEstimation:  # transformation_estimation.h:49-77
     def get_transformation_estimation_type(self):
         return self._type
 
+    def _corr_dev(self, corres):
+        d = DeviceArray.wrap(np.ascontiguousarray(corres, np.int32).reshape(-1, 2), np.int32) if not isinstance(corres, DeviceArray) else corres
+        return d, (len(d) if d is not None else 0)
+
+    def compute_transformation(self, source, target, corres):
+        """TransformationEstimation::ComputeTransformation on an explicit correspondence set (registration.cpp:115-118)."""
+        _lib.require_gpu()
+        d, n = self._corr_dev(corres)
+        sc, tc = source._cloud(), target._cloud()
+        p = _params(self, 0.0, ICPConvergenceCriteria())
+        T = (C.c_float * 16)()
+        _lib.check(_lib.lib().cphb_compute_transformation(self._type, C.byref(sc), C.byref(tc), d.ptr if n else None, n,
+                                                          C.byref(p), T, None))
+        return np.array(T, np.float32).reshape(4, 4)
+
+    def compute_rmse(self, source, target, corres):
+        """TransformationEstimation::ComputeRMSE (registration.cpp:111-114)."""
+        _lib.require_gpu()
+        d, n = self._corr_dev(corres)
+        sc, tc = source._cloud(), target._cloud()
+        p = _params(self, 0.0, ICPConvergenceCriteria())
+        r = C.c_float(0)
+        _lib.check(_lib.lib().cphb_compute_rmse(self._type, C.byref(sc), C.byref(tc), d.ptr if n else None, n, C.byref(p),
+                                                C.byref(r), None))
+        return float(r.value)
+
 
 class TransformationEstimationPointToPoint(TransformationEstimation):
     _type = _lib.EST_POINT_TO_POINT
@@ -226,6 +252,19 @@ def registration_colored_icp(source, target, max_correspondence_distance, init=N
     return registration_icp(source, target_c, max_correspondence_distance, init,
                             TransformationEstimationForColoredICP(lambda_geometric, det_thresh), criteria, comm,
                             return_correspondences, shard)
+
+
+def kabsch(model, target, corres=None):
+    """registration::Kabsch(model, target[, corres]) (kabsch.h:30-49) on device vectors / arrays."""
+    _lib.require_gpu()
+    m, t = DeviceArray.wrap(model), DeviceArray.wrap(target)
+    T = (C.c_float * 16)()
+    if corres is None:
+        _lib.check(_lib.lib().cphb_kabsch(m.ptr, len(m), t.ptr, None, 0, T, None))
+    else:
+        d = DeviceArray.wrap(np.ascontiguousarray(corres, np.int32).reshape(-1, 2), np.int32)
+        _lib.check(_lib.lib().cphb_kabsch(m.ptr, len(m), t.ptr, d.ptr, len(d), T, None))
+    return np.array(T, np.float32).reshape(4, 4)
 
 
 class IcpContext:

@@ -642,6 +642,11 @@ void orc_color_gradient(const float *pts, const float *nrm, const float *col,
 /* estimator rows -> 27(+1) sums    eigen.inl:33-145                           */
 /* ======================================================================== */
 static inline void acc_row(double *S, const float J[6], float r) {
+    /* deliberate deviation shared with the product (parity hazard 8): rows with a non-finite entry
+     * are dropped (the reference would let the NaN poison the sum, eigenvalue.inl:28 signf(0) = 0/0) */
+    float chk = r;
+    for (int a = 0; a < 6; ++a) chk += J[a];
+    if (!isfinite(chk)) return;
     int p = 0;
     for (int a = 0; a < 6; ++a)
         for (int b = a; b < 6; ++b) S[p++] += (double)J[a] * (double)J[b];

@@ -218,3 +218,59 @@ def test_retiling_does_not_change_results(orc):
     np.testing.assert_array_equal(a.correspondence_set, b.correspondence_set)
     ref = orc.registration_icp(orc.P2PLANE, src, tgt, 0.03, tgt_nrm=tn, relative_fitness=0, relative_rmse=0, max_iteration=14)
     _compare(a, ref)
+
+
+def test_kabsch_golden(golden, orc):
+    """tests/registration/kabsch.cpp:35-55: a 30-degree z rotation is recovered (isApprox 1e-3)."""
+    g = golden["kabsch"]
+    p = np.array(g["points"], np.float32)
+    a = np.deg2rad(np.float32(g["angle_deg_z"]))
+    T = np.array([[np.cos(a), -np.sin(a), 0, 0], [np.sin(a), np.cos(a), 0, 0], [0, 0, 1, 0], [0, 0, 0, 1]], np.float32)
+    q = orc.transform_points(p, T)
+    Rk = R.kabsch(p, q)
+    assert np.linalg.norm(Rk - T) <= g["tolerance"] * min(np.linalg.norm(Rk), np.linalg.norm(T))
+    corr = np.stack([np.arange(len(p)), np.arange(len(p))], 1).astype(np.int32)
+    To, _ = orc.kabsch(p, q, corr)
+    np.testing.assert_array_equal(Rk, To)      # same double-precision SVD path, bit for bit
+
+
+def test_compute_transformation_and_rmse(orc):
+    """TransformationEstimation*::ComputeTransformation / ComputeRMSE on an explicit correspondence list."""
+    src, sn, tgt, tn = small_pair(n=8000)
+    corr, _, _ = orc.correspondences(src, tgt, 0.03)
+    s_pc, t_pc = cloud(src, sn), cloud(tgt, tn)
+    # point to plane
+    est = R.TransformationEstimationPointToPlane()
+    sums = orc.jtj_jtr(orc.P2PLANE, src, tgt, corr, tgt_nrm=tn)
+    ok, To = orc.solve_jtj(sums[:21].astype(np.float32), sums[21:27].astype(np.float32))
+    np.testing.assert_array_equal(est.compute_transformation(s_pc, t_pc, corr), To)
+    assert abs(est.compute_rmse(s_pc, t_pc, corr) - np.sqrt(np.float32(sums[27]) / np.float32(len(corr)))) < 1e-7
+    # point to point (Kabsch with the divide-by-N quirk) and its rmse
+    est = R.TransformationEstimationPointToPoint()
+    To, _ = orc.kabsch(src, tgt, corr)
+    np.testing.assert_array_equal(est.compute_transformation(cloud(src), cloud(tgt), corr), To)
+    d = src[corr[:, 0]].astype(np.float64) - tgt[corr[:, 1]]
+    assert abs(est.compute_rmse(cloud(src), cloud(tgt), corr) - np.sqrt((d ** 2).sum() / len(corr))) < 1e-6
+    # empty correspondence set -> identity (transformation_estimation.cu:199-200)
+    np.testing.assert_array_equal(R.TransformationEstimationPointToPlane().compute_transformation(s_pc, t_pc, np.zeros((0, 2), np.int32)),
+                                  np.eye(4, dtype=np.float32))
+
+
+def test_gicp_nonfinite_rows_are_dropped(orc):
+    """Covariances whose degenerate eigen-plane is axis aligned make the reference's FastEigen3x3 evaluate
+    signf(0) = 0/0 (eigenvalue.inl:28): every GICP row is NaN there.  Product and oracle drop such rows
+    (DESIGN.md parity hazard 8) instead of returning an all-NaN pose."""
+    rng = np.random.default_rng(5)
+    n = 6000
+    nrm = np.array([1.0, 1.0, 0.0]) / np.sqrt(2.0)
+    uv = rng.random((n, 2))
+    tgt = (np.outer(uv[:, 0], [1, -1, 0]) / np.sqrt(2) + np.outer(uv[:, 1], [0, 0, 1])).astype(np.float32)
+    src = (tgt[rng.permutation(n)] + 0.002 * nrm).astype(np.float32)
+    nn = np.tile(nrm.astype(np.float32), (n, 1))
+    crit = R.ICPConvergenceCriteria(0, 0, 3)
+    res = R.registration_generalized_icp(cloud(src, nn), cloud(tgt, nn), 0.01, np.eye(4), None, crit)
+    cov = orc.covariances_from_normals(nn, 1e-3)
+    ref = orc.registration_icp(orc.GICP, src, tgt, 0.01, src_cov=cov, tgt_cov=cov, relative_fitness=0, relative_rmse=0, max_iteration=3)
+    assert np.isfinite(res.transformation).all() and np.isfinite(ref["transformation"]).all()
+    assert res.fitness > 0.5
+    _compare(res, ref, exact_corr=False)
