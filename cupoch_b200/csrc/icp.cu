@@ -197,6 +197,138 @@ __device__ bool solve_jtj(const double *S, float det_thresh, float *T) {
     se3_exp(x, T);
     return true;
 }
+// ---------------------------------------------------------------------------
+// Warp-parallel versions of the 6x6 determinant / LDLT / solve above (one warp, matrices in shared memory).
+// Every scalar is produced by exactly the same operations in the same order as in the sequential code
+// (and the oracle); only independent rows / elements are spread over lanes, which shortens the dependent
+// chain of the per-iteration epilogue from ~15 us to a few us.
+// ---------------------------------------------------------------------------
+struct SolveSmem {
+    float A[36], L[36], b[8], y[8], x[8], temp[8];
+    float T[16];
+    int piv, ok;
+};
+__device__ float det6_warp(SolveSmem &m) {  // on m.L (copy of A), result broadcast to all lanes
+    const int lane = lane_id();
+    float det = 1.f;
+    for (int k = 0; k < 6; ++k) {
+        if (lane == 0) {
+            int p = k;
+            float best = fabsf(m.L[6 * k + k]);
+            for (int i = k + 1; i < 6; ++i)
+                if (fabsf(m.L[6 * i + k]) > best) { best = fabsf(m.L[6 * i + k]); p = i; }
+            m.piv = (best == 0.f) ? -1 : p;
+        }
+        __syncwarp();
+        const int p = m.piv;
+        if (p < 0) return 0.f;
+        if (p != k) {
+            if (lane < 6) { float t = m.L[6 * k + lane]; m.L[6 * k + lane] = m.L[6 * p + lane]; m.L[6 * p + lane] = t; }
+            det = -det;
+        }
+        __syncwarp();
+        const float piv = m.L[6 * k + k];
+        det = det * piv;
+        const int nr = 5 - k;  // rows/cols below/right of the pivot
+        if (lane < nr * nr) {
+            const int i = k + 1 + lane / nr, j = k + 1 + lane % nr;
+            const float f = m.L[6 * i + k] / piv;
+            m.L[6 * i + j] = m.L[6 * i + j] - f * m.L[6 * k + j];
+        }
+        __syncwarp();
+    }
+    return det;
+}
+__device__ void ldlt6_solve_warp(SolveSmem &m) {  // factors m.L (copy of A) in place, solves into m.x
+    const int lane = lane_id();
+    int tr[6];
+    for (int k = 0; k < 6; ++k) {
+        if (lane == 0) {
+            int ib = k;
+            float big = fabsf(m.L[6 * k + k]);
+            for (int i = k + 1; i < 6; ++i)
+                if (fabsf(m.L[6 * i + i]) > big) { big = fabsf(m.L[6 * i + i]); ib = i; }
+            m.piv = ib;
+        }
+        __syncwarp();
+        const int ib = m.piv;
+        tr[k] = ib;
+        if (ib != k) {  // symmetric swap of rows/cols k and ib in the lower triangle (disjoint element sets)
+            if (lane < k) { float t = m.L[6 * k + lane]; m.L[6 * k + lane] = m.L[6 * ib + lane]; m.L[6 * ib + lane] = t; }
+            if (lane > ib && lane < 6) { float t = m.L[6 * lane + k]; m.L[6 * lane + k] = m.L[6 * lane + ib]; m.L[6 * lane + ib] = t; }
+            if (lane == 31) { float t = m.L[6 * k + k]; m.L[6 * k + k] = m.L[6 * ib + ib]; m.L[6 * ib + ib] = t; }
+            if (lane > k && lane < ib) { float t = m.L[6 * lane + k]; m.L[6 * lane + k] = m.L[6 * ib + lane]; m.L[6 * ib + lane] = t; }
+        }
+        __syncwarp();
+        if (k > 0) {
+            if (lane < k) m.temp[lane] = m.L[6 * lane + lane] * m.L[6 * k + lane];
+            __syncwarp();
+            if (lane == 0) {
+                float sacc = 0.f;
+                for (int j = 0; j < k; ++j) sacc = sacc + m.L[6 * k + j] * m.temp[j];
+                m.L[6 * k + k] = m.L[6 * k + k] - sacc;
+            } else if (lane > k && lane < 6) {
+                float s2 = 0.f;
+                for (int j = 0; j < k; ++j) s2 = s2 + m.L[6 * lane + j] * m.temp[j];
+                m.L[6 * lane + k] = m.L[6 * lane + k] - s2;
+            }
+            __syncwarp();
+        }
+        const float akk = m.L[6 * k + k];
+        if (fabsf(akk) > 0.f && lane > k && lane < 6) m.L[6 * lane + k] = m.L[6 * lane + k] / akk;
+        __syncwarp();
+    }
+    if (lane == 0) {  // substitutions: short sequential chains
+        float y[6];
+        for (int i = 0; i < 6; ++i) y[i] = m.b[i];
+        for (int k = 0; k < 6; ++k)
+            if (tr[k] != k) { float t = y[k]; y[k] = y[tr[k]]; y[tr[k]] = t; }
+        for (int i = 0; i < 6; ++i) {
+            float sacc = y[i];
+            for (int j = 0; j < i; ++j) sacc = sacc - m.L[6 * i + j] * y[j];
+            y[i] = sacc;
+        }
+        for (int i = 0; i < 6; ++i) y[i] = (fabsf(m.L[6 * i + i]) > FLT_MIN) ? y[i] / m.L[6 * i + i] : 0.f;
+        for (int i = 5; i >= 0; --i) {
+            float sacc = y[i];
+            for (int j = i + 1; j < 6; ++j) sacc = sacc - m.L[6 * j + i] * y[j];
+            y[i] = sacc;
+        }
+        for (int k = 5; k >= 0; --k)
+            if (tr[k] != k) { float t = y[k]; y[k] = y[tr[k]]; y[tr[k]] = t; }
+        for (int i = 0; i < 6; ++i) m.x[i] = y[i];
+    }
+    __syncwarp();
+}
+// warp version of solve_jtj: result in m.T (all lanes may read after the call), returns success
+__device__ bool solve_jtj_warp(const double *S, float det_thresh, SolveSmem &m) {
+    const int lane = lane_id();
+    if (lane == 0) {
+        int p = 0;
+        for (int a = 0; a < 6; ++a)
+            for (int c = a; c < 6; ++c) { float v = (float)S[p++]; m.A[6 * a + c] = v; m.A[6 * c + a] = v; }
+        for (int a = 0; a < 6; ++a) m.b[a] = -(float)S[21 + a];
+        identity4(m.T);
+    }
+    __syncwarp();
+    if (det_thresh > 0) {
+        for (int e = lane; e < 36; e += 32) m.L[e] = m.A[e];
+        __syncwarp();
+        const float det = det6_warp(m);
+        if (fabsf(det) < det_thresh || isnan(det) || isinf(det)) return false;
+    }
+    for (int e = lane; e < 36; e += 32) m.L[e] = m.A[e];
+    __syncwarp();
+    ldlt6_solve_warp(m);
+    if (lane == 0) {
+        float x[6];
+        for (int i = 0; i < 6; ++i) x[i] = m.x[i];
+        se3_exp(x, m.T);
+    }
+    __syncwarp();
+    return true;
+}
+
 __device__ void matmul4(const float *A, const float *B, float *C) {  // registration.cu:159
     float R[16];
     for (int i = 0; i < 4; ++i)
@@ -283,35 +415,44 @@ __device__ void kabsch_from_sums(const double *S, unsigned long long n_model, fl
     }
 }
 
-// registration.cu:71-78,154-172 -- runs in ONE thread after the grid-wide sum.
+// registration.cu:71-78,154-172 -- runs in ONE WARP (all 32 lanes call it) after the grid-wide sum.
 template <int KIND>
-__device__ void icp_finalize(const IcpArgs &a, IcpState *st) {
+__device__ void icp_finalize(const IcpArgs &a, IcpState *st, SolveSmem &m) {
+    const int lane = lane_id();
     const double *S = st->total;
-    double cnt = S[29];
-    float fit = 0.f, rmse = 0.f;
-    if (cnt > 0) {
-        fit = (float)cnt / (float)a.n_total;
-        rmse = sqrtf((float)S[28] / (float)cnt);
+    int action = 0;  // 0 = nothing more, 1 = compute an update
+    double cnt = 0.0;
+    if (lane == 0) {
+        cnt = S[29];
+        float fit = 0.f, rmse = 0.f;
+        if (cnt > 0) {
+            fit = (float)cnt / (float)a.n_total;
+            rmse = sqrtf((float)S[28] / (float)cnt);
+        }
+        const float pf = st->fitness, pr = st->rmse;
+        st->fitness = fit;
+        st->rmse = rmse;
+        st->n_corr = (long long)cnt;
+        if (a.step_mode) {
+            action = 0;
+        } else if (a.launch_idx > 0 && fabsf(pf - fit) < a.rel_fitness && fabsf(pr - rmse) < a.rel_rmse) {
+            st->converged = 1;
+            st->done = (a.corr_index && a.launch_idx < a.max_iter) ? 1 : 2;
+        } else if (a.launch_idx >= a.max_iter) {
+            st->done = 2;
+        } else {
+            action = 1;
+        }
     }
-    float pf = st->fitness, pr = st->rmse;
-    st->fitness = fit;
-    st->rmse = rmse;
-    st->n_corr = (long long)cnt;
-    if (a.step_mode) return;
-    if (a.launch_idx > 0 && fabsf(pf - fit) < a.rel_fitness && fabsf(pr - rmse) < a.rel_rmse) {
-        st->converged = 1;
-        st->done = (a.corr_index && a.launch_idx < a.max_iter) ? 1 : 2;
-        return;
-    }
-    if (a.launch_idx >= a.max_iter) {
-        st->done = 2;
-        return;
-    }
-    float Up[16];
-    identity4(Up);
-    if (cnt > 0) {
+    action = __shfl_sync(CPHB_FULL, action, 0);
+    if (!action) return;
+    const bool have_corr = __shfl_sync(CPHB_FULL, (int)(cnt > 0), 0) != 0;
+    if (lane == 0) identity4(m.T);
+    __syncwarp();
+    if (have_corr) {
         if (KIND == CPHB_EST_POINT_TO_POINT) {
-            kabsch_from_sums(S, a.n_total, Up);
+            if (lane == 0) kabsch_from_sums(S, a.n_total, m.T);
+            __syncwarp();
         } else {
             bool have = true;
             if ((KIND == CPHB_EST_POINT_TO_PLANE || KIND == CPHB_EST_COLORED_ICP) && !a.tgt_nrm) have = false;
@@ -319,26 +460,40 @@ __device__ void icp_finalize(const IcpArgs &a, IcpState *st) {
             if (KIND == CPHB_EST_COLORED_ICP && (!a.tgt_col || !a.src_col)) have = false;
             if (KIND == CPHB_EST_GENERALIZED_ICP && (!a.tgt_cov || !a.src_cov)) have = false;
             if (have) {
-                float dt = (KIND == CPHB_EST_GENERALIZED_ICP) ? -1.f : a.det_thresh;
-                bool ok = solve_jtj(S, dt, Up);
-                if (ok && KIND == CPHB_EST_SYMMETRIC) {  // transformation_estimation.cu:319-339
+                const float dt = (KIND == CPHB_EST_GENERALIZED_ICP) ? -1.f : a.det_thresh;
+                const bool ok = solve_jtj_warp(S, dt, m);
+                if (!ok && lane == 0) identity4(m.T);
+                if (ok && KIND == CPHB_EST_SYMMETRIC && lane == 0) {  // transformation_estimation.cu:319-339
                     double R[9], R2[9];
                     for (int i = 0; i < 3; ++i)
-                        for (int j = 0; j < 3; ++j) R[3 * i + j] = (double)Up[4 * i + j];
+                        for (int j = 0; j < 3; ++j) R[3 * i + j] = (double)m.T[4 * i + j];
                     for (int i = 0; i < 3; ++i)
                         for (int j = 0; j < 3; ++j)
                             R2[3 * i + j] = R[3 * i] * R[j] + R[3 * i + 1] * R[3 + j] + R[3 * i + 2] * R[6 + j];
                     for (int i = 0; i < 3; ++i)
-                        for (int j = 0; j < 3; ++j) Up[4 * i + j] = (float)R2[3 * i + j];
+                        for (int j = 0; j < 3; ++j) m.T[4 * i + j] = (float)R2[3 * i + j];
                 }
+                __syncwarp();
             }
         }
     }
-    float Tn[16];
-    matmul4(Up, st->T, Tn);
-    for (int i = 0; i < 16; ++i) { st->T[i] = Tn[i]; st->U[i] = Up[i]; }
-    st->apply_u = 1;
-    st->iterations += 1;
+    // transformation = update * transformation (registration.cu:159): one output element per lane
+    float tn = 0.f;
+    if (lane < 16) {
+        const int i = lane >> 2, j = lane & 3;
+        const float *A = m.T, *B = st->T;
+        tn = ((A[4 * i] * B[j] + A[4 * i + 1] * B[4 + j]) + A[4 * i + 2] * B[8 + j]) + A[4 * i + 3] * B[12 + j];
+    }
+    __syncwarp();
+    if (lane < 16) {
+        st->T[lane] = tn;
+        st->U[lane] = m.T[lane];
+    }
+    if (lane == 0) {
+        st->apply_u = 1;
+        st->iterations += 1;
+    }
+    __syncwarp();
 }
 
 // ===========================================================================
@@ -623,6 +778,7 @@ template <int KIND>
 __global__ void __launch_bounds__(ICP_REDUCE_BLOCK) icp_reduce_kernel(const __grid_constant__ IcpArgs a) {
     __shared__ double s_acc[ICP_REDUCE_BLOCK / 32][32];
     __shared__ unsigned s_last;
+    __shared__ SolveSmem s_solve;
     IcpState *st = a.st;
     const int done = *(volatile int *)&st->done;
     if (done == 2) return;
@@ -669,12 +825,12 @@ __global__ void __launch_bounds__(ICP_REDUCE_BLOCK) icp_reduce_kernel(const __gr
         if (a.use_p2p) t = p2p_exchange_sum(a.p2p, t);  // the collective, fused: NVLink stores + flags
         if (a.defer_finalize) st->local[threadIdx.x] = t;
         else st->total[threadIdx.x] = t;
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        st->ticket = 0;
-        st->tile_counter = 0;
-        if (!a.defer_finalize) icp_finalize<KIND>(a, st);
+        __syncwarp();
+        if (threadIdx.x == 0) {
+            st->ticket = 0;
+            st->tile_counter = 0;
+        }
+        if (!a.defer_finalize) icp_finalize<KIND>(a, st, s_solve);
         __threadfence();
     }
 }
@@ -682,7 +838,8 @@ __global__ void __launch_bounds__(ICP_REDUCE_BLOCK) icp_reduce_kernel(const __gr
 // multi-GPU: runs after the all-reduce of st->local into st->total
 template <int KIND>
 __global__ void icp_finalize_kernel(const __grid_constant__ IcpArgs a) {
-    if (threadIdx.x == 0 && a.st->done != 2) icp_finalize<KIND>(a, a.st);
+    __shared__ SolveSmem s_solve;
+    if (threadIdx.x < 32 && a.st->done != 2) icp_finalize<KIND>(a, a.st, s_solve);
 }
 
 // ---------------------------------------------------------------------------
