@@ -650,11 +650,14 @@ __global__ void __launch_bounds__(ICP_SEARCH_WARPS * 32) icp_iteration_kernel(co
     const unsigned live = (KIND == CPHB_EST_POINT_TO_POINT) ? c_live_p2p : c_live_jtj;
     constexpr int NROWS = (KIND == CPHB_EST_COLORED_ICP) ? 2 : (KIND == CPHB_EST_GENERALIZED_ICP) ? 3 : 1;
 
+    // the claim of the NEXT tile (one L2 atomic round trip) is issued at the top of the current tile and only
+    // consumed at its end, so it never sits on the critical path
+    unsigned next_tile = 0;
+    if (lane == 0) next_tile = atomicAdd(&st->tile_counter, 1u);
     while (true) {
-        unsigned tile = 0;
-        if (lane == 0) tile = atomicAdd(&st->tile_counter, 1u);
-        tile = __shfl_sync(CPHB_FULL, tile, 0);
+        const unsigned tile = __shfl_sync(CPHB_FULL, next_tile, 0);
         if (tile >= n_tiles) break;
+        if (lane == 0) next_tile = atomicAdd(&st->tile_counter, 1u);
         const unsigned i = tile * 32 + lane;  // position in Hilbert order (< n_pad)
         float4 s = a.src[i];
         const unsigned orig = __float_as_uint(s.w);
@@ -1287,7 +1290,7 @@ extern "C" int cphb_icp_create(const cphb_cloud *source, const cphb_cloud *targe
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
         const unsigned n_tiles = n_pad / 32;
         unsigned want = (n_tiles + ICP_SEARCH_WARPS - 1) / ICP_SEARCH_WARPS;
-        unsigned cap = (unsigned)sms * 8u;  // 8 blocks x 4 warps = 32 resident warps / SM
+        unsigned cap = (unsigned)sms * 9u;  // 9 blocks x 4 warps = 36 resident warps / SM at <= 56 registers
         icp->grid = want < cap ? want : cap;
         unsigned rg = (n_tiles + 63) / 64;
         icp->reduce_grid = rg < 1 ? 1 : (rg > (unsigned)sms ? (unsigned)sms : rg);

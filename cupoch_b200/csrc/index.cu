@@ -203,33 +203,50 @@ __global__ void __launch_bounds__(256) gather_points_kernel(const float *__restr
 // ---------------------------------------------------------------------------
 #define KD_GROUP 1024
 #define KD_THREADS 256
+#define KD_QBITS 14 /* coordinate quantisation inside a segment's bbox; ties broken by position */
+// Per level: bbox per segment -> widest axis -> 24-bit key (14-bit quantised coordinate, 10-bit position:
+// unique) -> radix select of the median key per segment (3 passes of 8 bits, 256-bin histograms in shared
+// memory) -> stable partition around it.  The split only has to be a valid partition (search correctness
+// never depends on it); quantisation can make sibling boxes overlap by at most 2^-14 of the extent.
+struct KdSmem {
+    float4 p[2][KD_GROUP];
+    unsigned key[KD_GROUP];
+    unsigned hist[16][256];
+    unsigned lo[16][3], hi[16][3];
+    unsigned prefix[16], rank[16], pivot[16];
+    int axis[16];
+    unsigned scan[KD_GROUP + 1];
+    unsigned warp_tot[KD_THREADS / 32];
+};
 __global__ void __launch_bounds__(KD_THREADS) kd_refine_kernel(float4 *pts, size_t n_pad) {
-    __shared__ float4 s_p[KD_GROUP];
-    __shared__ unsigned s_k[KD_GROUP];
-    __shared__ unsigned s_lo[32][3], s_hi[32][3];
-    __shared__ int s_axis[32];
+    extern __shared__ __align__(16) unsigned char kd_raw[];
+    KdSmem &m = *reinterpret_cast<KdSmem *>(kd_raw);
     const size_t base = (size_t)blockIdx.x * KD_GROUP;
-    const int tid = threadIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     for (int e = tid; e < KD_GROUP; e += KD_THREADS) {
         size_t i = base + e;
-        s_p[e] = (i < n_pad) ? pts[i] : make_float4(FLT_MAX, FLT_MAX, FLT_MAX, __uint_as_float(0xffffffffu));
+        m.p[0][e] = (i < n_pad) ? pts[i] : make_float4(FLT_MAX, FLT_MAX, FLT_MAX, __uint_as_float(0xffffffffu));
     }
     __syncthreads();
+    int cur = 0;
     for (int level = 0; level < 5; ++level) {
-        const int S = KD_GROUP >> level;  // segment size (>= 64), n_seg = 1 << level
-        const int n_seg = 1 << level;
+        const int S = KD_GROUP >> level, n_seg = 1 << level, half = S >> 1;
+        const float4 *src = m.p[cur];
+        float4 *dst = m.p[cur ^ 1];
         if (tid < n_seg) {
 #pragma unroll
-            for (int a = 0; a < 3; ++a) { s_lo[tid][a] = 0xffffffffu; s_hi[tid][a] = 0u; }
+            for (int a = 0; a < 3; ++a) { m.lo[tid][a] = 0xffffffffu; m.hi[tid][a] = 0u; }
+            m.prefix[tid] = 0u;
+            m.rank[tid] = (unsigned)half;  // 0-based rank of the pivot = first element of the upper half
         }
         __syncthreads();
         for (int e = tid; e < KD_GROUP; e += KD_THREADS) {
-            const float4 p = s_p[e];
-            if (__float_as_uint(p.w) != 0xffffffffu) {  // padding does not stretch the boxes
+            const float4 q = src[e];
+            if (__float_as_uint(q.w) != 0xffffffffu) {
                 const int sg = e / S;
-                atomicMin(&s_lo[sg][0], f2ord(p.x)); atomicMax(&s_hi[sg][0], f2ord(p.x));
-                atomicMin(&s_lo[sg][1], f2ord(p.y)); atomicMax(&s_hi[sg][1], f2ord(p.y));
-                atomicMin(&s_lo[sg][2], f2ord(p.z)); atomicMax(&s_hi[sg][2], f2ord(p.z));
+                atomicMin(&m.lo[sg][0], f2ord(q.x)); atomicMax(&m.hi[sg][0], f2ord(q.x));
+                atomicMin(&m.lo[sg][1], f2ord(q.y)); atomicMax(&m.hi[sg][1], f2ord(q.y));
+                atomicMin(&m.lo[sg][2], f2ord(q.z)); atomicMax(&m.hi[sg][2], f2ord(q.z));
             }
         }
         __syncthreads();
@@ -237,43 +254,108 @@ __global__ void __launch_bounds__(KD_THREADS) kd_refine_kernel(float4 *pts, size
             float ex[3];
 #pragma unroll
             for (int a = 0; a < 3; ++a)
-                ex[a] = (s_lo[tid][a] <= s_hi[tid][a]) ? ord2f(s_hi[tid][a]) - ord2f(s_lo[tid][a]) : 0.f;
+                ex[a] = (m.lo[tid][a] <= m.hi[tid][a]) ? ord2f(m.hi[tid][a]) - ord2f(m.lo[tid][a]) : 0.f;
             int ax = 0;
             if (ex[1] > ex[ax]) ax = 1;
             if (ex[2] > ex[ax]) ax = 2;
-            s_axis[tid] = ax;
+            m.axis[tid] = ax;
         }
         __syncthreads();
         for (int e = tid; e < KD_GROUP; e += KD_THREADS) {
-            const float4 p = s_p[e];
-            const int ax = s_axis[e / S];
-            const float c = (ax == 0) ? p.x : (ax == 1) ? p.y : p.z;
-            // padding sorts last; ties broken by original index so the order is deterministic
-            s_k[e] = (__float_as_uint(p.w) == 0xffffffffu) ? 0xffffffffu : f2ord(c);
+            const float4 q = src[e];
+            const int sg = e / S, ax = m.axis[sg];
+            unsigned qk = (1u << KD_QBITS) - 1u;  // padding sorts last
+            if (__float_as_uint(q.w) != 0xffffffffu) {
+                const float c = (ax == 0) ? q.x : (ax == 1) ? q.y : q.z;
+                const float lo = ord2f(m.lo[sg][ax]), hi = ord2f(m.hi[sg][ax]);
+                const float t = (hi > lo) ? (c - lo) / (hi - lo) : 0.f;
+                qk = (unsigned)fminf(fmaxf(t * (float)((1u << KD_QBITS) - 2u), 0.f), (float)((1u << KD_QBITS) - 2u));
+            }
+            m.key[e] = (qk << 10) | (unsigned)(e & (S - 1)) | 0u;  // 24 bits, unique inside a segment
         }
         __syncthreads();
-        // sort every aligned segment of S elements ascending
-        for (int k = 2; k <= S; k <<= 1) {
-            for (int j = k >> 1; j > 0; j >>= 1) {
-                for (int t = tid; t < KD_GROUP / 2; t += KD_THREADS) {
-                    const int i = 2 * t - (t & (j - 1));  // lower index of the pair (i, i + j)
-                    const int l = i + j;
-                    const bool up = (k == S) ? true : ((i & k) == 0);
-                    const unsigned ki = s_k[i], kl = s_k[l];
-                    const unsigned wi = __float_as_uint(s_p[i].w), wl = __float_as_uint(s_p[l].w);
-                    const bool gt = (ki > kl) || (ki == kl && wi > wl);
-                    if (gt == up) {
-                        s_k[i] = kl; s_k[l] = ki;
-                        const float4 tmp = s_p[i]; s_p[i] = s_p[l]; s_p[l] = tmp;
-                    }
+        // ---- radix select of the element of rank `half` per segment: 3 passes of 8 bits, MSB first ----
+        for (int pass = 0; pass < 3; ++pass) {
+            const int shift = 16 - 8 * pass;
+            for (int e = tid; e < n_seg * 256; e += KD_THREADS) (&m.hist[0][0])[e] = 0u;
+            __syncthreads();
+            for (int e = tid; e < KD_GROUP; e += KD_THREADS) {
+                const int sg = e / S;
+                const unsigned k = m.key[e];
+                // elements whose higher digits equal the prefix found so far
+                if (pass == 0 || (k >> (shift + 8)) == m.prefix[sg]) atomicAdd(&m.hist[sg][(k >> shift) & 255u], 1u);
+            }
+            __syncthreads();
+            for (int sg = warp; sg < n_seg; sg += KD_THREADS / 32) {
+                // lane owns bins [8*lane, 8*lane+8): find the bin where the cumulative count passes rank
+                unsigned c[8], tot = 0;
+#pragma unroll
+                for (int b8 = 0; b8 < 8; ++b8) { c[b8] = m.hist[sg][8 * lane + b8]; tot += c[b8]; }
+                unsigned incl = tot;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    unsigned y = __shfl_up_sync(CPHB_FULL, incl, o);
+                    if (lane >= o) incl += y;
                 }
-                __syncthreads();
+                const unsigned excl = incl - tot, r = m.rank[sg];
+                if (r >= excl && r < incl) {  // exactly one lane
+                    unsigned acc = excl;
+                    int bin = 8 * lane;
+#pragma unroll
+                    for (int b8 = 0; b8 < 8; ++b8) {
+                        if (r >= acc + c[b8]) { acc += c[b8]; bin = 8 * lane + b8 + 1; }
+                        else break;
+                    }
+                    m.prefix[sg] = (m.prefix[sg] << 8) | (unsigned)bin;
+                    m.rank[sg] = r - acc;
+                }
+            }
+            __syncthreads();
+        }
+        // prefix[sg] is now the full 24-bit key of the pivot: lower half = keys < pivot (exactly `half` of them)
+        // ---- stable partition: exclusive scan of is_lower over the group in position order ----
+        {
+            unsigned f[4], cnt = 0;
+#pragma unroll
+            for (int r4 = 0; r4 < 4; ++r4) {
+                const int e = 4 * tid + r4;
+                f[r4] = (m.key[e] < m.prefix[e / S]) ? 1u : 0u;
+                cnt += f[r4];
+            }
+            unsigned incl = cnt;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                unsigned y = __shfl_up_sync(CPHB_FULL, incl, o);
+                if (lane >= o) incl += y;
+            }
+            if (lane == 31) m.warp_tot[warp] = incl;
+            __syncthreads();
+            unsigned wbase = 0;
+            for (int w2 = 0; w2 < warp; ++w2) wbase += m.warp_tot[w2];
+            unsigned run = wbase + incl - cnt;
+#pragma unroll
+            for (int r4 = 0; r4 < 4; ++r4) {
+                m.scan[4 * tid + r4] = run;
+                run += f[r4];
+            }
+            if (tid == KD_THREADS - 1) m.scan[KD_GROUP] = run;
+            __syncthreads();
+#pragma unroll
+            for (int r4 = 0; r4 < 4; ++r4) {
+                const int e = 4 * tid + r4;
+                const int sg = e / S, s0 = sg * S;
+                const unsigned lower_before = m.scan[e] - m.scan[s0];
+                const unsigned pos_in_seg = (unsigned)(e - s0);
+                const unsigned d = f[r4] ? (unsigned)s0 + lower_before : (unsigned)s0 + (unsigned)half + (pos_in_seg - lower_before);
+                dst[d] = src[e];
             }
         }
+        __syncthreads();
+        cur ^= 1;
     }
     for (int e = tid; e < KD_GROUP; e += KD_THREADS) {
         size_t i = base + e;
-        if (i < n_pad) pts[i] = s_p[e];
+        if (i < n_pad) pts[i] = m.p[cur][e];
     }
 }
 
@@ -440,7 +522,8 @@ extern "C" int cphb_index_create(const float *xyz, size_t n, void *stream, cphb_
     }
     CPHB_LAUNCH(gather_points_kernel, (unsigned)((n_pad + 255) / 256), 256, 0, s, xyz, perm, n, n_pad, pts, inv);
     if (n > KD_GROUP / 2) {  // tiny clouds: nothing to gain
-        CPHB_LAUNCH(kd_refine_kernel, (unsigned)((n_pad + KD_GROUP - 1) / KD_GROUP), KD_THREADS, 0, s, pts, n_pad);
+        CPHB_CUDA(cudaFuncSetAttribute(kd_refine_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(KdSmem)));
+        CPHB_LAUNCH(kd_refine_kernel, (unsigned)((n_pad + KD_GROUP - 1) / KD_GROUP), KD_THREADS, sizeof(KdSmem), s, pts, n_pad);
         CPHB_LAUNCH(inverse_perm_kernel, (unsigned)((n_pad + 255) / 256), 256, 0, s, pts, n_pad, inv);
     }
     CPHB_LAUNCH(leaf_box_kernel, (unsigned)((pad[0] * 32 + 255) / 256), 256, 0, s, pts, n, pad[0], boxes[0]);

@@ -55,10 +55,11 @@ __global__ void __launch_bounds__(256) voxel_insert_kernel(const float *__restri
     size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
     bool valid = i < n;
     unsigned long long key = valid ? voxel_key(pts + 3 * i, g) : VX_EMPTY;
-    // warp-cooperative dedup: one inserter per distinct key in the warp
-    unsigned peers = __match_any_sync(CPHB_FULL, key);
-    bool leader = valid && (__ffs(peers) - 1 == lane_id());
-    if (!leader) return;
+    // warp-cooperative dedup of runs: scan-ordered inputs put consecutive points into the same voxel, so a
+    // lane whose left neighbour holds the same key leaves the insert to it (one CAS per run per warp).
+    // (A full __match_any_sync costs more than the CAS it saves on unordered inputs.)
+    const unsigned long long left = __shfl_up_sync(CPHB_FULL, key, 1);
+    if (!valid || (lane_id() > 0 && left == key)) return;
     unsigned h = hash64(key) & mask;
     while (true) {
         unsigned long long prev = atomicCAS(&keys[h], VX_EMPTY, key);
@@ -70,14 +71,22 @@ __global__ void __launch_bounds__(256) voxel_insert_kernel(const float *__restri
 __global__ void __launch_bounds__(256) voxel_assign_kernel(const unsigned long long *__restrict__ keys, size_t T,
                                                            unsigned *ids, unsigned long long *dense_keys,
                                                            unsigned *dense_ids, unsigned *counter) {
+    __shared__ unsigned s_warp[8];
+    __shared__ unsigned s_base;
     size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
     bool occ = i < T && keys[i] != VX_EMPTY;
     unsigned m = __ballot_sync(CPHB_FULL, occ);
-    unsigned base = 0;
-    if (lane_id() == 0 && m) base = atomicAdd(counter, (unsigned)__popc(m));
-    base = __shfl_sync(CPHB_FULL, base, 0);
+    const int warp = threadIdx.x >> 5;
+    if (lane_id() == 0) s_warp[warp] = __popc(m);
+    __syncthreads();
+    if (threadIdx.x == 0) {  // one global atomic per block (not per warp: 131k same-address atomics serialise)
+        unsigned tot = 0;
+        for (int w2 = 0; w2 < 8; ++w2) { unsigned c = s_warp[w2]; s_warp[w2] = tot; tot += c; }
+        s_base = tot ? atomicAdd(counter, tot) : 0u;
+    }
+    __syncthreads();
     if (occ) {
-        unsigned id = base + __popc(m & ((1u << lane_id()) - 1u));
+        unsigned id = s_base + s_warp[warp] + __popc(m & ((1u << lane_id()) - 1u));
         ids[i] = id;
         dense_keys[id] = keys[i];
         dense_ids[id] = id;
