@@ -6,11 +6,10 @@ import socket
 
 import numpy as np
 import pytest
-import torch
-import torch.distributed as dist
-import torch.multiprocessing as mp
 
 from cupoch_b200.distributed import gather_correspondences, shard_range
+
+# torch is imported inside the tests: collecting this module for `-m gpu` must not pay the cold `import torch`
 
 
 def test_shard_range_tiles_exactly():
@@ -35,6 +34,8 @@ def _free_port():
 
 
 def _worker(rank, world, port, q):
+    import torch
+    import torch.distributed as dist
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
@@ -63,6 +64,7 @@ def _worker(rank, world, port, q):
 
 
 def test_sharded_sums_equal_global_sums(orc):
+    import torch.multiprocessing as mp
     from cupoch_b200.testing import datagen
     world, port = 2, _free_port()
     ctx = mp.get_context("spawn")
