@@ -301,6 +301,7 @@ struct WarpSearchBase {
     unsigned bound;        // warp-uniform cull bound (d2 bits)
     unsigned phase;        // bit b = parity of mbarrier b
     bool valid;            // lane holds a real query
+    bool warm;             // bounds are already tight (ICP warm start): skip the ordering refinements
     float4 *tile;          // per-warp smem: 2 leaf tiles [2][CPHB_LEAF]
     uint64_t *bar;         // per-warp smem: 2 mbarriers
 };
@@ -410,7 +411,7 @@ struct Visit {
             dkey = __float_as_uint(box_dist2(lo, hi, c3, c3));
             // boxes containing the centre all have key 0: break those ties by the distance of the box
             // centre so the box "around" the warp comes first
-            if (dkey == 0u) {
+            if (!w.warm && dkey == 0u) {
                 const float mx = 0.5f * lo.x + 0.5f * hi.x - c3[0], my = 0.5f * lo.y + 0.5f * hi.y - c3[1],
                             mz = 0.5f * lo.z + 0.5f * hi.z - c3[2];
                 // scaled far below any non-zero box distance of interest: only an ordering hint
@@ -479,6 +480,7 @@ __device__ __forceinline__ void warp_search_setup(W &w, float4 *tile, uint64_t *
     w.tile = tile;
     w.bar = bar;
     w.phase = 0;
+    w.warm = false;
     if (lane_id() == 0) {
         mbar_init(bar, 1);
         mbar_init(bar + 1, 1);

@@ -20,6 +20,7 @@
 #include <float.h>
 #include <math.h>
 #include <stddef.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "cphb_internal.cuh"
@@ -729,6 +730,7 @@ __global__ void __launch_bounds__(ICP_SEARCH_WARPS * 32) icp_iteration_kernel(co
             }
         }
         warp_update_bound(w);
+        w.warm = (w.bound < (unsigned)(init >> 32));  // every valid lane starts from a real candidate
         if (!w.valid) w.best = init;
         warp_query_box(w);
         if (__any_sync(CPHB_FULL, w.valid)) warp_nn_search<TOP>(a.ix, w);
@@ -794,8 +796,20 @@ __global__ void __launch_bounds__(ICP_REDUCE_BLOCK) icp_reduce_kernel(const __gr
     const unsigned t0 = blockIdx.x * chunk, t1 = min(n_tiles, t0 + chunk);
     const int c = threadIdx.x & 31, g = threadIdx.x >> 5;
     {
+        // 8 loads in flight per thread, added in tile order (x + 0.0 is exact, so the padding loads of the
+        // last batch do not change the sum): the naive loop serialises one L2 round trip per tile
         double t = 0.0;
-        for (unsigned k = t0 + g; k < t1; k += ICP_REDUCE_BLOCK / 32) t += __ldcg(&a.tile_sums[(size_t)k * 32 + c]);
+        constexpr unsigned STRIDE = ICP_REDUCE_BLOCK / 32;
+        for (unsigned k = t0 + g; k < t1; k += 8 * STRIDE) {
+            double v[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const unsigned kk = k + u * STRIDE;
+                v[u] = (kk < t1) ? __ldcg(&a.tile_sums[(size_t)kk * 32 + c]) : 0.0;
+            }
+#pragma unroll
+            for (int u = 0; u < 8; ++u) t += v[u];
+        }
         s_acc[g][c] = t;
     }
     __syncthreads();
@@ -816,8 +830,17 @@ __global__ void __launch_bounds__(ICP_REDUCE_BLOCK) icp_reduce_kernel(const __gr
     __threadfence();
     {   // all 8 warps share the grid sum (fixed order: row groups of 8, then the 8 group sums)
         double t = 0.0;
-#pragma unroll 4
-        for (unsigned b = g; b < gridDim.x; b += ICP_REDUCE_BLOCK / 32) t += __ldcg(&a.partials[(size_t)b * 32 + c]);
+        constexpr unsigned STRIDE = ICP_REDUCE_BLOCK / 32;
+        for (unsigned b = g; b < gridDim.x; b += 8 * STRIDE) {
+            double v[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const unsigned bb = b + u * STRIDE;
+                v[u] = (bb < gridDim.x) ? __ldcg(&a.partials[(size_t)bb * 32 + c]) : 0.0;
+            }
+#pragma unroll
+            for (int u = 0; u < 8; ++u) t += v[u];
+        }
         s_acc[g][c] = t;
     }
     __syncthreads();
@@ -1290,7 +1313,12 @@ extern "C" int cphb_icp_create(const cphb_cloud *source, const cphb_cloud *targe
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
         const unsigned n_tiles = n_pad / 32;
         unsigned want = (n_tiles + ICP_SEARCH_WARPS - 1) / ICP_SEARCH_WARPS;
-        unsigned cap = (unsigned)sms * 9u;  // 9 blocks x 4 warps = 36 resident warps / SM at <= 56 registers
+        unsigned per_sm = 9u;  // 9 blocks x 4 warps = 36 resident warps / SM at <= 56 registers
+        if (const char *e = getenv("CPHB_ICP_BLOCKS_PER_SM")) {  // tuning hook
+            int v = atoi(e);
+            if (v >= 1 && v <= 32) per_sm = (unsigned)v;
+        }
+        unsigned cap = (unsigned)sms * per_sm;
         icp->grid = want < cap ? want : cap;
         unsigned rg = (n_tiles + 63) / 64;
         icp->reduce_grid = rg < 1 ? 1 : (rg > (unsigned)sms ? (unsigned)sms : rg);
