@@ -302,6 +302,7 @@ struct WarpSearchBase {
     unsigned phase;        // bit b = parity of mbarrier b
     bool valid;            // lane holds a real query
     bool warm;             // bounds are already tight (ICP warm start): skip the ordering refinements
+    int tmax;              // transposed scan when at most this many lanes need the leaf
     float4 *tile;          // per-warp smem: 2 leaf tiles [2][CPHB_LEAF]
     uint64_t *bar;         // per-warp smem: 2 mbarriers
 };
@@ -353,7 +354,7 @@ __device__ __forceinline__ void wait_leaf(W &w, int b) {
 //                 equal d2: the same (d2, index) order as the sequential scan).
 #define CPHB_TRANSPOSE_MAX 14
 __device__ __forceinline__ void scan_tile(const float4 *tile, WarpSearch &w, unsigned need) {
-    if (__popc(need) > CPHB_TRANSPOSE_MAX) {
+    if (__popc(need) > w.tmax) {
         unsigned long long best = w.best;
 #pragma unroll
         for (int j = 0; j < CPHB_LEAF; ++j) {
@@ -481,6 +482,7 @@ __device__ __forceinline__ void warp_search_setup(W &w, float4 *tile, uint64_t *
     w.bar = bar;
     w.phase = 0;
     w.warm = false;
+    w.tmax = CPHB_TRANSPOSE_MAX;
     if (lane_id() == 0) {
         mbar_init(bar, 1);
         mbar_init(bar + 1, 1);

@@ -69,6 +69,7 @@ struct IcpArgs {
     int use_p2p;         // multi-GPU over the fused peer-memory exchange
     P2pView p2p;
     int step_mode;       // debug hook: one search + sums, no solve
+    int tmax;            // transposed-scan threshold (tuning hook)
 };
 
 // sums layout (32 doubles): JTJ kinds: 0..20 JTJ upper | 21..26 JTr | 27 r^2 | 28 sum d2 | 29 count
@@ -639,6 +640,7 @@ __global__ void __launch_bounds__(ICP_SEARCH_WARPS * 32) icp_iteration_kernel(co
 
     WarpSearch w;
     warp_search_setup(w, s_tile[warp], s_bar[warp]);
+    w.tmax = a.tmax;
     float U[12];
 #pragma unroll
     for (int k = 0; k < 12; ++k) U[k] = apply ? st->U[k] : ((k % 5 == 0) ? 1.f : 0.f);
@@ -1449,6 +1451,11 @@ static void fill_args(const cphb_icp *icp, IcpArgs &a) {
     a.sg = (float)sqrt((double)lg);
     float lp = (float)(1.0 - (double)lg);
     a.sp = (float)sqrt((double)lp);
+    a.tmax = CPHB_TRANSPOSE_MAX;
+    if (const char *e = getenv("CPHB_TRANSPOSE_MAX")) {  // tuning hook
+        int v = atoi(e);
+        if (v >= 0 && v <= 32) a.tmax = v;
+    }
 }
 
 static int reset_working_copy(cphb_icp *icp, cudaStream_t s) {

@@ -144,12 +144,20 @@ __global__ void __launch_bounds__(256) bounds_kernel(const float *__restrict__ x
         lo[a] = __reduce_min_sync(CPHB_FULL, lo[a]);
         hi[a] = __reduce_max_sync(CPHB_FULL, hi[a]);
     }
+    // block-level combine first: ~10k same-address global atomics (one set per warp) serialise for ~40 us
+    __shared__ unsigned s_lo[8][3], s_hi[8][3];
+    const int warp = threadIdx.x >> 5;
     if (lane_id() == 0) {
 #pragma unroll
-        for (int a = 0; a < 3; ++a) {
-            atomicMin(&b[a], lo[a]);
-            atomicMax(&b[3 + a], hi[a]);
-        }
+        for (int a = 0; a < 3; ++a) { s_lo[warp][a] = lo[a]; s_hi[warp][a] = hi[a]; }
+    }
+    __syncthreads();
+    if (threadIdx.x < 3) {
+        const int a = threadIdx.x;
+        unsigned l = s_lo[0][a], h = s_hi[0][a];
+        for (int w2 = 1; w2 < (int)(blockDim.x >> 5); ++w2) { l = min(l, s_lo[w2][a]); h = max(h, s_hi[w2][a]); }
+        atomicMin(&b[a], l);
+        atomicMax(&b[3 + a], h);
     }
 }
 
