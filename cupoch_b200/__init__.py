@@ -16,6 +16,11 @@ __version__ = "0.1.0"
 
 
 def initialize_allocator(mode=None, initial_pool_size=0, devices=None):
-    """cupoch.initialize_allocator (cupoch_pybind.cpp:47-50).  The B200 engine uses the CUDA
-    stream-ordered pool with an unlimited release threshold; nothing to configure."""
+    """cupoch.initialize_allocator(mode, initial_pool_size, devices) (cupoch_pybind.cpp:47-50,
+    utility/device_vector.cu:28-69).  The B200 engine always allocates from the CUDA stream-ordered pool
+    with an unlimited release threshold; `initial_pool_size` bytes are reserved up front so that no
+    registration call has to grow the pool (a growth step costs tens of milliseconds)."""
+    if initial_pool_size and initial_pool_size > 0:
+        _lib.require_gpu()
+        _lib.check(_lib.lib().cphb_reserve_pool(int(initial_pool_size)))
     return None

@@ -71,6 +71,7 @@ _SIGNATURES = {
     "cphb_compute_rmse": (C.c_int, [C.c_int, C.POINTER(Cloud), C.POINTER(Cloud), _P, C.c_size_t, C.POINTER(IcpParams),
                                     C.POINTER(C.c_float), _P]),
     "cphb_kabsch": (C.c_int, [_P, C.c_size_t, _P, _P, C.c_size_t, C.POINTER(C.c_float), _P]),
+    "cphb_reserve_pool": (C.c_int, [C.c_size_t]),
     "cphb_malloc": (_P, [C.c_size_t]),
     "cphb_free": (None, [_P]),
     "cphb_malloc_host": (_P, [C.c_size_t]),

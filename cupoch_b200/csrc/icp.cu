@@ -21,6 +21,7 @@
 #include <math.h>
 #include <stddef.h>
 #include <stdlib.h>
+#include <time.h>
 #include <string.h>
 
 #include "cphb_internal.cuh"
@@ -1629,11 +1630,22 @@ extern "C" int cphb_icp_step(cphb_icp *icp, const float h_T[16], double h_sums[3
 extern "C" int cphb_registration_icp(const cphb_cloud *source, const cphb_cloud *target, const float h_init[16],
                                      const cphb_icp_params *params, cphb_comm *comm, cphb_icp_result *h_result,
                                      int32_t *corr_out, void *stream) {
+    static const bool dbg = getenv("CPHB_DEBUG_TIMING") != nullptr;
+    struct timespec t0, t1, t2, t3;
+    if (dbg) clock_gettime(CLOCK_MONOTONIC, &t0);
     cphb_icp *icp = nullptr;
     int rc = cphb_icp_create(source, target, params, stream, &icp);
     if (rc) return rc;
+    if (dbg) clock_gettime(CLOCK_MONOTONIC, &t1);
     rc = cphb_icp_run(icp, h_init, comm, h_result, corr_out, stream);
+    if (dbg) clock_gettime(CLOCK_MONOTONIC, &t2);
     cphb_icp_destroy(icp);
+    if (dbg) {
+        clock_gettime(CLOCK_MONOTONIC, &t3);
+        auto ms = [](const timespec &a, const timespec &b) { return (b.tv_sec - a.tv_sec) * 1e3 + (b.tv_nsec - a.tv_nsec) * 1e-6; };
+        fprintf(stderr, "[cphb] registration_icp host ms: create %.3f run %.3f destroy %.3f (loop device %.3f)\n", ms(t0, t1),
+                ms(t1, t2), ms(t2, t3), h_result->loop_ms);
+    }
     return rc;
 }
 

@@ -58,6 +58,15 @@ void cphb_free_async(void *p, cudaStream_t s) {
     if (p) cudaFreeAsync(p, s);
 }
 
+extern "C" int cphb_reserve_pool(size_t bytes) {
+    void *p = nullptr;
+    int rc = cphb_alloc_async(&p, bytes, (cudaStream_t)0);  // also sets the pool's release threshold to "never"
+    if (rc) return rc;
+    CPHB_CUDA(cudaFreeAsync(p, (cudaStream_t)0));
+    CPHB_CUDA(cudaStreamSynchronize((cudaStream_t)0));
+    return CPHB_OK;
+}
+
 // Stream-ordered pool allocation on the default stream: freed blocks stay in the pool (release threshold
 // = max), so repeated allocate/free cycles of the API layers cost microseconds instead of cudaMalloc/cudaFree.
 extern "C" void *cphb_malloc(size_t bytes) {

@@ -236,7 +236,11 @@ int cphb_evaluate_registration(const cphb_cloud *source, const cphb_cloud *targe
  * Host-buffer convenience used by bench.py's e2e leg and the Python mirror:
  * thin wrappers that cudaMalloc/cudaMemcpyAsync around the calls above.
  * ------------------------------------------------------------------------ */
-void *cphb_malloc(size_t bytes);              /* cudaMalloc, NULL on failure */
+/* utility::InitializeAllocator(PoolAllocation, initial_pool_size, ...) (device_vector.cu:28-69): pre-reserve
+ * physical memory in the stream-ordered pool that every allocation of this library comes from, so that no call
+ * on the hot path ever has to grow the pool (a growth step costs tens of milliseconds). */
+int cphb_reserve_pool(size_t bytes);
+void *cphb_malloc(size_t bytes);              /* pool allocation on the default stream, NULL on failure */
 void cphb_free(void *p);
 void *cphb_malloc_host(size_t bytes);         /* pinned */
 void cphb_free_host(void *p);
