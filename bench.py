@@ -48,12 +48,32 @@ def peaks():
 
 
 class ClockSampler(threading.Thread):
+    """SM clock + throttle reasons during the timed region.  NVML (pynvml) when importable -- a sample costs
+    microseconds, so even a 100 ms timed region gets tens of samples -- else nvidia-smi."""
+    REASONS = {"hw_slowdown": 0x8, "sw_power_cap": 0x4, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20}
+
     def __init__(self, index=0):
         super().__init__(daemon=True)
         self.index, self.samples, self.reasons, self.stop_flag = index, [], set(), False
         self.maxclk = None
 
-    def run(self):
+    def _run_nvml(self):
+        import pynvml as nv
+        nv.nvmlInit()
+        h = nv.nvmlDeviceGetHandleByIndex(self.index)
+        self.maxclk = float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM))
+        while not self.stop_flag:
+            self.samples.append(float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)))
+            try:
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                for name, bit in self.REASONS.items():
+                    if r & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(0.005)
+
+    def _run_smi(self):
         q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
@@ -71,10 +91,26 @@ class ClockSampler(threading.Thread):
                 pass
             time.sleep(0.2)
 
+    def run(self):
+        try:
+            self._run_nvml()
+        except Exception:
+            self._run_smi()
+
     def summary(self):
         s = sorted(self.samples)
         return {"sm_mhz": s[len(s) // 2] if s else None, "sm_max_mhz": self.maxclk, "reasons": sorted(self.reasons),
                 "samples": len(s)}
+
+
+def measured_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the fused kernel, from the committed ncu
+    capture of this workload (profiles/roofline_traffic.json); None if absent."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "roofline_traffic.json")) as f:
+            return json.load(f)
+    except Exception:
+        return None
 
 
 def make_workload(n):
@@ -241,6 +277,7 @@ def run_native(args, rank, world):
         total_ms, e2e_ms, knn_ms, loop_ms = [float(x) for x in t.tolist()]
     if rank == 0:
         peak, peak_src = peaks()
+        traffic = measured_traffic()
         ms_step = total_ms / args.steps
         value = ITERS * 1e3 / ms_step
         kern_ms = loop_ms / max(loop_launches, 1)
@@ -264,7 +301,9 @@ def run_native(args, rank, world):
                     "ms": knn_ms / knn_steps,
                     "note": "SearchRadius of all %d source points (sharded by index over the ranks, no collective) incl. query ordering; aggregate rate" % n},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "peak_source": peak_src, "kernel": "icp_iteration_kernel<PointToPlane>",
+                         "traffic": (traffic["traffic_bytes_per_launch"] if traffic and world == 1 and n == 1_000_000 else None),
+                         "traffic_source": (traffic["source"] if traffic else None),
+                         "peak_source": peak_src, "kernel": "icp_iteration_kernel<PointToPlane>",
                          "algorithmic_bytes_per_launch": ALG_BYTES_PER_POINT * units},
             "clocks": sampler.summary(),
             "final": {"fitness": res.fitness, "inlier_rmse": res.inlier_rmse, "iterations": res.iterations,
@@ -283,19 +322,18 @@ def run_native(args, rank, world):
 
 
 def cpu_baseline(src, tgt, tn):
-    """Bounded CPU sample: the oracle port (kd-tree + OpenMP) with 1 and 4 iterations on the full clouds,
-    extrapolated to the 30-iteration job (search cost is flat once aligned)."""
+    """Bounded CPU sample: ONE full 30-iteration registration with the oracle port (kd-tree + OpenMP on all host
+    cores), kd-tree build included -- the same unit of work as a GPU step (a few seconds on a many-core host)."""
     from oracle import oracle_py as orc
-    def t(iters):
-        t0 = time.perf_counter()
-        orc.registration_icp(orc.P2PLANE, src, tgt, MAX_DIST, tgt_nrm=tn, relative_fitness=0, relative_rmse=0,
-                             max_iteration=iters)
-        return time.perf_counter() - t0
-    t1, t4 = t(1), t(4)
-    per_iter = max((t4 - t1) / 3, 1e-9)
-    job = t4 + (ITERS - 4) * per_iter
-    return {"value": ITERS / job, "unit": "iter/s", "cores": orc.num_threads(), "kind": "port",
-            "sample": "1M->1M, 1 and 4 iterations measured (%.2fs, %.2fs), extrapolated to 30 incl. kd-tree build" % (t1, t4)}
+    orc.lib()
+    t0 = time.perf_counter()
+    r = orc.registration_icp(orc.P2PLANE, src, tgt, MAX_DIST, tgt_nrm=tn, relative_fitness=0, relative_rmse=0,
+                             max_iteration=ITERS)
+    dt = time.perf_counter() - t0
+    return {"value": ITERS / dt, "unit": "iter/s", "cores": orc.num_threads(), "kind": "port",
+            "sample": "one full registration: %d -> %d points, %d iterations, kd-tree build included (%.2f s)"
+                      % (len(src), len(tgt), ITERS, dt),
+            "final_fitness": r["fitness"], "final_rmse": r["inlier_rmse"]}
 
 
 def main():
