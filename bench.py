@@ -172,7 +172,18 @@ def run_native(args, rank, world):
         torch.cuda.set_device(local_rank)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
         from cupoch_b200.distributed import make_comm
-        comm = make_comm(dist, rank, world, device="cuda", kind=args.comm)
+        comm_kind = args.comm
+        try:
+            comm = make_comm(dist, rank, world, device="cuda", kind=comm_kind)
+            ok = torch.ones(1, device="cuda")
+        except Exception as e:  # e.g. CUDA IPC not permitted between these processes
+            sys.stderr.write("rank %d: %s exchange unavailable (%s)\n" % (rank, comm_kind, e))
+            comm, ok = None, torch.zeros(1, device="cuda")
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        if ok.item() == 0 and comm_kind == "p2p":   # every rank falls back together
+            comm_kind = "nccl"
+            comm = make_comm(dist, rank, world, device="cuda", kind="nccl")
+        args.comm = comm_kind
 
     n = args.points
     # like the reference's initialize_allocator(PoolAllocation, initial_pool_size): reserve the pool once

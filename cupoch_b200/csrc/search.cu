@@ -151,11 +151,11 @@ static int search_impl(const cphb_index *index, const float *query, size_t nq, f
         rc = cphb_alloc_async((void **)&perm, sizeof(uint32_t) * nq, s);
         if (rc) return rc;
         rc = cphb_hilbert_order(query, nq, perm, index->bounds, 1, s);
-        if (rc) return rc;
+        if (rc) { cphb_free_async(perm, s); return rc; }
     }
     if (h_count) {
         rc = cphb_alloc_async((void **)&count, 16, s);
-        if (rc) return rc;
+        if (rc) { cphb_free_async(perm, s); return rc; }
         CPHB_CUDA(cudaMemsetAsync(count, 0, 8, s));
     }
     const int top = index->v.top;
