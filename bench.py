@@ -175,12 +175,10 @@ def run_native(args, rank, world):
         comm_kind = args.comm
         try:
             comm = make_comm(dist, rank, world, device="cuda", kind=comm_kind)
-            ok = torch.ones(1, device="cuda")
-        except Exception as e:  # e.g. CUDA IPC not permitted between these processes
-            sys.stderr.write("rank %d: %s exchange unavailable (%s)\n" % (rank, comm_kind, e))
-            comm, ok = None, torch.zeros(1, device="cuda")
-        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
-        if ok.item() == 0 and comm_kind == "p2p":   # every rank falls back together
+        except Exception as e:  # make_comm fails on every rank together (e.g. CUDA IPC not permitted)
+            if comm_kind != "p2p":
+                raise
+            sys.stderr.write("rank %d: peer-memory exchange unavailable (%s); using NCCL\n" % (rank, e))
             comm_kind = "nccl"
             comm = make_comm(dist, rank, world, device="cuda", kind="nccl")
         args.comm = comm_kind

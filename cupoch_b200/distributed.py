@@ -43,16 +43,32 @@ def make_comm(dist, rank, world, device=None, kind="p2p"):
         uid = broadcast_unique_id(dist, rank, device)
         _lib.check(L.cphb_comm_nccl_create(uid, world, rank, C.byref(h)))
         return h
+    # every rank goes through the same collectives whatever happens locally, then all agree on the outcome
     mine = C.create_string_buffer(64)
-    _lib.check(L.cphb_comm_p2p_create(world, rank, mine, C.byref(h)))
+    ok = 1
+    try:
+        _lib.check(L.cphb_comm_p2p_create(world, rank, mine, C.byref(h)))
+    except Exception:
+        ok = 0
     t = torch.frombuffer(bytearray(mine.raw), dtype=torch.uint8).clone()
     if device is not None:
         t = t.to(device)
     allh = [torch.zeros_like(t) for _ in range(world)]
     dist.all_gather(allh, t)
-    blob = b"".join(bytes(x.cpu().numpy().tobytes()) for x in allh)
-    _lib.check(L.cphb_comm_p2p_connect(h, blob))
-    dist.barrier()
+    if ok:
+        blob = b"".join(bytes(x.cpu().numpy().tobytes()) for x in allh)
+        try:
+            _lib.check(L.cphb_comm_p2p_connect(h, blob))
+        except Exception:
+            ok = 0
+    flag = torch.tensor([ok], dtype=torch.int32)
+    if device is not None:
+        flag = flag.to(device)
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    if int(flag.item()) == 0:
+        if h:
+            L.cphb_comm_destroy(h)
+        raise _lib.CphbError("peer-memory communicator could not be set up on every rank (CUDA IPC / peer access)")
     return h
 
 
