@@ -314,7 +314,8 @@ __global__ void __launch_bounds__(KD_THREADS) kd_refine_kernel(float4 *pts, size
                     unsigned y = __shfl_up_sync(CPHB_FULL, incl, o);
                     if (lane >= o) incl += y;
                 }
-                const unsigned excl = incl - tot, r = m.rank[sg];
+                const unsigned excl = incl - tot, r = m.rank[sg], pf = m.prefix[sg];
+                __syncwarp();  // every lane has read rank/prefix before the winning lane overwrites them
                 if (r >= excl && r < incl) {  // exactly one lane
                     unsigned acc = excl;
                     int bin = 8 * lane;
@@ -323,7 +324,7 @@ __global__ void __launch_bounds__(KD_THREADS) kd_refine_kernel(float4 *pts, size
                         if (r >= acc + c[b8]) { acc += c[b8]; bin = 8 * lane + b8 + 1; }
                         else break;
                     }
-                    m.prefix[sg] = (m.prefix[sg] << 8) | (unsigned)bin;
+                    m.prefix[sg] = (pf << 8) | (unsigned)bin;
                     m.rank[sg] = r - acc;
                 }
             }
