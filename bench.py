@@ -214,6 +214,8 @@ def run_native(args, rank, world):
 
     ev = [L.cphb_event_create() for _ in range(2)]
 
+    step_log = []
+
     def timed(fn, steps):
         """sum of per-step device times (CUDA events), L2 flushed between steps outside the timed region"""
         total_ms, last = 0.0, None
@@ -226,6 +228,7 @@ def run_native(args, rank, world):
             ms = C.c_float(0)
             _lib.check(L.cphb_event_elapsed_ms(ev[0], ev[1], C.byref(ms)))
             total_ms += ms.value
+            step_log.append(round(ms.value, 3))
         return total_ms, last
 
     for _ in range(args.warmup):
@@ -236,6 +239,7 @@ def run_native(args, rank, world):
         sampler.start()
     launches0 = L.cphb_launch_count()
     total_ms, res = timed(step_resident, args.steps)
+    resident_steps_ms = list(step_log)
     launches = L.cphb_launch_count() - launches0
     loop_ms, loop_launches = res.loop_ms, res.loop_launches
 
@@ -315,6 +319,7 @@ def run_native(args, rank, world):
                          "peak_source": peak_src, "kernel": "icp_iteration_kernel<PointToPlane>",
                          "algorithmic_bytes_per_launch": ALG_BYTES_PER_POINT * units},
             "clocks": sampler.summary(),
+            "step_ms": resident_steps_ms,
             "final": {"fitness": res.fitness, "inlier_rmse": res.inlier_rmse, "iterations": res.iterations,
                       "T": np.asarray(res.transformation).round(6).tolist()},
         }

@@ -311,6 +311,33 @@ struct WarpSearch : WarpSearchBase {
     __device__ __forceinline__ unsigned lane_bound() const { return (unsigned)(best >> 32); }
 };
 
+// Certifying variant used by the ICP loop.  Besides the best key it keeps a LOWER BOUND on the squared distance
+// from the query to every target point other than the best one:
+//   * nodes are culled against the relaxed bound (sqrt(best_d2) + margin)^2 instead of best_d2, so every point
+//     that was never evaluated is farther than that (the bound only shrinks during a search, so a node culled
+//     against an earlier, larger bound is outside the final one too).  For a lane with no candidate yet best_d2
+//     is r^2, so the bound also covers points just outside the radius;
+//   * `second` is the smallest d2 among the evaluated candidates other than the best.
+// L2 = min(second, final relaxed bound) lets later ICP iterations prove, from the query's displacement alone, that
+// the match cannot have changed (icp.cu) -- the search is then skipped for that lane.  The best key itself is
+// found exactly as by WarpSearch: a larger cull bound never hides a candidate.
+struct WarpSearchC : WarpSearchBase {
+    unsigned long long best;
+    unsigned second;  // d2 bits of the second-best evaluated candidate (0x7f800000 = none)
+    unsigned rb;      // cached relaxed bound (d2 bits), >= best_d2
+    float margin;     // distance units, >= 0
+    __device__ __forceinline__ unsigned lane_bound() const { return rb; }
+    __device__ __forceinline__ void refresh() {
+        const unsigned hi = (unsigned)(best >> 32);
+        if (margin > 0.f && hi != 0u) {
+            const float e = __fadd_ru(__fsqrt_ru(__uint_as_float(hi)), margin);
+            rb = __float_as_uint(__fmul_ru(e, e));
+        } else {
+            rb = hi;
+        }
+    }
+};
+
 // key strictly below (r2, idx 0): accepts exactly d2 < r2
 __device__ __forceinline__ unsigned long long init_key(float r2) {
     return ((unsigned long long)__float_as_uint(r2) << 32) - 1ull;
@@ -378,6 +405,56 @@ __device__ __forceinline__ void scan_tile(const float4 *tile, WarpSearch &w, uns
         const unsigned m2 = __reduce_min_sync(CPHB_FULL, db == m1 ? pidx : 0xffffffffu);
         const unsigned long long key = ((unsigned long long)m1 << 32) | m2;
         if (lane_id() == t && key < w.best) w.best = key;
+    }
+}
+
+__device__ __forceinline__ void scan_tile(const float4 *tile, WarpSearchC &w, unsigned need) {
+    if (__popc(need) > w.tmax) {
+        unsigned long long best = w.best;
+        unsigned second = w.second;
+#pragma unroll
+        for (int j = 0; j < CPHB_LEAF; ++j) {
+            const float4 p = tile[j];
+            const unsigned db = __float_as_uint(dist2(w.qx, w.qy, w.qz, p.x, p.y, p.z));
+            const unsigned long long key = ((unsigned long long)db << 32) | __float_as_uint(p.w);
+            const bool better = key < best;
+            // the loser of (candidate, current best) is a non-best evaluated point; the warm-start point met
+            // again in its own leaf (key == best) is not
+            const unsigned loser = better ? (unsigned)(best >> 32) : (key == best ? 0x7f800000u : db);
+            second = min(second, loser);
+            best = better ? key : best;
+        }
+        w.best = best;
+        w.second = second;
+        w.refresh();
+        return;
+    }
+    const float4 p = tile[lane_id()];
+    const unsigned pidx = __float_as_uint(p.w);
+    while (need) {
+        const int t = __ffs(need) - 1;
+        need &= need - 1;
+        const float qx = __shfl_sync(CPHB_FULL, w.qx, t), qy = __shfl_sync(CPHB_FULL, w.qy, t),
+                    qz = __shfl_sync(CPHB_FULL, w.qz, t);
+        const unsigned long long tb = __shfl_sync(CPHB_FULL, w.best, t);  // the owner's current best
+        const unsigned db = __float_as_uint(dist2(qx, qy, qz, p.x, p.y, p.z));
+        const unsigned m1 = __reduce_min_sync(CPHB_FULL, db);
+        const unsigned m2 = __reduce_min_sync(CPHB_FULL, db == m1 ? pidx : 0xffffffffu);
+        const unsigned long long key = ((unsigned long long)m1 << 32) | m2;
+        // smallest d2 among this leaf's candidates that are neither the leaf's winner nor the owner's best point
+        const unsigned long long mine = ((unsigned long long)db << 32) | pidx;
+        const unsigned s2 = __reduce_min_sync(CPHB_FULL, (mine == key || mine == tb) ? 0x7f800000u : db);
+        if (lane_id() == t) {
+            unsigned second = min(w.second, s2);
+            if (key < w.best) {
+                second = min(second, (unsigned)(w.best >> 32));
+                w.best = key;
+            } else if (key != w.best) {
+                second = min(second, m1);
+            }
+            w.second = second;
+            w.refresh();
+        }
     }
 }
 

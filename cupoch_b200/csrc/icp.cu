@@ -58,7 +58,14 @@ struct IcpArgs {
     IcpState *st;
     double *partials;     // [reduce grid][32]
     double *tile_sums;    // [n_pad/32][32]
-    int *prev;            // [n_pad] last iteration's match per Hilbert position (warm start) or null
+    int2 *prev;           // [n_pad] per Hilbert position: .x last iteration's match (-1 none), .y float bits of the
+                          // certificate slack (lower bound on the distance to every OTHER target point); or null
+    float cert_gain;      // margin = cert_gain * displacement (0 disables the certificates)
+    float cert_cap;       // matched lanes: margins above cert_cap * (point spacing in the match's leaf) are not worth
+                          // the wider search (-> plain search)
+    float cert_cap_r;     // unmatched lanes: same, as a distance (a fraction of max_correspondence_distance)
+    float r_up;           // max_correspondence_distance rounded up (certified 'still unmatched' test)
+    unsigned *dbg;        // [2][64] certified lanes / skipped tiles per launch (CPHB_DEBUG_CERT) or null
     int32_t *corr_index;  // [n_src] matched target index per ORIGINAL source index, or null
     unsigned long long n_total;
     unsigned n_src, n_pad;
@@ -639,7 +646,7 @@ __global__ void __launch_bounds__(ICP_SEARCH_WARPS * 32) icp_iteration_kernel(co
     const bool apply = a.step_mode ? true : (!materialize && *(volatile int *)&st->apply_u != 0);
     const int warp = threadIdx.x >> 5, lane = lane_id();
 
-    WarpSearch w;
+    WarpSearchC w;
     warp_search_setup(w, s_tile[warp], s_bar[warp]);
     w.tmax = a.tmax;
     float U[12];
@@ -648,6 +655,7 @@ __global__ void __launch_bounds__(ICP_SEARCH_WARPS * 32) icp_iteration_kernel(co
     const unsigned n_tiles = a.n_pad / 32;
     const unsigned long long init = (a.r2 > 0.f) ? init_key(a.r2) : 0ull;
     const bool write_corr = a.corr_index && (materialize || a.step_mode || a.launch_idx == a.max_iter);
+    const bool use_cert = a.prev && !a.step_mode && a.cert_gain > 0.f;
     double *rows = s_rows[warp];
     const unsigned char(*pair)[2] = (KIND == CPHB_EST_POINT_TO_POINT) ? c_pair_p2p : c_pair_jtj;
     const int ca = pair[lane][0], cb = pair[lane][1];
@@ -665,7 +673,8 @@ __global__ void __launch_bounds__(ICP_SEARCH_WARPS * 32) icp_iteration_kernel(co
         const unsigned i = tile * 32 + lane;  // position in Hilbert order (< n_pad)
         float4 s = a.src[i];
         const unsigned orig = __float_as_uint(s.w);
-        w.valid = i < a.n_src;
+        const bool in_range = i < a.n_src;
+        const float ox = s.x, oy = s.y, oz = s.z;  // position the certificate slack refers to
 
         // ---- PointCloud::Transform(update) on the working copy (pointcloud.cu:293-299) ----
         float sn[3] = {0.f, 0.f, 0.f};
@@ -719,29 +728,78 @@ __global__ void __launch_bounds__(ICP_SEARCH_WARPS * 32) icp_iteration_kernel(co
         }
 
         // ---- SearchRadius(.., max_nn = 1) (registration.cu:47) ---------------------------
+        // Certificates: prev[i].y is a lower bound (rounded down) on the distance from this point's position at
+        // the time it was last searched (minus the displacements since) to every target point other than its
+        // match.  If, after this iteration's displacement, the old match is still strictly closer than that
+        // bound, no other point can have a smaller (d2, index) key: the search would return the same match, so
+        // the lane skips it.  All roundings go against the certificate (slack down, distances up, 1e-5 relative
+        // guard against the <= 3e-7 relative error of the float d2 arithmetic the keys are made of).
         w.qx = s.x; w.qy = s.y; w.qz = s.z;
         w.best = init;
-        if (a.prev && w.valid) {
-            // warm start: last iteration's match is a candidate like any other (same key
-            // arithmetic), so the result is unchanged; it only tightens the bounds early
-            const int pj = a.prev[i];
+        w.second = 0x7f800000u;
+        w.margin = 0.f;
+        bool cert = false;
+        float slk = 0.f;
+        if (a.prev && in_range) {
+            const int2 pv = a.prev[i];
+            const int pj = pv.x;
+            float disp = 0.f;
+            if (use_cert) {
+                disp = __fmul_ru(__fsqrt_ru(dist2(s.x, s.y, s.z, ox, oy, oz)), 1.00001f);
+                slk = __fsub_rd(__int_as_float(pv.y), disp);  // NaN (never searched) stays NaN: no certificate
+                w.margin = __fmul_ru(a.cert_gain, disp);
+            }
             if (pj >= 0) {
+                // warm start: last iteration's match is a candidate like any other (same key
+                // arithmetic), so the result is unchanged; it only tightens the bounds early
                 const float d2p = dist2(s.x, s.y, s.z, a.tgt_xyz[3 * (size_t)pj], a.tgt_xyz[3 * (size_t)pj + 1],
                                         a.tgt_xyz[3 * (size_t)pj + 2]);
                 const unsigned long long kp = ((unsigned long long)__float_as_uint(d2p) << 32) | (unsigned)pj;
-                if (kp < init) w.best = kp;
+                if (kp < init) {
+                    w.best = kp;
+                    if (use_cert) cert = __fmul_ru(__fsqrt_ru(d2p), 1.00001f) < slk;
+                }
+                if (!cert && w.margin > 0.f) {
+                    // local scale: a leaf holds 32 neighbouring points, so sqrt(largest face area / 32) is about
+                    // the point spacing around the match (surface or volume sampling alike, within 2x)
+                    const Box bx = a.ix.boxes[0][a.ix.inv[pj] >> 5];
+                    const float ex = bx.hi.x - bx.lo.x, ey = bx.hi.y - bx.lo.y, ez = bx.hi.z - bx.lo.z;
+                    const float area = fmaxf(ex * ey, fmaxf(ex * ez, ey * ez));
+                    if (w.margin > a.cert_cap * sqrtf(area * (1.f / 32.f))) w.margin = 0.f;
+                }
+            } else if (use_cert) {
+                cert = slk > a.r_up;  // every target point is still outside the radius
+                if (w.margin > a.cert_cap_r) w.margin = 0.f;
+            }
+            if (cert) w.margin = 0.f;
+        }
+        w.valid = in_range && !cert;
+        w.refresh();
+        warp_update_bound(w);
+        w.warm = __all_sync(CPHB_FULL, !w.valid || w.best < init);  // every searching lane starts from a real candidate
+        if (__any_sync(CPHB_FULL, w.valid)) {
+            warp_query_box(w);
+            warp_nn_search<TOP>(a.ix, w);
+        }
+        if (a.dbg) {
+            const unsigned nc = __popc(__ballot_sync(CPHB_FULL, cert));
+            const bool searched = __any_sync(CPHB_FULL, w.valid);
+            if (lane == 0) {
+                atomicAdd(&a.dbg[min(a.launch_idx, 63)], nc);
+                if (!searched) atomicAdd(&a.dbg[64 + min(a.launch_idx, 63)], 1u);
             }
         }
-        warp_update_bound(w);
-        w.warm = (w.bound < (unsigned)(init >> 32));  // every valid lane starts from a real candidate
-        if (!w.valid) w.best = init;
-        warp_query_box(w);
-        if (__any_sync(CPHB_FULL, w.valid)) warp_nn_search<TOP>(a.ix, w);
-        const bool found = w.valid && (w.best != init);
+        const bool found = in_range && (w.best != init);
         const unsigned j = (unsigned)(w.best & 0xffffffffull);
         const float d2 = __uint_as_float((unsigned)(w.best >> 32));
-        if (a.prev && !a.step_mode) a.prev[i] = found ? (int)j : -1;
-        if (write_corr && w.valid) a.corr_index[orig] = found ? (int32_t)j : -1;
+        if (a.prev && !a.step_mode) {
+            // searched lanes: everything not evaluated lies outside the final relaxed bound, everything evaluated
+            // except the winner is at least `second` away
+            const float l2 = __uint_as_float(min(w.second, w.rb));
+            const float fresh = __fmul_rd(__fsqrt_rd(l2), 0.99999f);
+            a.prev[i] = make_int2(found ? (int)j : -1, __float_as_int(cert ? slk : fresh));
+        }
+        if (write_corr && in_range) a.corr_index[orig] = found ? (int32_t)j : -1;
         if (materialize) continue;  // fitness / rmse / T of this pose are already in the state
 
         // ---- rows: J (6), r; staged as doubles, one row of 9 per lane ---------------------
@@ -1050,22 +1108,22 @@ __global__ void __launch_bounds__(256) gather_source_kernel(const float *__restr
 // of straddling a dozen.  Pure permutation of the working arrays (w / prev travel with the point): the
 // result set is unchanged, only the order in which exact products are added to the float64 sums.
 // ---------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) retile_key_kernel(const int *__restrict__ prev, const uint32_t *__restrict__ inv,
+__global__ void __launch_bounds__(256) retile_key_kernel(const int2 *__restrict__ prev, const uint32_t *__restrict__ inv,
                                                          unsigned n_src, unsigned n_pad, uint32_t *keys, uint32_t *vals) {
     unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n_pad) return;
     uint32_t k = 0xffffffffu;  // padding stays last
     if (i < n_src) {
-        const int pj = prev[i];
+        const int pj = prev[i].x;
         k = (pj >= 0) ? inv[pj] : 0xfffffffeu;  // unmatched points after the matched ones
     }
     keys[i] = k;
     vals[i] = i;
 }
 __global__ void __launch_bounds__(256) retile_gather_kernel(const uint32_t *__restrict__ order, unsigned n_pad,
-                                                            const float4 *__restrict__ xyz, const int *__restrict__ prev,
+                                                            const float4 *__restrict__ xyz, const int2 *__restrict__ prev,
                                                             const float4 *__restrict__ nrm, const float4 *__restrict__ col,
-                                                            const float4 *__restrict__ cov, float4 *o_xyz, int *o_prev,
+                                                            const float4 *__restrict__ cov, float4 *o_xyz, int2 *o_prev,
                                                             float4 *o_nrm, float4 *o_col, float4 *o_cov) {
     unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n_pad) return;
@@ -1210,7 +1268,7 @@ struct cphb_icp {
     float4 *work_xyz, *work_nrm, *work_cov;
     float4 *src_col;
     float4 *alt_xyz, *alt_nrm, *alt_cov, *alt_col, *cur_col;  // re-tiling ping-pong buffers
-    int *alt_prev;
+    int2 *alt_prev;
     uint32_t *rt_keys, *rt_keys2, *rt_vals, *rt_order;
     IcpState *st;
     IcpState *h_st;  // pinned
@@ -1221,7 +1279,8 @@ struct cphb_icp {
     unsigned *cmp_counts;
     unsigned *cmp_total;
     double *tile_sums;
-    int *prev;
+    int2 *prev;
+    unsigned *dbg = nullptr;  // CPHB_DEBUG_CERT statistics
     unsigned grid, reduce_grid;
     cudaStream_t stream;
 };
@@ -1338,8 +1397,8 @@ extern "C" int cphb_icp_create(const cphb_cloud *source, const cphb_cloud *targe
     size_t o_st = take(sizeof(IcpState));
     size_t o_part = take(sizeof(double) * 32 * icp->reduce_grid);
     size_t o_ts = take(sizeof(double) * n_pad);
-    size_t o_prev = take(sizeof(int) * n_pad);
-    size_t o_axyz = take(sizeof(float4) * n_pad), o_aprev = take(sizeof(int) * n_pad);
+    size_t o_prev = take(sizeof(int2) * n_pad);
+    size_t o_axyz = take(sizeof(float4) * n_pad), o_aprev = take(sizeof(int2) * n_pad);
     size_t o_anrm = want_nrm ? take(sizeof(float4) * n_pad) : 0, o_acov = want_cov ? take(sizeof(float4) * 3 * n_pad) : 0;
     size_t o_acol = want_col ? take(sizeof(float4) * n_pad) : 0, o_ccol = want_col ? take(sizeof(float4) * n_pad) : 0;
     size_t o_rt = take(sizeof(uint32_t) * 4 * n_pad);
@@ -1363,9 +1422,9 @@ extern "C" int cphb_icp_create(const cphb_cloud *source, const cphb_cloud *targe
     icp->st = (IcpState *)(b + o_st);
     icp->partials = (double *)(b + o_part);
     icp->tile_sums = (double *)(b + o_ts);
-    icp->prev = (int *)(b + o_prev);
+    icp->prev = (int2 *)(b + o_prev);
     icp->alt_xyz = (float4 *)(b + o_axyz);
-    icp->alt_prev = (int *)(b + o_aprev);
+    icp->alt_prev = (int2 *)(b + o_aprev);
     icp->alt_nrm = want_nrm ? (float4 *)(b + o_anrm) : nullptr;
     icp->alt_cov = want_cov ? (float4 *)(b + o_acov) : nullptr;
     icp->alt_col = want_col ? (float4 *)(b + o_acol) : nullptr;
@@ -1410,6 +1469,7 @@ extern "C" int cphb_icp_create(const cphb_cloud *source, const cphb_cloud *targe
 extern "C" void cphb_icp_destroy(cphb_icp *icp) {
     if (!icp) return;
     if (icp->arena) cudaFreeAsync(icp->arena, icp->stream);
+    if (icp->dbg) cudaFree(icp->dbg);
     if (icp->owns_host) {
         if (icp->h_st) cudaFreeHost(icp->h_st);
         if (icp->ev0) cudaEventDestroy(icp->ev0);
@@ -1452,6 +1512,13 @@ static void fill_args(const cphb_icp *icp, IcpArgs &a) {
     a.sg = (float)sqrt((double)lg);
     float lp = (float)(1.0 - (double)lg);
     a.sp = (float)sqrt((double)lp);
+    a.cert_gain = 8.f;
+    a.cert_cap = 1.f;
+    if (const char *e = getenv("CPHB_CERT_GAIN")) a.cert_gain = (float)atof(e);  // tuning hooks; 0 = no certificates
+    if (const char *e = getenv("CPHB_CERT_CAP")) a.cert_cap = (float)atof(e);
+    a.cert_cap_r = 0.25f * (r > 0.f ? r : 0.f);
+    a.r_up = (float)(sqrt((double)a.r2) * 1.00002);
+    a.dbg = icp->dbg;
     a.tmax = CPHB_TRANSPOSE_MAX;
     if (const char *e = getenv("CPHB_TRANSPOSE_MAX")) {  // tuning hook
         int v = atoi(e);
@@ -1460,7 +1527,7 @@ static void fill_args(const cphb_icp *icp, IcpArgs &a) {
 }
 
 static int reset_working_copy(cphb_icp *icp, cudaStream_t s) {
-    CPHB_CUDA(cudaMemsetAsync(icp->prev, 0xff, sizeof(int) * icp->n_pad, s));  // no warm start at launch 0
+    CPHB_CUDA(cudaMemsetAsync(icp->prev, 0xff, sizeof(int2) * icp->n_pad, s));  // no warm start at launch 0
     CPHB_CUDA(cudaMemcpyAsync(icp->work_xyz, icp->pristine_xyz, sizeof(float4) * icp->n_pad, cudaMemcpyDeviceToDevice, s));
     if (icp->work_nrm)
         CPHB_CUDA(cudaMemcpyAsync(icp->work_nrm, icp->pristine_nrm, sizeof(float4) * icp->n_pad, cudaMemcpyDeviceToDevice, s));
@@ -1489,7 +1556,7 @@ static int retile(cphb_icp *icp, IcpArgs &a, cudaStream_t s) {
     int rc = cphb_sort_pairs_u32(icp->rt_keys, icp->rt_keys2, icp->rt_vals, icp->rt_order, n_pad, 32, s);
     if (rc) return rc;
     float4 *o_xyz = (a.src == icp->work_xyz) ? icp->alt_xyz : icp->work_xyz;
-    int *o_prev = (a.prev == icp->prev) ? icp->alt_prev : icp->prev;
+    int2 *o_prev = (a.prev == icp->prev) ? icp->alt_prev : icp->prev;
     float4 *o_nrm = a.src_nrm ? ((a.src_nrm == icp->work_nrm) ? icp->alt_nrm : icp->work_nrm) : nullptr;
     float4 *o_cov = a.src_cov ? ((a.src_cov == icp->work_cov) ? icp->alt_cov : icp->work_cov) : nullptr;
     float4 *o_col = a.src_col ? ((a.src_col == icp->alt_col) ? icp->cur_col : icp->alt_col) : nullptr;
@@ -1519,6 +1586,11 @@ extern "C" int cphb_icp_run(cphb_icp *icp, const float h_init[16], cphb_comm *co
     memcpy(h->U, h_init, 64);
     h->apply_u = is_identity4(h_init) ? 0 : 1;
     CPHB_CUDA(cudaMemcpyAsync(icp->st, h, sizeof(IcpState), cudaMemcpyHostToDevice, s));
+    static const bool dbg_cert = getenv("CPHB_DEBUG_CERT") != nullptr;
+    if (dbg_cert) {
+        if (!icp->dbg) CPHB_CUDA(cudaMalloc(&icp->dbg, sizeof(unsigned) * 128));
+        CPHB_CUDA(cudaMemsetAsync(icp->dbg, 0, sizeof(unsigned) * 128, s));
+    }
     IcpArgs a;
     fill_args(icp, a);
     a.corr_index = corr_out ? icp->corr_index : nullptr;
@@ -1595,6 +1667,13 @@ extern "C" int cphb_icp_run(cphb_icp *icp, const float h_init[16], cphb_comm *co
     h_result->loop_ms = 0.f;
     cudaEventElapsedTime(&h_result->loop_ms, icp->ev0, icp->ev1);
     h_result->loop_launches = loop_launches;
+    if (dbg_cert && icp->dbg) {
+        unsigned hd[128];
+        CPHB_CUDA(cudaMemcpy(hd, icp->dbg, sizeof(hd), cudaMemcpyDeviceToHost));
+        fprintf(stderr, "[cphb] certificates (n_src %u, tiles %u): launch: certified lanes / skipped tiles\n", icp->n_src, icp->n_pad / 32);
+        for (int it = 0; it <= a.max_iter && it < 64; ++it) fprintf(stderr, " %d:%u/%u", it, hd[it], hd[64 + it]);
+        fprintf(stderr, "\n");
+    }
     return CPHB_OK;
 }
 
