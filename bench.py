@@ -56,28 +56,38 @@ class ClockSampler(threading.Thread):
         super().__init__(daemon=True)
         self.index, self.samples, self.reasons, self.stop_flag = index, [], set(), False
         self.maxclk = None
+        self.recording = False          # samples are kept only while the timed region runs
+        self.ready = threading.Event()  # NVML initialised (nvmlInit takes a driver lock for tens of ms:
+                                        # it must not happen inside the timed region)
 
     def _run_nvml(self):
         import pynvml as nv
         nv.nvmlInit()
         h = nv.nvmlDeviceGetHandleByIndex(self.index)
         self.maxclk = float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM))
+        nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)
+        self.ready.set()
         while not self.stop_flag:
-            self.samples.append(float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)))
-            try:
-                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
-                for name, bit in self.REASONS.items():
-                    if r & bit:
-                        self.reasons.add(name)
-            except Exception:
-                pass
+            if self.recording:
+                self.samples.append(float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)))
+                try:
+                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                    for name, bit in self.REASONS.items():
+                        if r & bit:
+                            self.reasons.add(name)
+                except Exception:
+                    pass
             time.sleep(0.005)
 
     def _run_smi(self):
         q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        self.ready.set()
         while not self.stop_flag:
+            if not self.recording:
+                time.sleep(0.005)
+                continue
             try:
                 out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q,
                                       "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
@@ -231,12 +241,14 @@ def run_native(args, rank, world):
             step_log.append(round(ms.value, 3))
         return total_ms, last
 
-    for _ in range(args.warmup):
-        step_resident()
-    barrier()
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
+        sampler.ready.wait(timeout=20)
+    for _ in range(args.warmup):
+        step_resident()
+    barrier()
+    sampler.recording = True
     launches0 = L.cphb_launch_count()
     total_ms, res = timed(step_resident, args.steps)
     resident_steps_ms = list(step_log)

@@ -275,6 +275,13 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, unsigned parity) {
     return ok != 0;
 }
 
+// sqrt.approx.f32: one MUFU, max relative error 2^-23 (callers pad the result in the safe direction)
+__device__ __forceinline__ float sqrt_approx(float x) {
+    float r;
+    asm("sqrt.approx.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+
 // ---------------------------------------------------------------------------
 // Warp-cooperative exact nearest-neighbour traversal.
 //
@@ -317,21 +324,24 @@ struct WarpSearch : WarpSearchBase {
 //     that was never evaluated is farther than that (the bound only shrinks during a search, so a node culled
 //     against an earlier, larger bound is outside the final one too).  For a lane with no candidate yet best_d2
 //     is r^2, so the bound also covers points just outside the radius;
-//   * `second` is the smallest d2 among the evaluated candidates other than the best.
-// L2 = min(second, final relaxed bound) lets later ICP iterations prove, from the query's displacement alone, that
+//   * m1 <= m2 are the two smallest d2 among the candidates this lane evaluated in leaf scans.  A leaf is scanned
+//     at most once per search and the best point's own leaf always is (its box is inside every bound), so m1 is
+//     the best point's d2 and m2 bounds every other evaluated point from below.
+// L2 = min(m2, final relaxed bound) lets later ICP iterations prove, from the query's displacement alone, that
 // the match cannot have changed (icp.cu) -- the search is then skipped for that lane.  The best key itself is
 // found exactly as by WarpSearch: a larger cull bound never hides a candidate.
 struct WarpSearchC : WarpSearchBase {
     unsigned long long best;
-    unsigned second;  // d2 bits of the second-best evaluated candidate (0x7f800000 = none)
+    unsigned m1, m2;  // d2 bits (0x7f800000 = none yet)
     unsigned rb;      // cached relaxed bound (d2 bits), >= best_d2
     float margin;     // distance units, >= 0
     __device__ __forceinline__ unsigned lane_bound() const { return rb; }
     __device__ __forceinline__ void refresh() {
         const unsigned hi = (unsigned)(best >> 32);
         if (margin > 0.f && hi != 0u) {
-            const float e = __fadd_ru(__fsqrt_ru(__uint_as_float(hi)), margin);
-            rb = __float_as_uint(__fmul_ru(e, e));
+            // approximate sqrt (rel. error 2^-23) padded upwards: only has to be >= the exact value
+            const float e = __fadd_ru(__fmul_ru(sqrt_approx(__uint_as_float(hi)), 1.000001f), margin);
+            rb = max(__float_as_uint(__fmul_ru(e, e)), hi);
         } else {
             rb = hi;
         }
@@ -411,21 +421,19 @@ __device__ __forceinline__ void scan_tile(const float4 *tile, WarpSearch &w, uns
 __device__ __forceinline__ void scan_tile(const float4 *tile, WarpSearchC &w, unsigned need) {
     if (__popc(need) > w.tmax) {
         unsigned long long best = w.best;
-        unsigned second = w.second;
+        unsigned m1 = w.m1, m2 = w.m2;
 #pragma unroll
         for (int j = 0; j < CPHB_LEAF; ++j) {
             const float4 p = tile[j];
             const unsigned db = __float_as_uint(dist2(w.qx, w.qy, w.qz, p.x, p.y, p.z));
             const unsigned long long key = ((unsigned long long)db << 32) | __float_as_uint(p.w);
-            const bool better = key < best;
-            // the loser of (candidate, current best) is a non-best evaluated point; the warm-start point met
-            // again in its own leaf (key == best) is not
-            const unsigned loser = better ? (unsigned)(best >> 32) : (key == best ? 0x7f800000u : db);
-            second = min(second, loser);
-            best = better ? key : best;
+            best = (key < best) ? key : best;
+            m2 = min(m2, max(db, m1));
+            m1 = min(m1, db);
         }
         w.best = best;
-        w.second = second;
+        w.m1 = m1;
+        w.m2 = m2;
         w.refresh();
         return;
     }
@@ -436,23 +444,15 @@ __device__ __forceinline__ void scan_tile(const float4 *tile, WarpSearchC &w, un
         need &= need - 1;
         const float qx = __shfl_sync(CPHB_FULL, w.qx, t), qy = __shfl_sync(CPHB_FULL, w.qy, t),
                     qz = __shfl_sync(CPHB_FULL, w.qz, t);
-        const unsigned long long tb = __shfl_sync(CPHB_FULL, w.best, t);  // the owner's current best
         const unsigned db = __float_as_uint(dist2(qx, qy, qz, p.x, p.y, p.z));
-        const unsigned m1 = __reduce_min_sync(CPHB_FULL, db);
-        const unsigned m2 = __reduce_min_sync(CPHB_FULL, db == m1 ? pidx : 0xffffffffu);
-        const unsigned long long key = ((unsigned long long)m1 << 32) | m2;
-        // smallest d2 among this leaf's candidates that are neither the leaf's winner nor the owner's best point
-        const unsigned long long mine = ((unsigned long long)db << 32) | pidx;
-        const unsigned s2 = __reduce_min_sync(CPHB_FULL, (mine == key || mine == tb) ? 0x7f800000u : db);
+        const unsigned l1 = __reduce_min_sync(CPHB_FULL, db);
+        const unsigned li = __reduce_min_sync(CPHB_FULL, db == l1 ? pidx : 0xffffffffu);
+        const unsigned l2 = __reduce_min_sync(CPHB_FULL, pidx == li ? 0x7f800000u : db);  // leaf's second smallest
         if (lane_id() == t) {
-            unsigned second = min(w.second, s2);
-            if (key < w.best) {
-                second = min(second, (unsigned)(w.best >> 32));
-                w.best = key;
-            } else if (key != w.best) {
-                second = min(second, m1);
-            }
-            w.second = second;
+            const unsigned long long key = ((unsigned long long)l1 << 32) | li;
+            if (key < w.best) w.best = key;
+            w.m2 = min(max(w.m1, l1), min(w.m2, l2));  // two smallest of {m1, m2, l1, l2}
+            w.m1 = min(w.m1, l1);
             w.refresh();
         }
     }

@@ -632,6 +632,23 @@ __device__ __forceinline__ void drop_nonfinite_rows(float (&J)[NROWS][6], float 
 // reproducible whatever the tile schedule was) and its last block runs the
 // solve / convergence logic.
 // ===========================================================================
+// pull the rows of target point j that a tile reads first into L1 (no register is tied up, nothing waits)
+__device__ __forceinline__ void prefetch_l1(const void *p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
+template <int KIND>
+__device__ __forceinline__ void prefetch_target(const IcpArgs &a, size_t j) {
+    prefetch_l1(a.tgt_xyz + 3 * j);
+    if ((KIND == CPHB_EST_POINT_TO_PLANE || KIND == CPHB_EST_SYMMETRIC || KIND == CPHB_EST_COLORED_ICP) && a.tgt_nrm)
+        prefetch_l1(a.tgt_nrm + 3 * j);
+    if (KIND == CPHB_EST_COLORED_ICP) {
+        if (a.tgt_col) prefetch_l1(a.tgt_col + 3 * j);
+        if (a.tgt_grad) prefetch_l1(a.tgt_grad + 3 * j);
+    }
+    if (KIND == CPHB_EST_GENERALIZED_ICP && a.tgt_cov) {
+        prefetch_l1(a.tgt_cov + 9 * j);
+        prefetch_l1(a.tgt_cov + 9 * j + 8);
+    }
+}
+
 #define ICP_SEARCH_WARPS 4
 template <int KIND, int TOP>
 __global__ void __launch_bounds__(ICP_SEARCH_WARPS * 32) icp_iteration_kernel(const __grid_constant__ IcpArgs a) {
@@ -662,16 +679,42 @@ __global__ void __launch_bounds__(ICP_SEARCH_WARPS * 32) icp_iteration_kernel(co
     const unsigned live = (KIND == CPHB_EST_POINT_TO_POINT) ? c_live_p2p : c_live_jtj;
     constexpr int NROWS = (KIND == CPHB_EST_COLORED_ICP) ? 2 : (KIND == CPHB_EST_GENERALIZED_ICP) ? 3 : 1;
 
-    // the claim of the NEXT tile (one L2 atomic round trip) is issued at the top of the current tile and only
-    // consumed at its end, so it never sits on the critical path
-    unsigned next_tile = 0;
-    if (lane == 0) next_tile = atomicAdd(&st->tile_counter, 1u);
-    while (true) {
-        const unsigned tile = __shfl_sync(CPHB_FULL, next_tile, 0);
-        if (tile >= n_tiles) break;
-        if (lane == 0) next_tile = atomicAdd(&st->tile_counter, 1u);
+    // Tile schedule.  Each warp starts on a static tile (its global warp id) and then claims RANGES of
+    // consecutive tiles from an atomic counter: one tile at a time while tiles need a search (cost varies 10x
+    // between tiles, fine-grained claims keep every warp busy), up to 8 at a time once its tiles are skipped by
+    // their certificates -- 31 k same-address atomics would otherwise serialise in one L2 slice (~1.5 ns each)
+    // and bound the launch at ~50 us.
+    // Software pipeline: the claim after next and the loads of the NEXT tile's point and certificate are issued
+    // at the top of the current tile, and the target rows the next tile reads first (its previous match) are
+    // pulled into L1 at the end of the current tile, so a certified tile never waits on a chain of L2 round trips.
+    const unsigned total_warps = gridDim.x * ICP_SEARCH_WARPS;
+    unsigned tile = blockIdx.x * ICP_SEARCH_WARPS + warp;
+    unsigned range_end = tile + 1;   // current range [tile, range_end)
+    unsigned pend = 0, pend_sz = 1;  // claim in flight (result in lane 0) and its size
+    unsigned csize = 1;              // size of the next claim
+    if (lane == 0) pend = atomicAdd(&st->tile_counter, 1u);
+    float4 s_pf = make_float4(0.f, 0.f, 0.f, 0.f);
+    int2 pv_pf = make_int2(-1, 0);
+    if (tile < n_tiles) {
+        s_pf = a.src[tile * 32 + lane];
+        if (a.prev) pv_pf = a.prev[tile * 32 + lane];
+    }
+    unsigned tn = 0;
+    for (; tile < n_tiles; tile = tn) {
+        float4 s = s_pf;
+        const int2 pv = pv_pf;
+        tn = tile + 1;
+        if (tn >= range_end) {  // last tile of the range: the next one comes from the claim in flight
+            tn = __shfl_sync(CPHB_FULL, pend, 0) + total_warps;
+            range_end = min(tn + pend_sz, n_tiles);
+            pend_sz = csize;
+            if (lane == 0) pend = atomicAdd(&st->tile_counter, csize);
+        }
+        if (tn < n_tiles) {
+            s_pf = a.src[tn * 32 + lane];
+            if (a.prev) pv_pf = a.prev[tn * 32 + lane];
+        }
         const unsigned i = tile * 32 + lane;  // position in Hilbert order (< n_pad)
-        float4 s = a.src[i];
         const unsigned orig = __float_as_uint(s.w);
         const bool in_range = i < a.n_src;
         const float ox = s.x, oy = s.y, oz = s.z;  // position the certificate slack refers to
@@ -736,16 +779,16 @@ __global__ void __launch_bounds__(ICP_SEARCH_WARPS * 32) icp_iteration_kernel(co
         // guard against the <= 3e-7 relative error of the float d2 arithmetic the keys are made of).
         w.qx = s.x; w.qy = s.y; w.qz = s.z;
         w.best = init;
-        w.second = 0x7f800000u;
+        w.m1 = 0x7f800000u;
+        w.m2 = 0x7f800000u;
         w.margin = 0.f;
         bool cert = false;
         float slk = 0.f;
         if (a.prev && in_range) {
-            const int2 pv = a.prev[i];
             const int pj = pv.x;
             float disp = 0.f;
             if (use_cert) {
-                disp = __fmul_ru(__fsqrt_ru(dist2(s.x, s.y, s.z, ox, oy, oz)), 1.00001f);
+                disp = __fmul_ru(sqrt_approx(dist2(s.x, s.y, s.z, ox, oy, oz)), 1.00001f);
                 slk = __fsub_rd(__int_as_float(pv.y), disp);  // NaN (never searched) stays NaN: no certificate
                 w.margin = __fmul_ru(a.cert_gain, disp);
             }
@@ -757,7 +800,7 @@ __global__ void __launch_bounds__(ICP_SEARCH_WARPS * 32) icp_iteration_kernel(co
                 const unsigned long long kp = ((unsigned long long)__float_as_uint(d2p) << 32) | (unsigned)pj;
                 if (kp < init) {
                     w.best = kp;
-                    if (use_cert) cert = __fmul_ru(__fsqrt_ru(d2p), 1.00001f) < slk;
+                    if (use_cert) cert = __fmul_ru(sqrt_approx(d2p), 1.00001f) < slk;
                 }
                 if (!cert && w.margin > 0.f) {
                     // local scale: a leaf holds 32 neighbouring points, so sqrt(largest face area / 32) is about
@@ -780,6 +823,9 @@ __global__ void __launch_bounds__(ICP_SEARCH_WARPS * 32) icp_iteration_kernel(co
         if (__any_sync(CPHB_FULL, w.valid)) {
             warp_query_box(w);
             warp_nn_search<TOP>(a.ix, w);
+            csize = 1;
+        } else {
+            csize = min(csize * 2, 8u);
         }
         if (a.dbg) {
             const unsigned nc = __popc(__ballot_sync(CPHB_FULL, cert));
@@ -794,9 +840,12 @@ __global__ void __launch_bounds__(ICP_SEARCH_WARPS * 32) icp_iteration_kernel(co
         const float d2 = __uint_as_float((unsigned)(w.best >> 32));
         if (a.prev && !a.step_mode) {
             // searched lanes: everything not evaluated lies outside the final relaxed bound, everything evaluated
-            // except the winner is at least `second` away
-            const float l2 = __uint_as_float(min(w.second, w.rb));
-            const float fresh = __fmul_rd(__fsqrt_rd(l2), 0.99999f);
+            // except the winner is at least sqrt(m2) away
+            // m1 is the winner's own d2 (its leaf is always scanned); if it is not -- no match, or a tie -- m1
+            // itself belongs to another point
+            const unsigned other = (found && w.m1 == (unsigned)(w.best >> 32)) ? w.m2 : w.m1;
+            const float l2 = __uint_as_float(min(other, w.rb));
+            const float fresh = __fmul_rd(sqrt_approx(l2), 0.99999f);
             a.prev[i] = make_int2(found ? (int)j : -1, __float_as_int(cert ? slk : fresh));
         }
         if (write_corr && in_range) a.corr_index[orig] = found ? (int32_t)j : -1;
@@ -834,6 +883,7 @@ __global__ void __launch_bounds__(ICP_SEARCH_WARPS * 32) icp_iteration_kernel(co
         }
         if (!((live >> lane) & 1u)) acc = 0.0;
         a.tile_sums[(size_t)tile * 32 + lane] = acc;
+        if (tn < n_tiles && pv_pf.x >= 0) prefetch_target<KIND>(a, (size_t)pv_pf.x);
     }
 }
 
@@ -1512,8 +1562,8 @@ static void fill_args(const cphb_icp *icp, IcpArgs &a) {
     a.sg = (float)sqrt((double)lg);
     float lp = (float)(1.0 - (double)lg);
     a.sp = (float)sqrt((double)lp);
-    a.cert_gain = 8.f;
-    a.cert_cap = 1.f;
+    a.cert_gain = 4.f;   // measured on config 2 (profiles/r1_cert_sweep.txt): 2..8 within 6 %
+    a.cert_cap = 0.5f;
     if (const char *e = getenv("CPHB_CERT_GAIN")) a.cert_gain = (float)atof(e);  // tuning hooks; 0 = no certificates
     if (const char *e = getenv("CPHB_CERT_CAP")) a.cert_cap = (float)atof(e);
     a.cert_cap_r = 0.25f * (r > 0.f ? r : 0.f);
