@@ -25,6 +25,7 @@
 #include <string.h>
 
 #include "cphb_internal.cuh"
+#include <vector>
 #include "cphb_eigen3.cuh"
 
 #define ICP_BLOCK 256
@@ -43,6 +44,8 @@ struct IcpState {
     int apply_u;
     unsigned ticket;
     unsigned tile_counter;
+    unsigned cert_tiles;  // tiles skipped by their certificates in the launch just finished
+    int static_sched;     // next search launch may use the static tile schedule (see icp_iteration_kernel)
     long long n_corr;
     unsigned pad_local;  // host-side staging only (count of locally written correspondence pairs)
     unsigned pad_;
@@ -66,6 +69,8 @@ struct IcpArgs {
     float cert_cap_r;     // unmatched lanes: same, as a distance (a fraction of max_correspondence_distance)
     float r_up;           // max_correspondence_distance rounded up (certified 'still unmatched' test)
     unsigned *dbg;        // [2][64] certified lanes / skipped tiles per launch (CPHB_DEBUG_CERT) or null
+    unsigned claim_max;   // largest range of tiles one claim may take (certified regime)
+    int static_sched;     // allow the atomics-free static schedule once >= 90 % of the tiles are skipped
     int32_t *corr_index;  // [n_src] matched target index per ORIGINAL source index, or null
     unsigned long long n_total;
     unsigned n_src, n_pad;
@@ -650,8 +655,11 @@ __device__ __forceinline__ void prefetch_target(const IcpArgs &a, size_t j) {
 }
 
 #define ICP_SEARCH_WARPS 4
+#ifndef ICP_MIN_BLOCKS
+#define ICP_MIN_BLOCKS 1  // resident blocks / SM the register allocation targets
+#endif
 template <int KIND, int TOP>
-__global__ void __launch_bounds__(ICP_SEARCH_WARPS * 32) icp_iteration_kernel(const __grid_constant__ IcpArgs a) {
+__global__ void __launch_bounds__(ICP_SEARCH_WARPS * 32, ICP_MIN_BLOCKS) icp_iteration_kernel(const __grid_constant__ IcpArgs a) {
     __shared__ __align__(16) float4 s_tile[ICP_SEARCH_WARPS][2 * CPHB_LEAF];
     __shared__ uint64_t s_bar[ICP_SEARCH_WARPS][2];
     __shared__ double s_rows[ICP_SEARCH_WARPS][32 * ROW_STRIDE];
@@ -688,11 +696,15 @@ __global__ void __launch_bounds__(ICP_SEARCH_WARPS * 32) icp_iteration_kernel(co
     // at the top of the current tile, and the target rows the next tile reads first (its previous match) are
     // pulled into L1 at the end of the current tile, so a certified tile never waits on a chain of L2 round trips.
     const unsigned total_warps = gridDim.x * ICP_SEARCH_WARPS;
+    // once (nearly) every tile is skipped the tiles cost the same, and a static round-robin schedule needs no
+    // atomics at all; tile_sums are indexed by tile, so the schedule never affects the result
+    const bool static_sched = a.static_sched && !a.step_mode && *(volatile int *)&st->static_sched != 0;
     unsigned tile = blockIdx.x * ICP_SEARCH_WARPS + warp;
     unsigned range_end = tile + 1;   // current range [tile, range_end)
     unsigned pend = 0, pend_sz = 1;  // claim in flight (result in lane 0) and its size
     unsigned csize = 1;              // size of the next claim
-    if (lane == 0) pend = atomicAdd(&st->tile_counter, 1u);
+    unsigned n_skipped = 0;
+    if (!static_sched && lane == 0) pend = atomicAdd(&st->tile_counter, 1u);
     float4 s_pf = make_float4(0.f, 0.f, 0.f, 0.f);
     int2 pv_pf = make_int2(-1, 0);
     if (tile < n_tiles) {
@@ -704,7 +716,9 @@ __global__ void __launch_bounds__(ICP_SEARCH_WARPS * 32) icp_iteration_kernel(co
         float4 s = s_pf;
         const int2 pv = pv_pf;
         tn = tile + 1;
-        if (tn >= range_end) {  // last tile of the range: the next one comes from the claim in flight
+        if (static_sched) {
+            tn = tile + total_warps;
+        } else if (tn >= range_end) {  // last tile of the range: the next one comes from the claim in flight
             tn = __shfl_sync(CPHB_FULL, pend, 0) + total_warps;
             range_end = min(tn + pend_sz, n_tiles);
             pend_sz = csize;
@@ -825,7 +839,8 @@ __global__ void __launch_bounds__(ICP_SEARCH_WARPS * 32) icp_iteration_kernel(co
             warp_nn_search<TOP>(a.ix, w);
             csize = 1;
         } else {
-            csize = min(csize * 2, 8u);
+            csize = min(csize * 2, a.claim_max);
+            ++n_skipped;
         }
         if (a.dbg) {
             const unsigned nc = __popc(__ballot_sync(CPHB_FULL, cert));
@@ -885,6 +900,7 @@ __global__ void __launch_bounds__(ICP_SEARCH_WARPS * 32) icp_iteration_kernel(co
         a.tile_sums[(size_t)tile * 32 + lane] = acc;
         if (tn < n_tiles && pv_pf.x >= 0) prefetch_target<KIND>(a, (size_t)pv_pf.x);
     }
+    if (a.static_sched && lane == 0 && n_skipped) atomicAdd(&st->cert_tiles, n_skipped);
 }
 
 // Fixed-order grid sum of the tile sums, then (last block) the host-side part of the loop.
@@ -899,7 +915,7 @@ __global__ void __launch_bounds__(ICP_REDUCE_BLOCK) icp_reduce_kernel(const __gr
     const int done = *(volatile int *)&st->done;
     if (done == 2) return;
     if (done == 1) {  // the search launch before this one only materialised correspondences
-        if (blockIdx.x == 0 && threadIdx.x == 0) { st->tile_counter = 0; st->done = 2; }
+        if (blockIdx.x == 0 && threadIdx.x == 0) { st->tile_counter = 0; st->cert_tiles = 0; st->static_sched = 0; st->done = 2; }
         return;
     }
     const unsigned n_tiles = a.n_pad / 32;
@@ -966,6 +982,8 @@ __global__ void __launch_bounds__(ICP_REDUCE_BLOCK) icp_reduce_kernel(const __gr
         if (threadIdx.x == 0) {
             st->ticket = 0;
             st->tile_counter = 0;
+            st->static_sched = ((unsigned long long)st->cert_tiles * 10ull >= (unsigned long long)n_tiles * 9ull) ? 1 : 0;
+            st->cert_tiles = 0;
         }
         if (!a.defer_finalize) icp_finalize<KIND>(a, st, s_solve);
         __threadfence();
@@ -1331,6 +1349,7 @@ struct cphb_icp {
     double *tile_sums;
     int2 *prev;
     unsigned *dbg = nullptr;  // CPHB_DEBUG_CERT statistics
+    cudaEvent_t *dbg_ev = nullptr;  // CPHB_DEBUG_EVENTS: 3 events per launch (before, between, after)
     unsigned grid, reduce_grid;
     cudaStream_t stream;
 };
@@ -1354,10 +1373,36 @@ static bool is_identity4(const float *T) {  // Eigen isIdentity(1e-5), registrat
     return true;
 }
 
+// resident blocks / SM of the iteration kernel instance a context will launch (register-limited)
+template <int KIND>
+static int iteration_occupancy(bool top3) {
+    int nb = 0;
+    cudaError_t e = top3 ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, icp_iteration_kernel<KIND, 3>, ICP_SEARCH_WARPS * 32, 0)
+                         : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, icp_iteration_kernel<KIND, 5>, ICP_SEARCH_WARPS * 32, 0);
+    if (e != cudaSuccess) { cudaGetLastError(); return 0; }
+    return nb;
+}
+static int iteration_occupancy_kind(int kind, bool top3) {
+    static int cache[8][2] = {};  // 0 = not queried yet
+    int &c = cache[kind & 7][top3 ? 0 : 1];
+    if (c == 0) {
+        switch (kind) {
+            case CPHB_EST_POINT_TO_POINT: c = iteration_occupancy<CPHB_EST_POINT_TO_POINT>(top3); break;
+            case CPHB_EST_POINT_TO_PLANE: c = iteration_occupancy<CPHB_EST_POINT_TO_PLANE>(top3); break;
+            case CPHB_EST_SYMMETRIC: c = iteration_occupancy<CPHB_EST_SYMMETRIC>(top3); break;
+            case CPHB_EST_COLORED_ICP: c = iteration_occupancy<CPHB_EST_COLORED_ICP>(top3); break;
+            case CPHB_EST_GENERALIZED_ICP: c = iteration_occupancy<CPHB_EST_GENERALIZED_ICP>(top3); break;
+        }
+        if (c <= 0) c = -1;
+    }
+    return c;
+}
+
 template <int KIND>
 static void launch_iteration(const cphb_icp *icp, const IcpArgs &a, cudaStream_t s) {
     if (icp->index->v.top <= 3) CPHB_LAUNCH((icp_iteration_kernel<KIND, 3>), icp->grid, ICP_SEARCH_WARPS * 32, 0, s, a);
     else CPHB_LAUNCH((icp_iteration_kernel<KIND, 5>), icp->grid, ICP_SEARCH_WARPS * 32, 0, s, a);
+    if (icp->dbg_ev) cudaEventRecord(icp->dbg_ev[3 * a.launch_idx + 1], s);
     CPHB_LAUNCH(icp_reduce_kernel<KIND>, icp->reduce_grid, ICP_REDUCE_BLOCK, 0, s, a);
 }
 static void launch_iteration_kind(const cphb_icp *icp, const IcpArgs &a, cudaStream_t s) {
@@ -1425,7 +1470,11 @@ extern "C" int cphb_icp_create(const cphb_cloud *source, const cphb_cloud *targe
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
         const unsigned n_tiles = n_pad / 32;
         unsigned want = (n_tiles + ICP_SEARCH_WARPS - 1) / ICP_SEARCH_WARPS;
-        unsigned per_sm = 9u;  // 9 blocks x 4 warps = 36 resident warps / SM at <= 56 registers
+        // every block must be resident: warps start on a static tile, and a block waiting for an SM slot
+        // would hold its four tiles back until the dynamic queue has drained
+        unsigned per_sm = 9u;
+        const int occ = iteration_occupancy_kind(params->estimation, icp->index->v.top <= 3);
+        if (occ > 0 && (unsigned)occ < per_sm) per_sm = (unsigned)occ;
         if (const char *e = getenv("CPHB_ICP_BLOCKS_PER_SM")) {  // tuning hook
             int v = atoi(e);
             if (v >= 1 && v <= 32) per_sm = (unsigned)v;
@@ -1569,6 +1618,10 @@ static void fill_args(const cphb_icp *icp, IcpArgs &a) {
     a.cert_cap_r = 0.25f * (r > 0.f ? r : 0.f);
     a.r_up = (float)(sqrt((double)a.r2) * 1.00002);
     a.dbg = icp->dbg;
+    a.claim_max = 8u;
+    if (const char *e = getenv("CPHB_CLAIM_MAX")) { int v = atoi(e); if (v >= 1 && v <= 1024) a.claim_max = (unsigned)v; }
+    a.static_sched = 0;
+    if (const char *e = getenv("CPHB_STATIC_SCHED")) a.static_sched = atoi(e) != 0;
     a.tmax = CPHB_TRANSPOSE_MAX;
     if (const char *e = getenv("CPHB_TRANSPOSE_MAX")) {  // tuning hook
         int v = atoi(e);
@@ -1681,16 +1734,27 @@ extern "C" int cphb_icp_run(cphb_icp *icp, const float h_init[16], cphb_comm *co
     // j < max_iter, launch j+1 re-runs that search only to materialise its correspondences;
     // launches after "done" exit at their first instruction.
     const unsigned long long launches0 = g_cphb_launches;
+    unsigned long long retile_mask = (1ull << 1) | (1ull << 4) | (1ull << 10);  // after these launches
+    if (const char *e = getenv("CPHB_RETILE_MASK")) retile_mask = strtoull(e, nullptr, 0);  // tuning hook
+    static const bool dbg_events = getenv("CPHB_DEBUG_EVENTS") != nullptr;
+    std::vector<cudaEvent_t> evs;
+    if (dbg_events) {
+        evs.resize(3 * (size_t)(a.max_iter + 1));
+        for (auto &e : evs) cudaEventCreate(&e);
+        icp->dbg_ev = evs.data();
+    }
     CPHB_CUDA(cudaEventRecord(icp->ev0, s));
     for (int it = 0; it <= a.max_iter; ++it) {
         a.launch_idx = it;
+        if (dbg_events) cudaEventRecord(evs[3 * it], s);
         launch_iteration_kind(icp, a, s);
+        if (dbg_events) cudaEventRecord(evs[3 * it + 2], s);
         if (nccl_comm) {
             rc = cphb_nccl_allreduce_f64(nccl_comm, icp->st->local, icp->st->total, 32, s);
             if (rc) return rc;
             launch_finalize_kind(icp, a, s);
         }
-        if (!(icp->prm.flags & CPHB_ICP_NO_RETILE) && it < a.max_iter && (it == 1 || it == 4 || it == 10) && icp->n_src >= 4096) {
+        if (!(icp->prm.flags & CPHB_ICP_NO_RETILE) && it < a.max_iter && it < 64 && ((retile_mask >> it) & 1ull) && icp->n_src >= 4096) {
             rc = retile(icp, a, s);
             if (rc) return rc;
         }
@@ -1717,6 +1781,19 @@ extern "C" int cphb_icp_run(cphb_icp *icp, const float h_init[16], cphb_comm *co
     h_result->loop_ms = 0.f;
     cudaEventElapsedTime(&h_result->loop_ms, icp->ev0, icp->ev1);
     h_result->loop_launches = loop_launches;
+    if (dbg_events) {
+        fprintf(stderr, "[cphb] per launch us (search kernel / reduce+solve / until next launch):\n");
+        for (int it = 0; it <= a.max_iter; ++it) {
+            float t_it = 0.f, t_red = 0.f, t_gap = 0.f;
+            cudaEventElapsedTime(&t_it, evs[3 * it], evs[3 * it + 1]);
+            cudaEventElapsedTime(&t_red, evs[3 * it + 1], evs[3 * it + 2]);
+            if (it < a.max_iter) cudaEventElapsedTime(&t_gap, evs[3 * it + 2], evs[3 * it + 3]);
+            fprintf(stderr, " %d:%.1f/%.1f/%.1f", it, 1e3f * t_it, 1e3f * t_red, 1e3f * t_gap);
+        }
+        fprintf(stderr, "\n");
+        for (auto &e : evs) cudaEventDestroy(e);
+        icp->dbg_ev = nullptr;
+    }
     if (dbg_cert && icp->dbg) {
         unsigned hd[128];
         CPHB_CUDA(cudaMemcpy(hd, icp->dbg, sizeof(hd), cudaMemcpyDeviceToHost));
