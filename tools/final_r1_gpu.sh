@@ -10,8 +10,8 @@ run() { echo "== $*"; env "$@" timeout 60 python bench.py --steps 4 --warmup 3 -
 run CPHB_NOOP=1
 run CPHB_STATIC_SCHED=1
 run CPHB_RETILE_MASK=0x2
-run CPHB_RETILE_MASK=0x12
-run CPHB_STATIC_SCHED=1 CPHB_RETILE_MASK=0x12
+run CPHB_RETILE_MASK=0x412
+run CPHB_STATIC_SCHED=1 CPHB_RETILE_MASK=0x2
 run CPHB_CLAIM_MAX=1
 } > gpurun_out/final_sweep.txt 2>&1
 cat gpurun_out/final_sweep.txt
