@@ -658,6 +658,28 @@ __device__ __forceinline__ void prefetch_target(const IcpArgs &a, size_t j) {
 #ifndef ICP_MIN_BLOCKS
 #define ICP_MIN_BLOCKS 1  // resident blocks / SM the register allocation targets
 #endif
+// Build-time experiments (tools/build_variant.sh; the default build has both off):
+//   ICP_LOWREG  keep the update transform in shared memory and prefetch the next tile with L1 hints instead of
+//               registers, so that ICP_MIN_BLOCKS=9 (56 registers, 36 warps / SM) fits without spilling
+//   CPHB_PDL    programmatic dependent launch: the kernels of the loop are launched with stream serialisation
+//               relaxed, run their prologue while the previous kernel drains and wait (griddepcontrol.wait)
+//               before they touch anything it wrote
+#ifndef ICP_LOWREG
+#define ICP_LOWREG 0
+#endif
+#ifndef CPHB_PDL
+#define CPHB_PDL 0
+#endif
+__device__ __forceinline__ void grid_dependency_wait() {
+#if CPHB_PDL
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+#endif
+}
+__device__ __forceinline__ void grid_dependency_trigger() {
+#if CPHB_PDL
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+#endif
+}
 template <int KIND, int TOP>
 __global__ void __launch_bounds__(ICP_SEARCH_WARPS * 32, ICP_MIN_BLOCKS) icp_iteration_kernel(const __grid_constant__ IcpArgs a) {
     __shared__ __align__(16) float4 s_tile[ICP_SEARCH_WARPS][2 * CPHB_LEAF];
@@ -665,18 +687,40 @@ __global__ void __launch_bounds__(ICP_SEARCH_WARPS * 32, ICP_MIN_BLOCKS) icp_ite
     __shared__ double s_rows[ICP_SEARCH_WARPS][32 * ROW_STRIDE];
 
     IcpState *st = a.st;
+    const int warp = threadIdx.x >> 5, lane = lane_id();
+#if CPHB_PDL
+    // everything up to the wait may overlap the tail of the reduce kernel that precedes this launch: it must
+    // not read the state that kernel writes (done, apply_u, U, static_sched, tile_counter).  The working
+    // arrays were last written by the search launch before it, which had completed before the reduce kernel
+    // released its dependents.
+    grid_dependency_trigger();
+    {
+        const unsigned t0 = blockIdx.x * ICP_SEARCH_WARPS + warp;
+        if (t0 < a.n_pad / 32) {
+            prefetch_l1(&a.src[t0 * 32 + lane]);
+            if (a.prev) prefetch_l1(&a.prev[t0 * 32 + lane]);
+        }
+    }
+    grid_dependency_wait();
+#endif
     const int done = *(volatile int *)&st->done;
     if (done == 2) return;
     const bool materialize = (done == 1);
     const bool apply = a.step_mode ? true : (!materialize && *(volatile int *)&st->apply_u != 0);
-    const int warp = threadIdx.x >> 5, lane = lane_id();
 
     WarpSearchC w;
     warp_search_setup(w, s_tile[warp], s_bar[warp]);
     w.tmax = a.tmax;
+#if ICP_LOWREG
+    __shared__ float s_U[12];
+    if (threadIdx.x < 12) s_U[threadIdx.x] = apply ? st->U[threadIdx.x] : ((threadIdx.x % 5 == 0) ? 1.f : 0.f);
+    __syncthreads();  // the only block-wide barrier: before any warp has started its tile loop
+    const float *U = s_U;
+#else
     float U[12];
 #pragma unroll
     for (int k = 0; k < 12; ++k) U[k] = apply ? st->U[k] : ((k % 5 == 0) ? 1.f : 0.f);
+#endif
     const unsigned n_tiles = a.n_pad / 32;
     const unsigned long long init = (a.r2 > 0.f) ? init_key(a.r2) : 0ull;
     const bool write_corr = a.corr_index && (materialize || a.step_mode || a.launch_idx == a.max_iter);
@@ -705,16 +749,23 @@ __global__ void __launch_bounds__(ICP_SEARCH_WARPS * 32, ICP_MIN_BLOCKS) icp_ite
     unsigned csize = 1;              // size of the next claim
     unsigned n_skipped = 0;
     if (!static_sched && lane == 0) pend = atomicAdd(&st->tile_counter, 1u);
+#if !ICP_LOWREG
     float4 s_pf = make_float4(0.f, 0.f, 0.f, 0.f);
     int2 pv_pf = make_int2(-1, 0);
     if (tile < n_tiles) {
         s_pf = a.src[tile * 32 + lane];
         if (a.prev) pv_pf = a.prev[tile * 32 + lane];
     }
+#endif
     unsigned tn = 0;
     for (; tile < n_tiles; tile = tn) {
+#if ICP_LOWREG
+        float4 s = a.src[tile * 32 + lane];  // L1 hit: prefetched while the previous tile was processed
+        const int2 pv = a.prev ? a.prev[tile * 32 + lane] : make_int2(-1, 0);
+#else
         float4 s = s_pf;
         const int2 pv = pv_pf;
+#endif
         tn = tile + 1;
         if (static_sched) {
             tn = tile + total_warps;
@@ -725,8 +776,13 @@ __global__ void __launch_bounds__(ICP_SEARCH_WARPS * 32, ICP_MIN_BLOCKS) icp_ite
             if (lane == 0) pend = atomicAdd(&st->tile_counter, csize);
         }
         if (tn < n_tiles) {
+#if ICP_LOWREG
+            if (lane < 4) prefetch_l1(reinterpret_cast<const char *>(a.src + tn * 32) + 128 * lane);
+            else if (lane < 6 && a.prev) prefetch_l1(reinterpret_cast<const char *>(a.prev + tn * 32) + 128 * (lane - 4));
+#else
             s_pf = a.src[tn * 32 + lane];
             if (a.prev) pv_pf = a.prev[tn * 32 + lane];
+#endif
         }
         const unsigned i = tile * 32 + lane;  // position in Hilbert order (< n_pad)
         const unsigned orig = __float_as_uint(s.w);
@@ -898,7 +954,14 @@ __global__ void __launch_bounds__(ICP_SEARCH_WARPS * 32, ICP_MIN_BLOCKS) icp_ite
         }
         if (!((live >> lane) & 1u)) acc = 0.0;
         a.tile_sums[(size_t)tile * 32 + lane] = acc;
+#if ICP_LOWREG
+        if (tn < n_tiles && a.prev) {
+            const int pn = a.prev[tn * 32 + lane].x;  // L1 hit (hinted at the top of this tile)
+            if (pn >= 0) prefetch_target<KIND>(a, (size_t)pn);
+        }
+#else
         if (tn < n_tiles && pv_pf.x >= 0) prefetch_target<KIND>(a, (size_t)pv_pf.x);
+#endif
     }
     if (a.static_sched && lane == 0 && n_skipped) atomicAdd(&st->cert_tiles, n_skipped);
 }
@@ -912,6 +975,8 @@ __global__ void __launch_bounds__(ICP_REDUCE_BLOCK) icp_reduce_kernel(const __gr
     __shared__ unsigned s_last;
     __shared__ SolveSmem s_solve;
     IcpState *st = a.st;
+    grid_dependency_wait();     // the search launch has completed: its tile sums and state are visible
+    grid_dependency_trigger();  // the next search launch may start its prologue while this kernel runs
     const int done = *(volatile int *)&st->done;
     if (done == 2) return;
     if (done == 1) {  // the search launch before this one only materialised correspondences
@@ -1398,8 +1463,38 @@ static int iteration_occupancy_kind(int kind, bool top3) {
     return c;
 }
 
+#if CPHB_PDL
+// launch with stream serialisation relaxed (programmatic dependent launch): the kernel may start while its
+// predecessor drains and synchronises on it with griddepcontrol.wait
+template <class K>
+static void launch_pdl(K kernel, unsigned grid, unsigned block, cudaStream_t s, const IcpArgs &a) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(block);
+    cfg.dynamicSmemBytes = 0;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, kernel, a);
+    ++g_cphb_launches;
+    if (e != cudaSuccess) cphb_set_error("PDL launch failed: %s", cudaGetErrorString(e));
+}
+#endif
+
 template <int KIND>
 static void launch_iteration(const cphb_icp *icp, const IcpArgs &a, cudaStream_t s) {
+#if CPHB_PDL
+    static const bool pdl = getenv("CPHB_NO_PDL") == nullptr;
+    if (pdl && !a.defer_finalize && !a.step_mode && !icp->dbg_ev) {
+        if (icp->index->v.top <= 3) launch_pdl(icp_iteration_kernel<KIND, 3>, icp->grid, ICP_SEARCH_WARPS * 32, s, a);
+        else launch_pdl(icp_iteration_kernel<KIND, 5>, icp->grid, ICP_SEARCH_WARPS * 32, s, a);
+        launch_pdl(icp_reduce_kernel<KIND>, icp->reduce_grid, ICP_REDUCE_BLOCK, s, a);
+        return;
+    }
+#endif
     if (icp->index->v.top <= 3) CPHB_LAUNCH((icp_iteration_kernel<KIND, 3>), icp->grid, ICP_SEARCH_WARPS * 32, 0, s, a);
     else CPHB_LAUNCH((icp_iteration_kernel<KIND, 5>), icp->grid, ICP_SEARCH_WARPS * 32, 0, s, a);
     if (icp->dbg_ev) cudaEventRecord(icp->dbg_ev[3 * a.launch_idx + 1], s);
