@@ -1242,13 +1242,14 @@ __global__ void __launch_bounds__(256) gather_source_kernel(const float *__restr
 // result set is unchanged, only the order in which exact products are added to the float64 sums.
 // ---------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) retile_key_kernel(const int2 *__restrict__ prev, const uint32_t *__restrict__ inv,
-                                                         unsigned n_src, unsigned n_pad, uint32_t *keys, uint32_t *vals) {
+                                                         unsigned n_src, unsigned n_pad, uint32_t n_tgt_pad, uint32_t *keys,
+                                                         uint32_t *vals) {
     unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n_pad) return;
-    uint32_t k = 0xffffffffu;  // padding stays last
+    uint32_t k = n_tgt_pad + 1u;  // padding stays last
     if (i < n_src) {
         const int pj = prev[i].x;
-        k = (pj >= 0) ? inv[pj] : 0xfffffffeu;  // unmatched points after the matched ones
+        k = (pj >= 0) ? inv[pj] : n_tgt_pad;  // unmatched points after the matched ones (target positions < n_tgt_pad)
     }
     keys[i] = k;
     vals[i] = i;
@@ -1748,10 +1749,15 @@ static int compact_correspondences(cphb_icp *icp, int32_t *corr_out, cudaStream_
 // permute the working arrays referenced by `a` into the alt buffers and swap
 static int retile(cphb_icp *icp, IcpArgs &a, cudaStream_t s) {
     const unsigned n_pad = icp->n_pad, grid = n_pad / 256;
-    CPHB_LAUNCH(retile_key_kernel, grid, 256, 0, s, a.prev, icp->index->v.inv, icp->n_src, n_pad, icp->rt_keys, icp->rt_vals);
+    const uint32_t n_tgt_pad = (uint32_t)icp->index->v.n_leaves * CPHB_LEAF;
+    CPHB_LAUNCH(retile_key_kernel, grid, 256, 0, s, a.prev, icp->index->v.inv, icp->n_src, n_pad, n_tgt_pad, icp->rt_keys,
+                icp->rt_vals);
     CPHB_CHECK_LAUNCH();
-    // keys are target positions or the sentinels 0xfffffffe / 0xffffffff: 32-bit radix sort, 4 onesweep passes
-    int rc = cphb_sort_pairs_u32(icp->rt_keys, icp->rt_keys2, icp->rt_vals, icp->rt_order, n_pad, 32, s);
+    // keys are target positions (< n_tgt_pad) or the two sentinels right above them: the stable radix sort only
+    // has to look at the bits that can differ (21 for 1 M points: 3 onesweep passes instead of 4)
+    int bits = 1;
+    while (bits < 32 && ((uint64_t)1 << bits) < (uint64_t)n_tgt_pad + 2u) ++bits;
+    int rc = cphb_sort_pairs_u32(icp->rt_keys, icp->rt_keys2, icp->rt_vals, icp->rt_order, n_pad, bits, s);
     if (rc) return rc;
     float4 *o_xyz = (a.src == icp->work_xyz) ? icp->alt_xyz : icp->work_xyz;
     int2 *o_prev = (a.prev == icp->prev) ? icp->alt_prev : icp->prev;
