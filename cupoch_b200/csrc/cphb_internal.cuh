@@ -335,6 +335,8 @@ struct WarpSearchC : WarpSearchBase {
     unsigned m1, m2;  // d2 bits (0x7f800000 = none yet)
     unsigned rb;      // cached relaxed bound (d2 bits), >= best_d2
     float margin;     // distance units, >= 0
+    bool track;       // warp-uniform: some searching lane has margin > 0.  Without a margin the relaxed bound IS
+                      // best_d2 and min(m2, bound) = best_d2 whatever m2 is: nothing to track, plain scan
     __device__ __forceinline__ unsigned lane_bound() const { return rb; }
     __device__ __forceinline__ void refresh() {
         const unsigned hi = (unsigned)(best >> 32);
@@ -419,6 +421,38 @@ __device__ __forceinline__ void scan_tile(const float4 *tile, WarpSearch &w, uns
 }
 
 __device__ __forceinline__ void scan_tile(const float4 *tile, WarpSearchC &w, unsigned need) {
+    if (!w.track) {  // exactly the WarpSearch scan; rb follows best_d2 (every margin in the warp is 0)
+        if (__popc(need) > w.tmax) {
+            unsigned long long best = w.best;
+#pragma unroll
+            for (int j = 0; j < CPHB_LEAF; ++j) {
+                const float4 p = tile[j];
+                const float d2 = dist2(w.qx, w.qy, w.qz, p.x, p.y, p.z);
+                const unsigned long long key = ((unsigned long long)__float_as_uint(d2) << 32) | __float_as_uint(p.w);
+                best = (key < best) ? key : best;
+            }
+            w.best = best;
+            w.rb = (unsigned)(best >> 32);
+            return;
+        }
+        const float4 p = tile[lane_id()];
+        const unsigned pidx = __float_as_uint(p.w);
+        while (need) {
+            const int t = __ffs(need) - 1;
+            need &= need - 1;
+            const float qx = __shfl_sync(CPHB_FULL, w.qx, t), qy = __shfl_sync(CPHB_FULL, w.qy, t),
+                        qz = __shfl_sync(CPHB_FULL, w.qz, t);
+            const unsigned db = __float_as_uint(dist2(qx, qy, qz, p.x, p.y, p.z));
+            const unsigned l1 = __reduce_min_sync(CPHB_FULL, db);
+            const unsigned li = __reduce_min_sync(CPHB_FULL, db == l1 ? pidx : 0xffffffffu);
+            const unsigned long long key = ((unsigned long long)l1 << 32) | li;
+            if (lane_id() == t && key < w.best) {
+                w.best = key;
+                w.rb = l1;
+            }
+        }
+        return;
+    }
     if (__popc(need) > w.tmax) {
         unsigned long long best = w.best;
         unsigned m1 = w.m1, m2 = w.m2;

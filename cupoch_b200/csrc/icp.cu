@@ -887,6 +887,7 @@ __global__ void __launch_bounds__(ICP_SEARCH_WARPS * 32, ICP_MIN_BLOCKS) icp_ite
             if (cert) w.margin = 0.f;
         }
         w.valid = in_range && !cert;
+        w.track = __any_sync(CPHB_FULL, w.valid && w.margin > 0.f);
         w.refresh();
         warp_update_bound(w);
         w.warm = __all_sync(CPHB_FULL, !w.valid || w.best < init);  // every searching lane starts from a real candidate
