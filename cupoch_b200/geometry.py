@@ -124,6 +124,76 @@ class PointCloud:
         out._points, out._normals, out._colors = cut(op), cut(on), cut(oc)
         return out
 
+    def select_by_index(self, indices, invert=False):
+        """PointCloud::SelectByIndex (down_sample.cu:110-127): rows named by `indices` (host or device int array),
+        in the order given; invert=True selects the complement in ascending order (sort + set_difference there,
+        a host-side mask here)."""
+        out = PointCloud()
+        n = len(self)
+        idx = indices.cpu() if hasattr(indices, "cpu") else np.asarray(indices)
+        idx = np.ascontiguousarray(idx, np.int64).reshape(-1)
+        if invert:
+            mask = np.ones(n, bool)
+            mask[idx[(idx >= 0) & (idx < n)]] = False
+            idx = np.flatnonzero(mask)
+        m = len(idx)
+        if m == 0 or n == 0:
+            return out
+        d_idx = DeviceArray.from_numpy(idx.astype(np.int32), np.int32)
+        hn, hc = self.has_normals(), self.has_colors()
+        op = DeviceArray((m, 3), np.float32)
+        on = DeviceArray((m, 3), np.float32) if hn else None
+        oc = DeviceArray((m, 3), np.float32) if hc else None
+        _lib.check(_lib.lib().cphb_select_by_index(
+            self._points.ptr, self._normals.ptr if hn else None, self._colors.ptr if hc else None, n, d_idx.ptr, m,
+            op.ptr, on.ptr if hn else None, oc.ptr if hc else None, None))
+        _lib.check(_lib.lib().cphb_stream_synchronize(None))
+        out._points, out._normals, out._colors = op, on, oc
+        return out
+
+    def _filtered(self, d_idx, m):
+        """(selected cloud, device index vector) from the first m entries of a device index buffer"""
+        kept = DeviceArray((m,), np.int32, ptr=d_idx.ptr, base=d_idx)
+        out = PointCloud()
+        n = len(self)
+        if m:
+            hn, hc = self.has_normals(), self.has_colors()
+            op = DeviceArray((m, 3), np.float32)
+            on = DeviceArray((m, 3), np.float32) if hn else None
+            oc = DeviceArray((m, 3), np.float32) if hc else None
+            _lib.check(_lib.lib().cphb_select_by_index(
+                self._points.ptr, self._normals.ptr if hn else None, self._colors.ptr if hc else None, n, kept.ptr, m,
+                op.ptr, on.ptr if hn else None, oc.ptr if hc else None, None))
+            _lib.check(_lib.lib().cphb_stream_synchronize(None))
+            out._points, out._normals, out._colors = op, on, oc
+        return out, kept
+
+    def remove_radius_outlier(self, nb_points, radius):
+        """PointCloud::RemoveRadiusOutliers (down_sample.cu:317-354; bound as remove_radius_outlier,
+        pointcloud.cpp:190-203) -> (filtered cloud, kept indices on the device, ascending)."""
+        n = len(self)
+        if n == 0:
+            return PointCloud(), DeviceArray((0,), np.int32)
+        d_idx = DeviceArray((n,), np.int32)
+        m = C.c_size_t(0)
+        _lib.check(_lib.lib().cphb_remove_radius_outliers(self._points.ptr, n, int(nb_points), float(radius), d_idx.ptr,
+                                                          C.byref(m), None))
+        return self._filtered(d_idx, m.value)
+
+    def remove_statistical_outlier(self, nb_neighbors, std_ratio):
+        """PointCloud::RemoveStatisticalOutliers (down_sample.cu:356-438; bound as remove_statistical_outlier,
+        pointcloud.cpp:204-217) -> (filtered cloud, kept indices on the device, ascending)."""
+        n = len(self)
+        if n == 0:
+            return PointCloud(), DeviceArray((0,), np.int32)
+        d_idx = DeviceArray((n,), np.int32)
+        m = C.c_size_t(0)
+        stats = (C.c_float * 3)()
+        _lib.check(_lib.lib().cphb_remove_statistical_outliers(self._points.ptr, n, int(nb_neighbors), float(std_ratio),
+                                                               d_idx.ptr, C.byref(m), stats, None))
+        self.last_outlier_stats = tuple(float(x) for x in stats)  # (cloud mean, std, threshold): diagnostics
+        return self._filtered(d_idx, m.value)
+
     def estimate_normals(self, search_param=None):
         """PointCloud::EstimateNormals (estimate_normals.cu:82-127)."""
         search_param = search_param or KDTreeSearchParamKNN()

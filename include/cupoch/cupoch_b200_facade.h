@@ -319,6 +319,48 @@ public:
         utility::check(cphb_estimate_normals(cfp(points_), points_.size(), knn, radius, max_nn, fp(normals_), nullptr));
         return true;
     }
+    /// PointCloud::SelectByIndex (down_sample.cu:110-127).  Index vectors are size_t like the reference's.
+    std::shared_ptr<PointCloud> SelectByIndex(const utility::device_vector<size_t> &indices, bool invert = false) const {
+        std::vector<size_t> h = indices.to_host();
+        const size_t n = points_.size();
+        std::vector<int32_t> sel;
+        if (invert) {  // sort + set_difference(0..n, indices) there: ascending complement
+            std::vector<char> drop(n, 0);
+            for (size_t i : h) if (i < n) drop[i] = 1;
+            for (size_t i = 0; i < n; ++i) if (!drop[i]) sel.push_back((int32_t)i);
+        } else {
+            sel.reserve(h.size());
+            for (size_t i : h) sel.push_back((int32_t)i);
+        }
+        utility::device_vector<int32_t> d;
+        d = sel;
+        return gather(d, sel.size());
+    }
+    /// PointCloud::RemoveRadiusOutliers (down_sample.cu:317-354) -> (filtered cloud, kept indices)
+    std::tuple<std::shared_ptr<PointCloud>, utility::device_vector<size_t>> RemoveRadiusOutliers(size_t nb_points,
+                                                                                                   float search_radius) const {
+        if (nb_points < 1 || search_radius <= 0)
+            utility::LogError("[RemoveRadiusOutliers] Illegal input parameters, number of points and radius must be positive");
+        utility::device_vector<int32_t> kept(points_.size());
+        size_t m = 0;
+        if (!points_.empty())
+            utility::check(cphb_remove_radius_outliers(cfp(points_), points_.size(), (int)nb_points, search_radius, kept.data(), &m,
+                                                       nullptr));
+        return finish_filter(kept, m);
+    }
+    /// PointCloud::RemoveStatisticalOutliers (down_sample.cu:356-438) -> (filtered cloud, kept indices)
+    std::tuple<std::shared_ptr<PointCloud>, utility::device_vector<size_t>> RemoveStatisticalOutliers(size_t nb_neighbors,
+                                                                                                        float std_ratio) const {
+        if (nb_neighbors < 1 || std_ratio <= 0)
+            utility::LogError("[RemoveStatisticalOutliers] Illegal input parameters, number of neighbors and standard deviation "
+                              "ratio must be positive");
+        utility::device_vector<int32_t> kept(points_.size());
+        size_t m = 0;
+        if (!points_.empty())
+            utility::check(cphb_remove_statistical_outliers(cfp(points_), points_.size(), (int)nb_neighbors, std_ratio, kept.data(),
+                                                            &m, nullptr, nullptr));
+        return finish_filter(kept, m);
+    }
     cphb_cloud view() const {
         cphb_cloud c;
         std::memset(&c, 0, sizeof(c));
@@ -340,6 +382,29 @@ public:
 private:
     template <class V> static float *fp(V &v) { return reinterpret_cast<float *>(v.data()); }
     template <class V> static const float *cfp(const V &v) { return reinterpret_cast<const float *>(v.data()); }
+    std::shared_ptr<PointCloud> gather(const utility::device_vector<int32_t> &idx, size_t m) const {
+        auto out = std::make_shared<PointCloud>();
+        if (m == 0 || points_.empty()) return out;
+        const bool hn = HasNormals(), hc = HasColors();
+        out->points_.resize(m);
+        if (hn) out->normals_.resize(m);
+        if (hc) out->colors_.resize(m);
+        utility::check(cphb_select_by_index(cfp(points_), hn ? cfp(normals_) : nullptr, hc ? cfp(colors_) : nullptr, points_.size(),
+                                            idx.data(), m, fp(out->points_), hn ? fp(out->normals_) : nullptr,
+                                            hc ? fp(out->colors_) : nullptr, nullptr));
+        utility::check(cphb_stream_synchronize(nullptr));
+        return out;
+    }
+    std::tuple<std::shared_ptr<PointCloud>, utility::device_vector<size_t>> finish_filter(utility::device_vector<int32_t> &kept,
+                                                                                            size_t m) const {
+        auto out = gather(kept, m);
+        kept.resize(m);
+        std::vector<int32_t> h32 = kept.to_host();
+        std::vector<size_t> h(h32.begin(), h32.end());  // the reference hands back device_vector<size_t>
+        utility::device_vector<size_t> idx;
+        idx = h;
+        return std::make_tuple(out, std::move(idx));
+    }
     Eigen::Vector3f bound(int which) const {
         float mn[3] = {0, 0, 0}, mx[3] = {0, 0, 0};
         if (!points_.empty()) utility::check(cphb_min_max_bound(cfp(points_), points_.size(), mn, mx, nullptr));

@@ -140,6 +140,25 @@ int cphb_covariances_from_normals(const float *normals, size_t n, float epsilon,
 int cphb_color_gradient(const float *points, const float *normals, const float *colors, size_t n,
                         float radius, int max_nn, float *out_gradient, void *stream);
 
+/* PointCloud::RemoveRadiusOutliers (down_sample.cu:317-354): search the cloud against itself with
+ * (radius, nb_points + 1) and keep the points all of whose slots are filled (more than nb_points neighbours
+ * inside the radius, the point itself included).  indices_out (device, n int32) receives the ascending indices
+ * of the kept points, *h_n_out their number (synchronises).  As in the reference a negative radius acts as
+ * |radius| and radius == 0 keeps nothing; nb_points + 1 > 100 (NUM_MAX_NN) is CPHB_ERR_INVALID. */
+int cphb_remove_radius_outliers(const float *points, size_t n, int nb_points, float radius,
+                                int32_t *indices_out, size_t *h_n_out, void *stream);
+/* PointCloud::RemoveStatisticalOutliers (down_sample.cu:356-438): per point the mean of the squared distances
+ * to its nb_neighbors nearest points (itself included), cloud mean and Bessel-corrected standard deviation of
+ * those means, keep 0 < mean_i < cloud mean + std_ratio * std.  h_stats (optional) = {cloud mean, std,
+ * threshold}.  Outputs as above. */
+int cphb_remove_statistical_outliers(const float *points, size_t n, int nb_neighbors, float std_ratio,
+                                     int32_t *indices_out, size_t *h_n_out, float h_stats[3], void *stream);
+/* PointCloud::SelectByIndex (down_sample.cu:40-127, invert = false): out row t = in row indices[t].
+ * normals / colors in and out may be NULL (together). */
+int cphb_select_by_index(const float *points, const float *normals, const float *colors, size_t n,
+                         const int32_t *indices, size_t n_indices, float *out_points, float *out_normals,
+                         float *out_colors, void *stream);
+
 /* ------------------------------------------------------------------------ *
  * registration  (registration.h:35-91, transformation_estimation.h:36-143,
  * generalized_icp.h, colored_icp.h)

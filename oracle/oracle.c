@@ -569,6 +569,87 @@ void orc_estimate_normals(const float *pts, int n, int knn, float radius,
     free(d2);
 }
 
+/* ---- outlier filters (kNN consumers) -------------------- */
+/* down_sample.cu:317-354 RemoveRadiusOutliers: SearchRadius(points, r, nb_points + 1) of the cloud against
+ * itself (every point finds itself, d2 = 0); a point is kept when MORE than nb_points of its nb_points + 1
+ * slots are valid, i.e. when all of them are.  Output: ascending indices.  The reference only logs
+ * nb_points < 1 / radius <= 0 and carries on: the search uses float(radius * radius) (kdtree_flann.inl:118), so a
+ * negative radius acts as |radius| and radius == 0 matches nothing (strict d2 < 0), i.e. an empty selection. */
+int orc_remove_radius_outliers(const float *pts, int n, int nb_points, float radius, int32_t *out_idx) {
+    if (n <= 0 || radius == 0.f || nb_points < 0) return 0;
+    radius = fabsf(radius);
+    const int k = nb_points + 1;
+    int32_t *idx = (int32_t *)malloc(sizeof(int32_t) * (size_t)n * k);
+    float *d2 = (float *)malloc(sizeof(float) * (size_t)n * k);
+    orc_kdtree *t = orc_kdtree_build(pts, n);
+    orc_kdtree_search(t, pts, n, k, radius, idx, d2);
+    int m = 0;
+    for (int i = 0; i < n; ++i) {
+        int cnt = 0;
+        for (int j = 0; j < k; ++j) cnt += idx[(size_t)i * k + j] >= 0;
+        if (cnt > nb_points) out_idx[m++] = i;
+    }
+    orc_kdtree_free(t);
+    free(idx);
+    free(d2);
+    return m;
+}
+
+/* down_sample.cu:356-438 RemoveStatisticalOutliers.  Per point: mean of the SQUARED distances (the kd-tree
+ * returns d2 and the reference averages them as they are) of its nb_neighbors nearest points, itself included;
+ * slots with inf / negative d2 do not count; no valid slot -> -1.  Cloud mean and Bessel-corrected standard
+ * deviation over the points with avg >= 0 (the deviation sum skips avg <= 0, :423-427); keep
+ * 0 < avg < mean + std_ratio * std.  Sums: thrust's float reductions have no specified order -- here (and in
+ * the kernels) every sum is accumulated in float64 and rounded to float once. */
+int orc_remove_statistical_outliers(const float *pts, int n, int nb_neighbors, float std_ratio, int32_t *out_idx,
+                                    float *out_avg /* [n] or NULL */, float out_stats[3] /* mean, std, thr */) {
+    if (out_stats) out_stats[0] = out_stats[1] = out_stats[2] = 0.f;
+    if (n <= 0 || nb_neighbors < 1) return 0;
+    const int k = nb_neighbors;
+    int32_t *idx = (int32_t *)malloc(sizeof(int32_t) * (size_t)n * k);
+    float *d2 = (float *)malloc(sizeof(float) * (size_t)n * k);
+    float *avg = (float *)malloc(sizeof(float) * (size_t)n);
+    orc_kdtree *t = orc_kdtree_build(pts, n);
+    orc_kdtree_search(t, pts, n, k, -1.0f, idx, d2);
+    double msum = 0.0;
+    long valid = 0;
+    for (int i = 0; i < n; ++i) {
+        double s = 0.0;
+        int c = 0;
+        for (int j = 0; j < k; ++j) {
+            const float d = d2[(size_t)i * k + j];
+            if (isinf(d) || d < 0.f) continue;
+            s += (double)d;
+            ++c;
+        }
+        avg[i] = (c > 0) ? (float)s / (float)c : -1.0f;
+        if (avg[i] >= 0.f) { msum += (double)avg[i]; ++valid; }
+    }
+    int m = 0;
+    if (valid > 0) {
+        float mean = (float)msum;
+        mean /= (float)valid;
+        double sq = 0.0;
+        for (int i = 0; i < n; ++i)
+            if (avg[i] > 0.f) {
+                const float e = avg[i] - mean;
+                sq += (double)(e * e);
+            }
+        const float sqf = (float)sq;
+        const float std_dev = sqrtf(sqf / (float)(valid - 1)); /* valid == 1: x/0 -> inf or nan, as the reference */
+        const float thr = mean + std_ratio * std_dev;
+        for (int i = 0; i < n; ++i)
+            if (avg[i] > 0.f && avg[i] < thr) out_idx[m++] = i;
+        if (out_stats) { out_stats[0] = mean; out_stats[1] = std_dev; out_stats[2] = thr; }
+    }
+    if (out_avg) memcpy(out_avg, avg, sizeof(float) * (size_t)n);
+    orc_kdtree_free(t);
+    free(idx);
+    free(d2);
+    free(avg);
+    return m;
+}
+
 /* generalized_icp.cu:18-61: Rx*diag(eps,1,1)*Rx^T, Rx = rotation e1 -> n */
 void orc_covariances_from_normals(const float *nrm, int n, float eps, float *out) {
 #pragma omp parallel for schedule(static)

@@ -146,6 +146,26 @@ def estimate_normals(pts, knn=30, radius=0.0, max_nn=0):
     return out
 
 
+def remove_radius_outliers(pts, nb_points, radius):
+    """-> ascending indices of the kept points (down_sample.cu:317-354)"""
+    pts = _f(pts).reshape(-1, 3)
+    out = np.empty(len(pts), np.int32)
+    m = lib().orc_remove_radius_outliers(_p(pts), C.c_int(len(pts)), C.c_int(nb_points), C.c_float(radius), _p(out))
+    return out[:m].copy()
+
+
+def remove_statistical_outliers(pts, nb_neighbors, std_ratio):
+    """-> (ascending kept indices, per-point mean squared neighbour distance, (mean, std, threshold))
+    (down_sample.cu:356-438)"""
+    pts = _f(pts).reshape(-1, 3)
+    out = np.empty(len(pts), np.int32)
+    avg = np.empty(len(pts), np.float32)
+    stats = np.zeros(3, np.float32)
+    m = lib().orc_remove_statistical_outliers(_p(pts), C.c_int(len(pts)), C.c_int(nb_neighbors), C.c_float(std_ratio),
+                                              _p(out), _p(avg), _p(stats))
+    return out[:m].copy(), avg, stats
+
+
 def normals_from_neighbors(pts, nbr):
     pts = _f(pts).reshape(-1, 3)
     nbr = np.ascontiguousarray(nbr, np.int32)

@@ -1,0 +1,83 @@
+"""GPU parity of the kNN consumers added in round 1: RemoveRadiusOutliers,
+RemoveStatisticalOutliers, SelectByIndex -- C ABI through the Python mirror vs the CPU oracle, plus the
+reference's known-answer tests (tests/golden).  Last in collection order: these kernels were written after the
+round's GPU budget was spent and are validated by the driver's round-end run first."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+import cupoch_b200 as cph
+
+
+def _cloud(n, seed, outliers=40):
+    rng = np.random.default_rng(seed)
+    pts = rng.random((n, 3), dtype=np.float32)
+    pts[:outliers] += rng.random((outliers, 3), dtype=np.float32) * 3 + 1.5
+    nrm = rng.standard_normal((n, 3)).astype(np.float32)
+    col = rng.random((n, 3), dtype=np.float32)
+    return pts, nrm, col
+
+
+def test_radius_outliers_golden(golden):
+    g = golden["radius_outliers"]
+    pc = cph.geometry.PointCloud(np.array(g["points"], np.float32))
+    out, idx = pc.remove_radius_outlier(g["nb_points"], g["radius"])
+    assert idx.cpu().tolist() == [0]
+    np.testing.assert_array_equal(out.points.cpu(), np.array(g["kept_points"], np.float32))
+
+
+def test_select_by_index_golden(golden):
+    g = golden["select_by_index"]
+    pts = np.array(g["points"], np.float32)
+    pc = cph.geometry.PointCloud(pts)
+    out = pc.select_by_index(np.array(g["indices"]))
+    np.testing.assert_array_equal(out.points.cpu(), pts[g["indices"]])
+    inv = pc.select_by_index(np.array(g["indices"]), invert=True)
+    mask = np.ones(len(pts), bool)
+    mask[g["indices"]] = False
+    np.testing.assert_array_equal(inv.points.cpu(), pts[mask])
+
+
+@pytest.mark.parametrize("n,nb,r", [(20000, 5, 0.04), (20000, 16, 0.07), (5000, 0, 0.01), (100000, 8, 0.03)])
+def test_radius_outliers_vs_oracle(orc, n, nb, r):
+    pts, nrm, col = _cloud(n, 7)
+    pc = cph.geometry.PointCloud(pts)
+    pc.normals, pc.colors = nrm, col
+    out, idx = pc.remove_radius_outlier(nb, r)
+    ref = orc.remove_radius_outliers(pts, nb, r)
+    np.testing.assert_array_equal(idx.cpu(), ref)                    # same search arithmetic: exact
+    np.testing.assert_array_equal(out.points.cpu(), pts[ref])
+    np.testing.assert_array_equal(out.normals.cpu(), nrm[ref])
+    np.testing.assert_array_equal(out.colors.cpu(), col[ref])
+
+
+@pytest.mark.parametrize("n,k,ratio", [(20000, 16, 1.0), (20000, 8, 2.0), (100000, 20, 1.5)])
+def test_statistical_outliers_vs_oracle(orc, n, k, ratio):
+    pts, _, _ = _cloud(n, 9)
+    pc = cph.geometry.PointCloud(pts)
+    out, idx = pc.remove_statistical_outlier(k, ratio)
+    ref, avg, (mean, std, thr) = orc.remove_statistical_outliers(pts, k, ratio)
+    got = idx.cpu()
+    gm, gs, gt = pc.last_outlier_stats
+    # float64 sums in a different order: the float32 statistics agree to an ulp or two
+    np.testing.assert_allclose([gm, gs, gt], [mean, std, thr], rtol=1e-6)
+    # points whose mean distance sits on the threshold may fall either way; everything else must agree
+    amb = set(np.flatnonzero(np.abs(avg - thr) <= 1e-5 * thr).tolist())
+    assert set(got.tolist()) - amb == set(ref.tolist()) - amb
+    assert (np.diff(got) > 0).all()
+    np.testing.assert_array_equal(out.points.cpu(), pts[got])
+
+
+def test_filters_degenerate():
+    pts, _, _ = _cloud(3000, 11)
+    pc = cph.geometry.PointCloud(pts)
+    out, idx = pc.remove_radius_outlier(5, 0.0)          # radius 0 matches nothing
+    assert len(out) == 0 and idx.shape == (0,)
+    a = pc.remove_radius_outlier(5, -0.05)[1].cpu()      # the search squares the radius
+    b = pc.remove_radius_outlier(5, 0.05)[1].cpu()
+    np.testing.assert_array_equal(a, b)
+    out, idx = pc.remove_statistical_outlier(1, 1.0)     # k = 1: only the point itself, every mean is 0
+    assert len(out) == 0
+    with pytest.raises(cph._lib.CphbError):
+        pc.remove_radius_outlier(100, 0.05)              # nb_points + 1 > NUM_MAX_NN

@@ -140,6 +140,24 @@ def main():
         "tolerance": 1e-3,
         "cite": "src/tests/registration/kabsch.cpp:35-55",
     }
+    # ---- container / filter known answers (pointcloud.cpp:303-334, 676-693) ----
+    b = test_body(pc, "PointCloud", "RemoveRadiusOutliers")
+    pat = re.compile(r"points\.push_back\(Eigen::Vector3f\(\{\s*(-?[\d.]+)\s*,\s*(-?[\d.]+)\s*,\s*(-?[\d.]+)\s*\}\)\)")
+    rro_pts = [[float(x), float(y), float(z)] for x, y, z in pat.findall(b)]
+    m = re.search(r"RemoveRadiusOutliers\((\d+),\s*([\d.]+)\)", b)
+    assert len(rro_pts) == 8 and m
+    g["radius_outliers"] = {
+        "points": rro_pts, "nb_points": int(m.group(1)), "radius": float(m.group(2)),
+        "kept_points": [[0.0, 0.0, 0.0]],  # EXPECT_EQ(size, 1); EXPECT_EQ(h_pt[0], (0,0,0))
+        "cite": "src/tests/geometry/pointcloud.cpp:676-693",
+    }
+    b = test_body(pc, "PointCloud", "SelectByIndex")
+    g["select_by_index"] = {
+        "points": pts1000.tolist(),
+        "indices": [int(x) for x in re.findall(r"ref_idx\.push_back\((\d+)\)", b)],
+        "cite": "src/tests/geometry/pointcloud.cpp:303-334 (output == the named rows, compared as sorted sets)",
+    }
+    assert len(g["select_by_index"]["indices"]) == 10
     os.makedirs(os.path.dirname(OUT), exist_ok=True)
     with open(OUT, "w") as f:
         json.dump(g, f)
