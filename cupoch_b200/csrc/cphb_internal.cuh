@@ -90,6 +90,10 @@ int cphb_sort_pairs_u32(const uint32_t *keys_in, uint32_t *keys_out, const uint3
 int cphb_sort_pairs_u64(const uint64_t *keys_in, uint64_t *keys_out, const uint32_t *vals_in,
                         uint32_t *vals_out, size_t n, int bits, cudaStream_t s);
 
+// stable compaction (filters.cu): ascending positions i < n with keep[i] != 0 -> indices_out, their number to
+// *h_n_out (synchronises the stream)
+int cphb_compact_flags(const uint8_t *keep, size_t n, int32_t *indices_out, size_t *h_n_out, cudaStream_t s);
+
 // index.cu internals reused by icp.cu (Hilbert-ordering of the source)
 // perm_out[pos] = original index of the pos-th point along the Hilbert curve.
 // bounds_dev6: device buffer of 6 ordered-uint floats; computed here unless

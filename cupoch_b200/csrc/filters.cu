@@ -200,7 +200,7 @@ __global__ void __launch_bounds__(FLT_BLOCK) keep_write_kernel(const uint8_t *__
 }
 
 // keep flags -> ascending indices in indices_out, count to *h_n_out (synchronises)
-static int compact_keep(const uint8_t *keep, size_t n, int32_t *indices_out, size_t *h_n_out, cudaStream_t s) {
+int cphb_compact_flags(const uint8_t *keep, size_t n, int32_t *indices_out, size_t *h_n_out, cudaStream_t s) {
     const unsigned nb = (unsigned)((n + FLT_BLOCK - 1) / FLT_BLOCK);
     unsigned *counts = nullptr;
     unsigned long long *total = nullptr;
@@ -215,7 +215,7 @@ static int compact_keep(const uint8_t *keep, size_t n, int32_t *indices_out, siz
         if (e == cudaSuccess) e = cudaMemcpyAsync(&h, total, sizeof(h), cudaMemcpyDeviceToHost, s);
         if (e == cudaSuccess) e = cudaStreamSynchronize(s);
         if (e != cudaSuccess) {
-            cphb_set_error("compact_keep: %s", cudaGetErrorString(e));
+            cphb_set_error("cphb_compact_flags: %s", cudaGetErrorString(e));
             rc = CPHB_ERR_CUDA;
         } else {
             *h_n_out = (size_t)h;
@@ -259,7 +259,7 @@ extern "C" int cphb_remove_radius_outliers(const float *points, size_t n, int nb
     if (!rc) rc = cphb_search_radius(ix, points, n, radius, k, idx, d2, nullptr, stream);
     if (!rc) {
         CPHB_LAUNCH(radius_keep_kernel, (unsigned)((n + 255) / 256), 256, 0, s, idx, n, k, nb_points, keep);
-        rc = compact_keep(keep, n, indices_out, h_n_out, s);
+        rc = cphb_compact_flags(keep, n, indices_out, h_n_out, s);
     }
     cphb_free_async(idx, s);
     cphb_free_async(d2, s);
@@ -311,7 +311,7 @@ extern "C" int cphb_remove_statistical_outliers(const float *points, size_t n, i
         CPHB_LAUNCH(stat_partial_kernel, nb, FLT_BLOCK, 0, s, avg, n, 1, scalars, partial);
         CPHB_LAUNCH(stat_final_kernel, 1, FLT_BLOCK, 0, s, partial, nb, 1, std_ratio, scalars);
         CPHB_LAUNCH(stat_keep_kernel, g256, 256, 0, s, avg, n, scalars, keep);
-        rc = compact_keep(keep, n, indices_out, h_n_out, s);
+        rc = cphb_compact_flags(keep, n, indices_out, h_n_out, s);
         if (!rc && h_stats) {
             cudaError_t e = cudaMemcpyAsync(h_stats, scalars, sizeof(float) * 3, cudaMemcpyDeviceToHost, s);
             if (e == cudaSuccess) e = cudaStreamSynchronize(s);

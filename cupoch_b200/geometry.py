@@ -210,6 +210,87 @@ class PointCloud:
         return True
 
 
+class VoxelGrid:
+    """geometry::VoxelGrid (voxelgrid.h:84-160), the part SURVEY 8f ranks next: creation from a point cloud
+    (voxelgrid_factory.cu:164-228) and the accessors that need nothing else.  voxels_keys / voxels_colors are
+    device arrays ([m, 3] int32 grid indices in lexicographic order, [m, 3] float32 mean colours)."""
+
+    def __init__(self):
+        self.voxel_size = 0.0
+        self.origin = np.zeros(3, np.float32)
+        self.voxels_keys = None
+        self.voxels_colors = None
+
+    def __len__(self):
+        return 0 if self.voxels_keys is None else self.voxels_keys.shape[0]
+
+    def has_voxels(self):
+        return len(self) > 0
+
+    def has_colors(self):
+        return True  # voxelgrid.h:112-114: by default the colours are (1, 1, 1)
+
+    def get_voxels(self):
+        """-> (keys [m,3] int32, colors [m,3] float32) on the host (VoxelGrid::GetVoxels)"""
+        if not len(self):
+            return np.zeros((0, 3), np.int32), np.zeros((0, 3), np.float32)
+        return self.voxels_keys.cpu(), self.voxels_colors.cpu()
+
+    def get_voxel(self, point):
+        """VoxelGrid::GetVoxel (voxelgrid.cu:338-341): floor((point - origin) / voxel_size)"""
+        p = np.asarray(point, np.float32)
+        return np.floor((p - self.origin) / np.float32(self.voxel_size)).astype(np.int32)
+
+    def get_min_bound(self):
+        """voxelgrid.cu:161-172: min grid index * voxel_size + origin (origin when empty)"""
+        if not len(self):
+            return self.origin.copy()
+        k = self.voxels_keys.cpu().min(0).astype(np.float32)
+        return k * np.float32(self.voxel_size) + self.origin
+
+    def get_max_bound(self):
+        """voxelgrid.cu:174-187: (max grid index + 1) * voxel_size + origin"""
+        if not len(self):
+            return self.origin.copy()
+        k = self.voxels_keys.cpu().max(0).astype(np.float32)
+        return (k + np.float32(1)) * np.float32(self.voxel_size) + self.origin
+
+    @staticmethod
+    def create_from_point_cloud_within_bounds(input, voxel_size, min_bound, max_bound):
+        """VoxelGrid::CreateFromPointCloudWithinBounds (voxelgrid_factory.cu:164-219)"""
+        out = VoxelGrid()
+        out.voxel_size = float(voxel_size)
+        out.origin = np.asarray(min_bound, np.float32).reshape(3).copy()
+        n = len(input)
+        if n == 0:
+            return out
+        mn = (C.c_float * 3)(*[float(x) for x in out.origin])
+        mx = (C.c_float * 3)(*[float(x) for x in np.asarray(max_bound, np.float32).reshape(3)])
+        keys = DeviceArray((n, 3), np.int32)
+        cols = DeviceArray((n, 3), np.float32)
+        m = C.c_size_t(0)
+        _lib.check(_lib.lib().cphb_voxel_grid_from_point_cloud(
+            input._points.ptr, input._colors.ptr if input.has_colors() else None, n, float(voxel_size), mn, mx,
+            keys.ptr, cols.ptr, C.byref(m), None))
+        m = m.value
+        if m:
+            out.voxels_keys = DeviceArray((m, 3), np.int32, ptr=keys.ptr, base=keys)
+            out.voxels_colors = DeviceArray((m, 3), np.float32, ptr=cols.ptr, base=cols)
+        return out
+
+    @staticmethod
+    def create_from_point_cloud(input, voxel_size):
+        """VoxelGrid::CreateFromPointCloud (voxelgrid_factory.cu:221-228): bounds widened by half a voxel"""
+        if len(input) == 0:
+            out = VoxelGrid()
+            out.voxel_size = float(voxel_size)
+            return out
+        v = np.float32(voxel_size)
+        mn, mx = input._bounds()
+        return VoxelGrid.create_from_point_cloud_within_bounds(input, voxel_size, mn - v * np.float32(0.5),
+                                                               mx + v * np.float32(0.5))
+
+
 class KDTreeFlann:
     """knn::KDTreeFlann (kdtree_flann.h:43-124), exposed as cupoch.geometry.KDTreeFlann
     (kdtree_flann.cpp:93-95)."""

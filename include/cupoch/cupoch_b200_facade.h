@@ -14,6 +14,7 @@
 #include <memory>
 #include <stdexcept>
 #include <tuple>
+#include <utility>
 #include <vector>
 
 #include "cupoch_b200.h"
@@ -34,6 +35,15 @@ struct Vector3f {
     float &operator()(int i) { return v[i]; }
     float operator()(int i) const { return v[i]; }
     static Vector3f Zero() { return Vector3f(); }
+};
+struct Vector3i {
+    int v[3];
+    Vector3i() : v{0, 0, 0} {}
+    Vector3i(int a, int b, int c) : v{a, b, c} {}
+    int &operator[](int i) { return v[i]; }
+    int operator[](int i) const { return v[i]; }
+    int &operator()(int i) { return v[i]; }
+    int operator()(int i) const { return v[i]; }
 };
 struct Vector2i {
     int v[2];
@@ -410,6 +420,71 @@ private:
         if (!points_.empty()) utility::check(cphb_min_max_bound(cfp(points_), points_.size(), mn, mx, nullptr));
         return which ? Eigen::Vector3f(mx[0], mx[1], mx[2]) : Eigen::Vector3f(mn[0], mn[1], mn[2]);
     }
+};
+
+/// geometry::Voxel (voxelgrid.h:48-62)
+class Voxel {
+public:
+    Voxel() {}
+    Voxel(const Eigen::Vector3i &grid_index) : grid_index_(grid_index) {}
+    Voxel(const Eigen::Vector3i &grid_index, const Eigen::Vector3f &color) : grid_index_(grid_index), color_(color) {}
+    Eigen::Vector3i grid_index_ = Eigen::Vector3i(0, 0, 0);
+    Eigen::Vector3f color_ = Eigen::Vector3f(1.0f, 1.0f, 1.0f);
+};
+
+/// geometry::VoxelGrid (voxelgrid.h:84-160): creation from a point cloud (voxelgrid_factory.cu:164-228) and the
+/// accessors that need nothing else.  Keys and colours are kept as two device vectors (the reference zips keys
+/// with Voxel{grid_index, color}); GetVoxels() hands back the reference's pair.
+class VoxelGrid {
+public:
+    bool HasVoxels() const { return voxels_keys_.size() > 0; }
+    bool HasColors() const { return true; }  // voxelgrid.h:112-114
+    bool IsEmpty() const { return !HasVoxels(); }
+    std::pair<std::vector<Eigen::Vector3i>, std::vector<Voxel>> GetVoxels() const {
+        std::vector<Eigen::Vector3i> k = voxels_keys_.to_host();
+        std::vector<Eigen::Vector3f> c = voxels_colors_.to_host();
+        std::vector<Voxel> v(k.size());
+        for (size_t i = 0; i < k.size(); ++i) v[i] = Voxel(k[i], c[i]);
+        return std::make_pair(std::move(k), std::move(v));
+    }
+    Eigen::Vector3i GetVoxel(const Eigen::Vector3f &point) const {  // voxelgrid.cu:338-341
+        return Eigen::Vector3i((int)std::floor((point[0] - origin_[0]) / voxel_size_), (int)std::floor((point[1] - origin_[1]) / voxel_size_),
+                               (int)std::floor((point[2] - origin_[2]) / voxel_size_));
+    }
+    static std::shared_ptr<VoxelGrid> CreateFromPointCloudWithinBounds(const PointCloud &input, float voxel_size,
+                                                                       const Eigen::Vector3f &min_bound,
+                                                                       const Eigen::Vector3f &max_bound) {
+        auto out = std::make_shared<VoxelGrid>();
+        if (voxel_size <= 0.0) utility::LogError("[VoxelGridFromPointCloud] voxel_size <= 0.");
+        out->voxel_size_ = voxel_size;
+        out->origin_ = min_bound;
+        const size_t n = input.points_.size();
+        if (n == 0) return out;
+        const float mn[3] = {min_bound[0], min_bound[1], min_bound[2]}, mx[3] = {max_bound[0], max_bound[1], max_bound[2]};
+        out->voxels_keys_.resize(n);
+        out->voxels_colors_.resize(n);
+        size_t m = 0;
+        utility::check(cphb_voxel_grid_from_point_cloud(
+                reinterpret_cast<const float *>(input.points_.data()),
+                input.HasColors() ? reinterpret_cast<const float *>(input.colors_.data()) : nullptr, n, voxel_size, mn, mx,
+                reinterpret_cast<int32_t *>(out->voxels_keys_.data()), reinterpret_cast<float *>(out->voxels_colors_.data()), &m,
+                nullptr));
+        out->voxels_keys_.resize(m);
+        out->voxels_colors_.resize(m);
+        return out;
+    }
+    static std::shared_ptr<VoxelGrid> CreateFromPointCloud(const PointCloud &input, float voxel_size) {  // :221-228
+        const Eigen::Vector3f lo = input.GetMinBound(), hi = input.GetMaxBound();
+        const float h = voxel_size * 0.5f;
+        return CreateFromPointCloudWithinBounds(input, voxel_size, Eigen::Vector3f(lo[0] - h, lo[1] - h, lo[2] - h),
+                                                Eigen::Vector3f(hi[0] + h, hi[1] + h, hi[2] + h));
+    }
+
+public:
+    float voxel_size_ = 0.0f;
+    Eigen::Vector3f origin_ = Eigen::Vector3f(0.f, 0.f, 0.f);
+    utility::device_vector<Eigen::Vector3i> voxels_keys_;
+    utility::device_vector<Eigen::Vector3f> voxels_colors_;
 };
 }  // namespace geometry
 

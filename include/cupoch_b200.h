@@ -140,6 +140,16 @@ int cphb_covariances_from_normals(const float *normals, size_t n, float epsilon,
 int cphb_color_gradient(const float *points, const float *normals, const float *colors, size_t n,
                         float radius, int max_nn, float *out_gradient, void *stream);
 
+/* VoxelGrid::CreateFromPointCloudWithinBounds (voxelgrid_factory.cu:164-219): grid index
+ * floor((p - min_bound) / voxel_size) per point (negative below the bound, as in the reference), one voxel per
+ * distinct index in lexicographic (x, y, z) order, colour = mean colour of its points ((1,1,1) when colors is
+ * NULL).  out_keys (device, n x 3 int32) / out_colors (device, n x 3 float) must hold n rows; *h_n_out = voxel
+ * count (synchronises).  For VoxelGrid::CreateFromPointCloud pass the cloud's bounds widened by half a voxel
+ * (:221-228).  voxel_size <= 0 or voxel_size * INT_MAX < extent give an empty grid. */
+int cphb_voxel_grid_from_point_cloud(const float *points, const float *colors, size_t n, float voxel_size,
+                                     const float h_min_bound[3], const float h_max_bound[3], int32_t *out_keys,
+                                     float *out_colors, size_t *h_n_out, void *stream);
+
 /* PointCloud::RemoveRadiusOutliers (down_sample.cu:317-354): search the cloud against itself with
  * (radius, nb_points + 1) and keep the points all of whose slots are filled (more than nb_points neighbours
  * inside the radius, the point itself included).  indices_out (device, n int32) receives the ascending indices

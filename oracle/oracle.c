@@ -368,6 +368,48 @@ int orc_voxel_down_sample(const float *pts, const float *nrm, const float *col,
 }
 
 /* ======================================================================== */
+/* VoxelGrid::CreateFromPointCloudWithinBounds  voxelgrid_factory.cu:164-219   */
+/* key = floor((p - min_bound) / voxel) (:73-76, negative for points below the  */
+/* bound: the reference does not clip); voxels sorted lexicographically,        */
+/* colour = mean of the points' colours (sum / count), (1,1,1) without colours  */
+/* (Voxel's default, voxelgrid.h:61).  voxel <= 0 and "voxel too small" are only */
+/* logged by the reference; here they return an empty grid.                     */
+/* ======================================================================== */
+int orc_voxel_grid_from_point_cloud(const float *pts, const float *col, int n, float voxel, const float min_bound[3],
+                                    const float max_bound[3], int32_t *out_keys, float *out_col) {
+    if (voxel <= 0.0f || n <= 0) return 0;
+    float ext = 0.f;
+    for (int a = 0; a < 3; ++a)
+        if (max_bound[a] - min_bound[a] > ext) ext = max_bound[a] - min_bound[a];
+    if (voxel * (float)2147483647 < ext) return 0; /* :174-177 */
+    vkey *keys = (vkey *)malloc(sizeof(vkey) * n);
+    for (int i = 0; i < n; ++i) {
+        for (int a = 0; a < 3; ++a) keys[i].k[a] = (int32_t)floorf((pts[3 * i + a] - min_bound[a]) / voxel);
+        keys[i].i = i;
+    }
+    qsort(keys, n, sizeof(vkey), vkey_cmp);
+    int n_out = 0;
+    for (int b = 0; b < n;) {
+        int e = b;
+        double sc[3] = {0, 0, 0};
+        while (e < n && keys[e].k[0] == keys[b].k[0] && keys[e].k[1] == keys[b].k[1] && keys[e].k[2] == keys[b].k[2]) {
+            if (col)
+                for (int a = 0; a < 3; ++a) sc[a] += col[3 * keys[e].i + a];
+            ++e;
+        }
+        const float cnt = (float)(e - b);
+        for (int a = 0; a < 3; ++a) {
+            out_keys[3 * n_out + a] = keys[b].k[a];
+            out_col[3 * n_out + a] = col ? (float)sc[a] / cnt : 1.0f;
+        }
+        ++n_out;
+        b = e;
+    }
+    free(keys);
+    return n_out;
+}
+
+/* ======================================================================== */
 /* symmetric 3x3 eigen solver   eigenvalue.inl:30-178                         */
 /* m is ROW-major 3x3; only the entries the reference reads are read.        */
 /* ======================================================================== */

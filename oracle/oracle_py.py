@@ -146,6 +146,23 @@ def estimate_normals(pts, knn=30, radius=0.0, max_nn=0):
     return out
 
 
+def voxel_grid_from_point_cloud(pts, voxel, lo=None, hi=None, colors=None):
+    """VoxelGrid::CreateFromPointCloud[WithinBounds] (voxelgrid_factory.cu:164-228) -> (keys[m,3] int32, colors[m,3],
+    origin[3])"""
+    pts = _f(pts).reshape(-1, 3)
+    v = np.float32(voxel)
+    if lo is None:  # CreateFromPointCloud: bounds of the cloud widened by half a voxel (:221-228)
+        lo = (min_bound(pts) - v * np.float32(0.5)).astype(np.float32)
+        hi = (max_bound(pts) + v * np.float32(0.5)).astype(np.float32)
+    mn, mx = _f(lo).reshape(3), _f(hi).reshape(3)
+    col = None if colors is None else _f(colors).reshape(-1, 3)
+    keys = np.empty((len(pts), 3), np.int32)
+    out = np.empty((len(pts), 3), np.float32)
+    m = lib().orc_voxel_grid_from_point_cloud(_p(pts), _p(col), C.c_int(len(pts)), C.c_float(voxel), _p(mn), _p(mx),
+                                              _p(keys), _p(out))
+    return keys[:m].copy(), out[:m].copy(), mn.copy()
+
+
 def remove_radius_outliers(pts, nb_points, radius):
     """-> ascending indices of the kept points (down_sample.cu:317-354)"""
     pts = _f(pts).reshape(-1, 3)
@@ -258,3 +275,4 @@ def registration_icp(kind, src, tgt, max_distance, init=None, src_nrm=None, src_
 
 def num_threads():
     return int(lib().orc_num_threads())
+

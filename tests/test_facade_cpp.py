@@ -12,21 +12,23 @@ from conftest import ROOT
 EXE = os.path.join(ROOT, "tests", "cpp", "_build", "facade_smoke")
 
 
-def build_facade():
+def build_facade(name="facade_smoke"):
     import __graft_entry__
     __graft_entry__.build()
-    os.makedirs(os.path.dirname(EXE), exist_ok=True)
+    exe = os.path.join(os.path.dirname(EXE), name)
+    os.makedirs(os.path.dirname(exe), exist_ok=True)
     lib = os.path.join(ROOT, "cupoch_b200", "lib")
     subprocess.check_call(["g++", "-std=c++17", "-O2", "-Wall", "-I" + os.path.join(ROOT, "include"),
-                           os.path.join(ROOT, "tests", "cpp", "facade_smoke.cpp"), "-o", EXE, "-L" + lib,
+                           os.path.join(ROOT, "tests", "cpp", name + ".cpp"), "-o", exe, "-L" + lib,
                            "-lcupoch_b200", "-Wl,-rpath," + lib])
-    return EXE
+    return exe
 
 
 def test_facade_compiles_and_links():
-    exe = build_facade()
-    out = subprocess.run(["ldd", exe], capture_output=True, text=True).stdout
-    assert "libcupoch_b200.so" in out and "not found" not in out
+    for name in ("facade_smoke", "facade_filters"):
+        exe = build_facade(name)
+        out = subprocess.run(["ldd", exe], capture_output=True, text=True).stdout
+        assert "libcupoch_b200.so" in out and "not found" not in out
 
 
 @pytest.mark.gpu

@@ -81,3 +81,42 @@ def test_filters_degenerate():
     assert len(out) == 0
     with pytest.raises(cph._lib.CphbError):
         pc.remove_radius_outlier(100, 0.05)              # nb_points + 1 > NUM_MAX_NN
+
+
+def test_voxel_grid_golden_and_oracle(orc):
+    """VoxelGrid::CreateFromPointCloud[WithinBounds] (voxelgrid_factory.cu:164-228): the reference's known answer
+    (tests/geometry/voxelgrid.cpp:57-68) and bit-exact parity with the oracle (same key arithmetic, colours added
+    in float64 in original index order on both sides)."""
+    VG = cph.geometry.VoxelGrid
+    one = VG.create_from_point_cloud_within_bounds(cph.geometry.PointCloud(np.array([[0.5, 0.5, 0.5]], np.float32)), 1.0,
+                                                   [-100.0] * 3, [100.0] * 3)
+    assert len(one) == 1 and one.get_voxels()[0].tolist() == [[100, 100, 100]]
+    rng = np.random.default_rng(8)
+    n = 200000
+    pts = (rng.random((n, 3), dtype=np.float32) * np.float32(2) - np.float32(0.7)).astype(np.float32)
+    col = rng.random((n, 3), dtype=np.float32)
+    pc = cph.geometry.PointCloud(pts)
+    pc.colors = col
+    for voxel, lo, hi in ((0.05, None, None), (0.03, [0.0, 0.0, 0.0], [1.0, 1.0, 1.0])):
+        vg = (VG.create_from_point_cloud(pc, voxel) if lo is None
+              else VG.create_from_point_cloud_within_bounds(pc, voxel, lo, hi))
+        k, c, o = orc.voxel_grid_from_point_cloud(pts, voxel, lo, hi, colors=col)
+        gk, gc = vg.get_voxels()
+        np.testing.assert_array_equal(vg.origin, o)
+        np.testing.assert_array_equal(gk, k)
+        np.testing.assert_array_equal(gc, c)
+    nocol = VG.create_from_point_cloud(cph.geometry.PointCloud(pts), 0.05)
+    assert (nocol.get_voxels()[1] == 1.0).all()                       # Voxel's default colour
+    assert len(VG.create_from_point_cloud(pc, 0.0)) == 0
+    b = VG.create_from_point_cloud(pc, 0.05)
+    assert (b.get_min_bound() <= pts.min(0)).all() and (b.get_max_bound() >= pts.max(0)).all()
+
+
+def test_facade_known_answers():
+    """tests/cpp/facade_filters.cpp: the reference's own RemoveRadiusOutliers / SelectByIndex / VoxelGrid tests,
+    compiled with plain g++ against the header-compatible facade."""
+    import subprocess
+    from test_facade_cpp import build_facade
+    exe = build_facade("facade_filters")
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr

@@ -54,3 +54,24 @@ def test_statistical_outliers_vs_numpy(orc):
         if k == 1:
             assert len(kept) == 0       # only the point itself: every mean is 0 and `dist > 0` drops it
     assert len(pts) - len(orc.remove_statistical_outliers(pts, 16, 1.0)[0]) >= 25  # the planted outliers go
+
+
+def test_voxel_grid_oracle(orc):
+    """voxelgrid_factory.cu:164-228 vs numpy; tests/geometry/voxelgrid.cpp:57-68 (one point inside wide bounds ->
+    one voxel) as the known answer."""
+    k, c, o = orc.voxel_grid_from_point_cloud(np.array([[0.5, 0.5, 0.5]], np.float32), 1.0, [-100] * 3, [100] * 3)
+    assert len(k) == 1 and k.tolist() == [[100, 100, 100]] and c.tolist() == [[1.0, 1.0, 1.0]]
+    rng = np.random.default_rng(8)
+    pts = (rng.random((5000, 3), dtype=np.float32) * np.float32(2) - np.float32(0.7)).astype(np.float32)
+    col = rng.random((5000, 3), dtype=np.float32)
+    for voxel, lo, hi in ((0.1, None, None), (0.07, [0.0, 0.0, 0.0], [1.0, 1.0, 1.0])):
+        k, c, o = orc.voxel_grid_from_point_cloud(pts, voxel, lo, hi, colors=col)
+        ki = np.floor((pts - o) / np.float32(voxel)).astype(np.int32)
+        u, inv, cnt = np.unique(ki, axis=0, return_inverse=True, return_counts=True)
+        np.testing.assert_array_equal(k, u)                       # lexicographic, negative indices included
+        ref = np.zeros((len(u), 3))
+        np.add.at(ref, inv.reshape(-1), col.astype(np.float64))
+        np.testing.assert_allclose(c, ref / cnt[:, None], rtol=1e-6)
+        if lo is not None:
+            assert k.min() < 0                                    # points below the bound are not clipped
+    assert len(orc.voxel_grid_from_point_cloud(pts, 0.0)[0]) == 0
