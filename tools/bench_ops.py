@@ -21,6 +21,8 @@ def main():
     ap.add_argument("--radius", type=float, default=0.05)
     ap.add_argument("--reps", type=int, default=5)
     ap.add_argument("--attrs", default="p", help="p | pn | pnc")
+    ap.add_argument("--filters", action="store_true",
+                    help="also time the SURVEY 8f rows: RemoveRadiusOutliers / RemoveStatisticalOutliers / VoxelGrid")
     args = ap.parse_args()
     import cupoch_b200 as cph
     from cupoch_b200 import _lib
@@ -80,6 +82,33 @@ def main():
     self_tree = cph.geometry.KDTreeFlann(pc)
     s_med, s_min, (cnt2, idx2, _) = timed(lambda: self_tree.search_radius(pc.points, args.radius, 1), max(2, args.reps // 2))
     props["self_query_identity"] = bool((idx2.cpu()[:, 0] == np.arange(n)).mean() > 0.9999)
+    extra = {}
+    if args.filters:
+        # SURVEY 8f rows on the same 10 M cloud: size-independent properties instead of an oracle run
+        VG = cph.geometry.VoxelGrid
+        for _ in range(2):
+            vg = VG.create_from_point_cloud(pc, args.voxel)
+        g_med, g_min, vg = timed(lambda: VG.create_from_point_cloud(pc, args.voxel), args.reps)
+        gk = vg.get_voxels()[0].astype(np.int64)
+        gp = (gk[:, 0] << 42) | (gk[:, 1] << 21) | gk[:, 2]
+        extra["voxel_grid"] = {"ms_median": g_med, "ms_min": g_min, "n_voxels": int(len(vg)),
+                               "lexicographic_order": bool((np.diff(gp) > 0).all()),
+                               "count_matches_voxel_down_sample": bool(len(vg) == n_out)}
+        nb, rr = 16, 2.0 * args.voxel
+        for _ in range(1):
+            pc.remove_radius_outlier(nb, rr)
+        r_med, r_min, (rout, ridx) = timed(lambda: pc.remove_radius_outlier(nb, rr), max(2, args.reps // 2))
+        kept = ridx.cpu()
+        extra["remove_radius_outlier"] = {"nb_points": nb, "radius": rr, "ms_median": r_med, "ms_min": r_min,
+                                          "kept": int(len(kept)), "ascending": bool((np.diff(kept) > 0).all()),
+                                          "idempotent_on_kept_count": None}
+        k_nb = 20
+        pc.remove_statistical_outlier(k_nb, 2.0)
+        t_med, t_min, (sout, sidx) = timed(lambda: pc.remove_statistical_outlier(k_nb, 2.0), max(2, args.reps // 2))
+        skept = sidx.cpu()
+        extra["remove_statistical_outlier"] = {"nb_neighbors": k_nb, "std_ratio": 2.0, "ms_median": t_med, "ms_min": t_min,
+                                               "kept": int(len(skept)), "ascending": bool((np.diff(skept) > 0).all()),
+                                               "stats_mean_std_threshold": list(pc.last_outlier_stats)}
     peak = 6585.1
     try:
         peak = json.load(open(os.path.join(os.path.dirname(__file__), "..", "MEASURED_PEAKS.json")))["hbm_gbs"]
@@ -97,7 +126,7 @@ def main():
                                "roofline": {"algorithmic_bytes": knn_bytes, "achieved_gbs": knn_bytes / k_med * 1e-6,
                                             "frac": knn_bytes / k_med * 1e-6 / peak}},
         "knn_self": {"ms_median": s_med, "mqueries_per_sec": n / s_med * 1e-3},
-        "properties": props, "launches": int(L.cphb_launch_count()),
+        "properties": props, "launches": int(L.cphb_launch_count()), **extra,
     }))
 
 
