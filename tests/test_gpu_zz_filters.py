@@ -109,7 +109,7 @@ def test_voxel_grid_golden_and_oracle(orc):
     assert (nocol.get_voxels()[1] == 1.0).all()                       # Voxel's default colour
     assert len(VG.create_from_point_cloud(pc, 0.0)) == 0
     b = VG.create_from_point_cloud(pc, 0.05)
-    assert (b.get_min_bound() <= pts.min(0)).all() and (b.get_max_bound() >= pts.max(0)).all()
+    assert (b.get_min_bound() <= pts.min(0) + 1e-5).all() and (b.get_max_bound() >= pts.max(0) - 1e-5).all()
 
 
 def test_facade_known_answers():
