@@ -664,8 +664,15 @@ __device__ __forceinline__ void prefetch_target(const IcpArgs &a, size_t j) {
 //   CPHB_PDL    programmatic dependent launch: the kernels of the loop are launched with stream serialisation
 //               relaxed, run their prologue while the previous kernel drains and wait (griddepcontrol.wait)
 //               before they touch anything it wrote
+//   ICP_DEEP_PIPE  under the static schedule, load the point + certificate TWO tiles ahead so that the L1 prefetch
+//               of the next tile's target rows can be issued at the top of the current tile instead of its end
+//               (r1_icp_certified_ncu: 58 % of the stall samples of a certified launch are long-scoreboard waits
+//               on exactly that gather)
 #ifndef ICP_LOWREG
 #define ICP_LOWREG 0
+#endif
+#ifndef ICP_DEEP_PIPE
+#define ICP_DEEP_PIPE 0
 #endif
 #ifndef CPHB_PDL
 #define CPHB_PDL 0
@@ -757,6 +764,15 @@ __global__ void __launch_bounds__(ICP_SEARCH_WARPS * 32, ICP_MIN_BLOCKS) icp_ite
         if (a.prev) pv_pf = a.prev[tile * 32 + lane];
     }
 #endif
+#if ICP_DEEP_PIPE && !ICP_LOWREG
+    // second pipeline stage (static schedule only): data of the tile after the current one
+    float4 s_pf2 = make_float4(0.f, 0.f, 0.f, 0.f);
+    int2 pv_pf2 = make_int2(-1, 0);
+    if (static_sched && tile + total_warps < n_tiles) {
+        s_pf2 = a.src[(tile + total_warps) * 32 + lane];
+        if (a.prev) pv_pf2 = a.prev[(tile + total_warps) * 32 + lane];
+    }
+#endif
     unsigned tn = 0;
     for (; tile < n_tiles; tile = tn) {
 #if ICP_LOWREG
@@ -775,6 +791,20 @@ __global__ void __launch_bounds__(ICP_SEARCH_WARPS * 32, ICP_MIN_BLOCKS) icp_ite
             pend_sz = csize;
             if (lane == 0) pend = atomicAdd(&st->tile_counter, csize);
         }
+#if ICP_DEEP_PIPE && !ICP_LOWREG
+        if (static_sched) {
+            // the next tile's point + certificate arrived a tile ago: its target rows can start moving now and
+            // have this whole tile to arrive; the loads issued here are for the tile after next
+            s_pf = s_pf2;
+            pv_pf = pv_pf2;
+            if (tn < n_tiles && pv_pf.x >= 0) prefetch_target<KIND>(a, (size_t)pv_pf.x);
+            const unsigned tnn = tn + total_warps;
+            if (tn < n_tiles && tnn < n_tiles) {
+                s_pf2 = a.src[tnn * 32 + lane];
+                if (a.prev) pv_pf2 = a.prev[tnn * 32 + lane];
+            }
+        } else
+#endif
         if (tn < n_tiles) {
 #if ICP_LOWREG
             if (lane < 4) prefetch_l1(reinterpret_cast<const char *>(a.src + tn * 32) + 128 * lane);
@@ -960,6 +990,8 @@ __global__ void __launch_bounds__(ICP_SEARCH_WARPS * 32, ICP_MIN_BLOCKS) icp_ite
             const int pn = a.prev[tn * 32 + lane].x;  // L1 hit (hinted at the top of this tile)
             if (pn >= 0) prefetch_target<KIND>(a, (size_t)pn);
         }
+#elif ICP_DEEP_PIPE
+        if (!static_sched && tn < n_tiles && pv_pf.x >= 0) prefetch_target<KIND>(a, (size_t)pv_pf.x);
 #else
         if (tn < n_tiles && pv_pf.x >= 0) prefetch_target<KIND>(a, (size_t)pv_pf.x);
 #endif

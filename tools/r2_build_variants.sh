@@ -9,5 +9,8 @@ for mb in 4 5 6 7 8; do tools/build_variant.sh mb$mb -DICP_MIN_BLOCKS=$mb; done
 tools/build_variant.sh lowreg9 -DICP_LOWREG=1 -DICP_MIN_BLOCKS=9
 tools/build_variant.sh lowreg8 -DICP_LOWREG=1 -DICP_MIN_BLOCKS=8
 tools/build_variant.sh pdl -DCPHB_PDL=1
+tools/build_variant.sh deep -DICP_DEEP_PIPE=1
+tools/build_variant.sh deep_mb4 -DICP_DEEP_PIPE=1 -DICP_MIN_BLOCKS=4
+tools/build_variant.sh deep_pdl -DICP_DEEP_PIPE=1 -DCPHB_PDL=1
 tools/build_variant.sh pdl_mb6 -DCPHB_PDL=1 -DICP_MIN_BLOCKS=6
 ls -la build_variants
