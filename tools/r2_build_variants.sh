@@ -11,6 +11,9 @@ tools/build_variant.sh lowreg8 -DICP_LOWREG=1 -DICP_MIN_BLOCKS=8
 tools/build_variant.sh pdl -DCPHB_PDL=1
 tools/build_variant.sh deep -DICP_DEEP_PIPE=1
 tools/build_variant.sh deep_mb4 -DICP_DEEP_PIPE=1 -DICP_MIN_BLOCKS=4
+tools/build_variant.sh faststart -DICP_FAST_START=1
+tools/build_variant.sh deep_fast_mb4 -DICP_DEEP_PIPE=1 -DICP_FAST_START=1 -DICP_MIN_BLOCKS=4
+tools/build_variant.sh deep_fast_pdl_mb4 -DICP_DEEP_PIPE=1 -DICP_FAST_START=1 -DCPHB_PDL=1 -DICP_MIN_BLOCKS=4
 tools/build_variant.sh deep_pdl -DICP_DEEP_PIPE=1 -DCPHB_PDL=1
 tools/build_variant.sh pdl_mb6 -DCPHB_PDL=1 -DICP_MIN_BLOCKS=6
 ls -la build_variants
