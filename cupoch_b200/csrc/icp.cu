@@ -674,8 +674,17 @@ __device__ __forceinline__ void prefetch_target(const IcpArgs &a, size_t j) {
 //   ICP_FAST_START  read the whole per-launch state (done, apply_u, static_sched, U) with independent loads: three
 //               dependent L2 round trips at the start of every warp become one (18 % of the stall samples of a
 //               certified launch sit in this prologue)
+//   ICP_DUAL    two instances of the kernel per iteration, one compiled for the searching launches (more resident
+//               warps: ICP_MIN_BLOCKS_SEARCH) and one for the launches that run under the static schedule (more
+//               registers, deeper pipeline); the device-side regime flag decides which of the two returns at once
 #ifndef ICP_DEEP_PIPE
 #define ICP_DEEP_PIPE 0
+#endif
+#ifndef ICP_DUAL
+#define ICP_DUAL 0
+#endif
+#ifndef ICP_MIN_BLOCKS_SEARCH
+#define ICP_MIN_BLOCKS_SEARCH 8
 #endif
 #ifndef ICP_FAST_START
 #define ICP_FAST_START 0
@@ -693,8 +702,11 @@ __device__ __forceinline__ void grid_dependency_trigger() {
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 #endif
 }
-template <int KIND, int TOP>
-__global__ void __launch_bounds__(ICP_SEARCH_WARPS * 32, ICP_MIN_BLOCKS) icp_iteration_kernel(const __grid_constant__ IcpArgs a) {
+// MODE 0: one kernel for every launch (the default build).  ICP_DUAL: MODE 1 does the launches of the searching
+// regime and returns at once under the static schedule, MODE 2 the reverse.
+template <int KIND, int TOP, int MODE = 0>
+__global__ void __launch_bounds__(ICP_SEARCH_WARPS * 32, (MODE == 1) ? ICP_MIN_BLOCKS_SEARCH : ICP_MIN_BLOCKS)
+        icp_iteration_kernel(const __grid_constant__ IcpArgs a) {
     __shared__ __align__(16) float4 s_tile[ICP_SEARCH_WARPS][2 * CPHB_LEAF];
     __shared__ uint64_t s_bar[ICP_SEARCH_WARPS][2];
     __shared__ double s_rows[ICP_SEARCH_WARPS][32 * ROW_STRIDE];
@@ -772,10 +784,13 @@ __global__ void __launch_bounds__(ICP_SEARCH_WARPS * 32, ICP_MIN_BLOCKS) icp_ite
     // once (nearly) every tile is skipped the tiles cost the same, and a static round-robin schedule needs no
     // atomics at all; tile_sums are indexed by tile, so the schedule never affects the result
 #if ICP_FAST_START
-    const bool static_sched = a.static_sched && !a.step_mode && static_word != 0;
+    const bool static_regime = a.static_sched && !a.step_mode && static_word != 0;
 #else
-    const bool static_sched = a.static_sched && !a.step_mode && *(volatile int *)&st->static_sched != 0;
+    const bool static_regime = a.static_sched && !a.step_mode && *(volatile int *)&st->static_sched != 0;
 #endif
+    if (MODE == 1 && static_regime) return;   // the other instance of the pair runs this launch
+    if (MODE == 2 && !static_regime) return;
+    const bool static_sched = (MODE == 1) ? false : (MODE == 2) ? true : static_regime;
     unsigned tile = blockIdx.x * ICP_SEARCH_WARPS + warp;
     unsigned range_end = tile + 1;   // current range [tile, range_end)
     unsigned pend = 0, pend_sz = 1;  // claim in flight (result in lane 0) and its size
@@ -1476,6 +1491,7 @@ struct cphb_icp {
     unsigned *dbg = nullptr;  // CPHB_DEBUG_CERT statistics
     cudaEvent_t *dbg_ev = nullptr;  // CPHB_DEBUG_EVENTS: 3 events per launch (before, between, after)
     unsigned grid, reduce_grid;
+    unsigned grid_search;  // ICP_DUAL: grid of the search-regime instance
     cudaStream_t stream;
 };
 
@@ -1499,24 +1515,25 @@ static bool is_identity4(const float *T) {  // Eigen isIdentity(1e-5), registrat
 }
 
 // resident blocks / SM of the iteration kernel instance a context will launch (register-limited)
-template <int KIND>
+template <int KIND, int MODE>
 static int iteration_occupancy(bool top3) {
     int nb = 0;
-    cudaError_t e = top3 ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, icp_iteration_kernel<KIND, 3>, ICP_SEARCH_WARPS * 32, 0)
-                         : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, icp_iteration_kernel<KIND, 5>, ICP_SEARCH_WARPS * 32, 0);
+    cudaError_t e = top3 ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, icp_iteration_kernel<KIND, 3, MODE>, ICP_SEARCH_WARPS * 32, 0)
+                         : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, icp_iteration_kernel<KIND, 5, MODE>, ICP_SEARCH_WARPS * 32, 0);
     if (e != cudaSuccess) { cudaGetLastError(); return 0; }
     return nb;
 }
+template <int MODE>
 static int iteration_occupancy_kind(int kind, bool top3) {
     static int cache[8][2] = {};  // 0 = not queried yet
     int &c = cache[kind & 7][top3 ? 0 : 1];
     if (c == 0) {
         switch (kind) {
-            case CPHB_EST_POINT_TO_POINT: c = iteration_occupancy<CPHB_EST_POINT_TO_POINT>(top3); break;
-            case CPHB_EST_POINT_TO_PLANE: c = iteration_occupancy<CPHB_EST_POINT_TO_PLANE>(top3); break;
-            case CPHB_EST_SYMMETRIC: c = iteration_occupancy<CPHB_EST_SYMMETRIC>(top3); break;
-            case CPHB_EST_COLORED_ICP: c = iteration_occupancy<CPHB_EST_COLORED_ICP>(top3); break;
-            case CPHB_EST_GENERALIZED_ICP: c = iteration_occupancy<CPHB_EST_GENERALIZED_ICP>(top3); break;
+            case CPHB_EST_POINT_TO_POINT: c = iteration_occupancy<CPHB_EST_POINT_TO_POINT, MODE>(top3); break;
+            case CPHB_EST_POINT_TO_PLANE: c = iteration_occupancy<CPHB_EST_POINT_TO_PLANE, MODE>(top3); break;
+            case CPHB_EST_SYMMETRIC: c = iteration_occupancy<CPHB_EST_SYMMETRIC, MODE>(top3); break;
+            case CPHB_EST_COLORED_ICP: c = iteration_occupancy<CPHB_EST_COLORED_ICP, MODE>(top3); break;
+            case CPHB_EST_GENERALIZED_ICP: c = iteration_occupancy<CPHB_EST_GENERALIZED_ICP, MODE>(top3); break;
         }
         if (c <= 0) c = -1;
     }
@@ -1546,7 +1563,7 @@ static void launch_pdl(K kernel, unsigned grid, unsigned block, cudaStream_t s, 
 
 template <int KIND>
 static void launch_iteration(const cphb_icp *icp, const IcpArgs &a, cudaStream_t s) {
-#if CPHB_PDL
+#if CPHB_PDL && !ICP_DUAL
     static const bool pdl = getenv("CPHB_NO_PDL") == nullptr;
     if (pdl && !a.defer_finalize && !a.step_mode && !icp->dbg_ev) {
         if (icp->index->v.top <= 3) launch_pdl(icp_iteration_kernel<KIND, 3>, icp->grid, ICP_SEARCH_WARPS * 32, s, a);
@@ -1555,8 +1572,18 @@ static void launch_iteration(const cphb_icp *icp, const IcpArgs &a, cudaStream_t
         return;
     }
 #endif
+#if ICP_DUAL
+    if (icp->index->v.top <= 3) {
+        CPHB_LAUNCH((icp_iteration_kernel<KIND, 3, 1>), icp->grid_search, ICP_SEARCH_WARPS * 32, 0, s, a);
+        CPHB_LAUNCH((icp_iteration_kernel<KIND, 3, 2>), icp->grid, ICP_SEARCH_WARPS * 32, 0, s, a);
+    } else {
+        CPHB_LAUNCH((icp_iteration_kernel<KIND, 5, 1>), icp->grid_search, ICP_SEARCH_WARPS * 32, 0, s, a);
+        CPHB_LAUNCH((icp_iteration_kernel<KIND, 5, 2>), icp->grid, ICP_SEARCH_WARPS * 32, 0, s, a);
+    }
+#else
     if (icp->index->v.top <= 3) CPHB_LAUNCH((icp_iteration_kernel<KIND, 3>), icp->grid, ICP_SEARCH_WARPS * 32, 0, s, a);
     else CPHB_LAUNCH((icp_iteration_kernel<KIND, 5>), icp->grid, ICP_SEARCH_WARPS * 32, 0, s, a);
+#endif
     if (icp->dbg_ev) cudaEventRecord(icp->dbg_ev[3 * a.launch_idx + 1], s);
     CPHB_LAUNCH(icp_reduce_kernel<KIND>, icp->reduce_grid, ICP_REDUCE_BLOCK, 0, s, a);
 }
@@ -1628,7 +1655,18 @@ extern "C" int cphb_icp_create(const cphb_cloud *source, const cphb_cloud *targe
         // every block must be resident: warps start on a static tile, and a block waiting for an SM slot
         // would hold its four tiles back until the dynamic queue has drained
         unsigned per_sm = 9u;
-        const int occ = iteration_occupancy_kind(params->estimation, icp->index->v.top <= 3);
+#if ICP_DUAL
+        const int occ = iteration_occupancy_kind<2>(params->estimation, icp->index->v.top <= 3);
+        {
+            unsigned ps = 9u;
+            const int occ_s = iteration_occupancy_kind<1>(params->estimation, icp->index->v.top <= 3);
+            if (occ_s > 0 && (unsigned)occ_s < ps) ps = (unsigned)occ_s;
+            const unsigned cap_s = (unsigned)sms * ps;
+            icp->grid_search = want < cap_s ? want : cap_s;
+        }
+#else
+        const int occ = iteration_occupancy_kind<0>(params->estimation, icp->index->v.top <= 3);
+#endif
         if (occ > 0 && (unsigned)occ < per_sm) per_sm = (unsigned)occ;
         if (const char *e = getenv("CPHB_ICP_BLOCKS_PER_SM")) {  // tuning hook
             int v = atoi(e);
