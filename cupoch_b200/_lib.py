@@ -61,6 +61,8 @@ _SIGNATURES = {
                                                    C.POINTER(C.c_float), _P]),
     "cphb_voxel_grid_from_point_cloud": (C.c_int, [_P, _P, C.c_size_t, C.c_float, C.POINTER(C.c_float), C.POINTER(C.c_float),
                                                    _P, _P, C.POINTER(C.c_size_t), _P]),
+    "cphb_gaussian_filter": (C.c_int, [_P, _P, _P, C.c_size_t, C.c_float, C.c_float, C.c_int, _P, _P, _P,
+                                       C.POINTER(C.c_size_t), _P]),
     "cphb_select_by_index": (C.c_int, [_P, _P, _P, C.c_size_t, _P, C.c_size_t, _P, _P, _P, _P]),
     "cphb_covariances_from_normals": (C.c_int, [_P, C.c_size_t, C.c_float, _P, C.c_int, _P]),
     "cphb_color_gradient": (C.c_int, [_P, _P, _P, C.c_size_t, C.c_float, C.c_int, _P, _P]),

@@ -329,6 +329,78 @@ extern "C" int cphb_remove_statistical_outliers(const float *points, size_t n, i
     return rc;
 }
 
+// PointCloud::GaussianFilter (pointcloud.cu:56-106,387-433): weighted mean of the neighbours found by a radius search
+// of the cloud against itself; weight = exp(-0.5 * d2 / sigma2) evaluated in double and rounded to float (the
+// reference's literal 0.5 promotes the expression), sequential float32 sums in slot order, one division per component
+__global__ void __launch_bounds__(128) gaussian_filter_kernel(const float *__restrict__ pts, const float *__restrict__ nrm,
+                                                              const float *__restrict__ col, size_t n,
+                                                              const int32_t *__restrict__ idx, const float *__restrict__ d2, int k,
+                                                              float sigma2, float *o_pts, float *o_nrm, float *o_col) {
+    const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float tw = 0.f, rp[3] = {0.f, 0.f, 0.f}, rn[3] = {0.f, 0.f, 0.f}, rc[3] = {0.f, 0.f, 0.f};
+    for (int s = 0; s < k; ++s) {
+        const int j = idx[i * k + s];
+        if (j < 0) continue;
+        const float w = (float)exp(-0.5 * (double)d2[i * k + s] / (double)sigma2);
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+            rp[a] = __fadd_rn(rp[a], __fmul_rn(w, pts[3 * (size_t)j + a]));
+            if (nrm) rn[a] = __fadd_rn(rn[a], __fmul_rn(w, nrm[3 * (size_t)j + a]));
+            if (col) rc[a] = __fadd_rn(rc[a], __fmul_rn(w, col[3 * (size_t)j + a]));
+        }
+        tw = __fadd_rn(tw, w);
+    }
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        o_pts[3 * i + a] = __fdiv_rn(rp[a], tw);
+        if (nrm) o_nrm[3 * i + a] = __fdiv_rn(rn[a], tw);
+        if (col) o_col[3 * i + a] = __fdiv_rn(rc[a], tw);
+    }
+}
+
+extern "C" int cphb_gaussian_filter(const float *points, const float *normals, const float *colors, size_t n, float search_radius,
+                                    float sigma2, int num_max_search_points, float *out_points, float *out_normals,
+                                    float *out_colors, size_t *h_n_out, void *stream) {
+    cudaStream_t s = (cudaStream_t)stream;
+    if (!h_n_out) {
+        cphb_set_error("cphb_gaussian_filter: null argument");
+        return CPHB_ERR_INVALID;
+    }
+    *h_n_out = 0;
+    // pointcloud.cu:390-395: illegal parameters are logged and an empty cloud is returned
+    if (search_radius <= 0.f || sigma2 <= 0.f || num_max_search_points <= 0 || n == 0) return CPHB_OK;
+    if (!points || !out_points || (normals && !out_normals) || (colors && !out_colors)) {
+        cphb_set_error("cphb_gaussian_filter: null argument");
+        return CPHB_ERR_INVALID;
+    }
+    if (num_max_search_points > 100) {
+        cphb_set_error("cphb_gaussian_filter: num_max_search_points = %d exceeds NUM_MAX_NN (100)", num_max_search_points);
+        return CPHB_ERR_INVALID;
+    }
+    const int k = num_max_search_points;
+    cphb_index *ix = nullptr;
+    int rc = cphb_index_create(points, n, stream, &ix);
+    if (rc) return rc;
+    int32_t *idx = nullptr;
+    float *d2 = nullptr;
+    rc = cphb_alloc_async((void **)&idx, sizeof(int32_t) * n * k, s);
+    if (!rc) rc = cphb_alloc_async((void **)&d2, sizeof(float) * n * k, s);
+    if (!rc) rc = cphb_search_radius(ix, points, n, search_radius, k, idx, d2, nullptr, stream);
+    if (!rc) {
+        CPHB_LAUNCH(gaussian_filter_kernel, (unsigned)((n + 127) / 128), 128, 0, s, points, normals, colors, n, idx, d2, k, sigma2,
+                    out_points, out_normals, out_colors);
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) { cphb_set_error("gaussian_filter_kernel: %s", cudaGetErrorString(e)); rc = CPHB_ERR_CUDA; }
+    }
+    cphb_free_async(idx, s);
+    cphb_free_async(d2, s);
+    cudaStreamSynchronize(s);
+    cphb_index_destroy(ix);
+    if (!rc) *h_n_out = n;
+    return rc;
+}
+
 // PointCloud::SelectByIndex (down_sample.cu:40-127): gather of the rows named by indices, in the order given
 __global__ void __launch_bounds__(256) select_rows_kernel(const float *__restrict__ points, const float *__restrict__ normals,
                                                           const float *__restrict__ colors, size_t n,

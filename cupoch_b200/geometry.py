@@ -194,6 +194,24 @@ class PointCloud:
         self.last_outlier_stats = tuple(float(x) for x in stats)  # (cloud mean, std, threshold): diagnostics
         return self._filtered(d_idx, m.value)
 
+    def gaussian_filter(self, search_radius, sigma2, num_max_search_points=50):
+        """PointCloud::GaussianFilter (pointcloud.cu:387-433) -> new cloud (empty for illegal parameters)"""
+        out = PointCloud()
+        n = len(self)
+        if n == 0:
+            return out
+        hn, hc = self.has_normals(), self.has_colors()
+        op = DeviceArray((n, 3), np.float32)
+        on = DeviceArray((n, 3), np.float32) if hn else None
+        oc = DeviceArray((n, 3), np.float32) if hc else None
+        m = C.c_size_t(0)
+        _lib.check(_lib.lib().cphb_gaussian_filter(
+            self._points.ptr, self._normals.ptr if hn else None, self._colors.ptr if hc else None, n, float(search_radius),
+            float(sigma2), int(num_max_search_points), op.ptr, on.ptr if hn else None, oc.ptr if hc else None, C.byref(m), None))
+        if m.value:
+            out._points, out._normals, out._colors = op, on, oc
+        return out
+
     def estimate_normals(self, search_param=None):
         """PointCloud::EstimateNormals (estimate_normals.cu:82-127)."""
         search_param = search_param or KDTreeSearchParamKNN()

@@ -371,6 +371,25 @@ public:
                                                             &m, nullptr, nullptr));
         return finish_filter(kept, m);
     }
+    /// PointCloud::GaussianFilter (pointcloud.cu:387-433)
+    std::shared_ptr<PointCloud> GaussianFilter(float search_radius, float sigma2, size_t num_max_search_points = 50) const {
+        auto out = std::make_shared<PointCloud>();
+        if (search_radius <= 0 || sigma2 <= 0 || num_max_search_points <= 0) {
+            utility::LogError("[GaussianFilter] Illegal input parameters, radius and sigma2 must be positive.");
+            return out;
+        }
+        const size_t n = points_.size();
+        if (n == 0) return out;
+        const bool hn = HasNormals(), hc = HasColors();
+        out->points_.resize(n);
+        if (hn) out->normals_.resize(n);
+        if (hc) out->colors_.resize(n);
+        size_t m = 0;
+        utility::check(cphb_gaussian_filter(cfp(points_), hn ? cfp(normals_) : nullptr, hc ? cfp(colors_) : nullptr, n, search_radius,
+                                            sigma2, (int)num_max_search_points, fp(out->points_), hn ? fp(out->normals_) : nullptr,
+                                            hc ? fp(out->colors_) : nullptr, &m, nullptr));
+        return out;
+    }
     cphb_cloud view() const {
         cphb_cloud c;
         std::memset(&c, 0, sizeof(c));

@@ -163,6 +163,13 @@ int cphb_remove_radius_outliers(const float *points, size_t n, int nb_points, fl
  * threshold}.  Outputs as above. */
 int cphb_remove_statistical_outliers(const float *points, size_t n, int nb_neighbors, float std_ratio,
                                      int32_t *indices_out, size_t *h_n_out, float h_stats[3], void *stream);
+/* PointCloud::GaussianFilter (pointcloud.cu:56-106,387-433): radius search of the cloud against itself
+ * (search_radius, num_max_search_points <= 100), every row replaced by the exp(-0.5 d2 / sigma2)-weighted mean of
+ * its neighbours' rows.  normals / colors in and out may be NULL (together); outputs hold n rows; *h_n_out = n, or
+ * 0 for illegal parameters (the reference returns an empty cloud).  Synchronises. */
+int cphb_gaussian_filter(const float *points, const float *normals, const float *colors, size_t n,
+                         float search_radius, float sigma2, int num_max_search_points, float *out_points,
+                         float *out_normals, float *out_colors, size_t *h_n_out, void *stream);
 /* PointCloud::SelectByIndex (down_sample.cu:40-127, invert = false): out row t = in row indices[t].
  * normals / colors in and out may be NULL (together). */
 int cphb_select_by_index(const float *points, const float *normals, const float *colors, size_t n,

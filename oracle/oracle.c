@@ -692,6 +692,43 @@ int orc_remove_statistical_outliers(const float *pts, int n, int nb_neighbors, f
     return m;
 }
 
+/* pointcloud.cu:56-106,387-433 PointCloud::GaussianFilter: radius search of the cloud against itself
+ * (search_radius, num_max_search_points); every output row is the weighted mean of the found neighbours' rows with
+ * weight = exp(-0.5 * d2 / sigma2) -- the product and the exponential are evaluated in double (the literal 0.5
+ * promotes them) and rounded to float; sums are sequential float32 in slot order.  Returns 0 (and writes nothing)
+ * for illegal parameters, as the reference returns an empty cloud. */
+int orc_gaussian_filter(const float *pts, const float *nrm, const float *col, int n, float radius, float sigma2, int max_nn,
+                        float *out_pts, float *out_nrm, float *out_col) {
+    if (radius <= 0.f || sigma2 <= 0.f || max_nn <= 0 || n <= 0) return 0;
+    int32_t *idx = (int32_t *)malloc(sizeof(int32_t) * (size_t)n * max_nn);
+    float *d2 = (float *)malloc(sizeof(float) * (size_t)n * max_nn);
+    orc_kdtree *t = orc_kdtree_build(pts, n);
+    orc_kdtree_search(t, pts, n, max_nn, radius, idx, d2);
+    for (int i = 0; i < n; ++i) {
+        float tw = 0.f, rp[3] = {0, 0, 0}, rn[3] = {0, 0, 0}, rc[3] = {0, 0, 0};
+        for (int s = 0; s < max_nn; ++s) {
+            const int j = idx[(size_t)i * max_nn + s];
+            if (j < 0) continue;
+            const float w = (float)exp(-0.5 * (double)d2[(size_t)i * max_nn + s] / (double)sigma2);
+            for (int a = 0; a < 3; ++a) {
+                rp[a] += w * pts[3 * j + a];
+                if (nrm) rn[a] += w * nrm[3 * j + a];
+                if (col) rc[a] += w * col[3 * j + a];
+            }
+            tw += w;
+        }
+        for (int a = 0; a < 3; ++a) {
+            out_pts[3 * i + a] = rp[a] / tw;
+            if (nrm) out_nrm[3 * i + a] = rn[a] / tw;
+            if (col) out_col[3 * i + a] = rc[a] / tw;
+        }
+    }
+    orc_kdtree_free(t);
+    free(idx);
+    free(d2);
+    return n;
+}
+
 /* generalized_icp.cu:18-61: Rx*diag(eps,1,1)*Rx^T, Rx = rotation e1 -> n */
 void orc_covariances_from_normals(const float *nrm, int n, float eps, float *out) {
 #pragma omp parallel for schedule(static)

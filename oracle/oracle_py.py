@@ -163,6 +163,21 @@ def voxel_grid_from_point_cloud(pts, voxel, lo=None, hi=None, colors=None):
     return keys[:m].copy(), out[:m].copy(), mn.copy()
 
 
+def gaussian_filter(pts, radius, sigma2, max_nn=50, normals=None, colors=None):
+    """PointCloud::GaussianFilter (pointcloud.cu:387-433) -> (points, normals or None, colors or None); empty arrays
+    for illegal parameters"""
+    pts = _f(pts).reshape(-1, 3)
+    nrm = None if normals is None else _f(normals).reshape(-1, 3)
+    col = None if colors is None else _f(colors).reshape(-1, 3)
+    op = np.empty_like(pts)
+    on = None if nrm is None else np.empty_like(pts)
+    oc = None if col is None else np.empty_like(pts)
+    m = lib().orc_gaussian_filter(_p(pts), _p(nrm), _p(col), C.c_int(len(pts)), C.c_float(radius), C.c_float(sigma2),
+                                  C.c_int(max_nn), _p(op), _p(on), _p(oc))
+    cut = (lambda a: None if a is None else a[:m])
+    return cut(op), cut(on), cut(oc)
+
+
 def remove_radius_outliers(pts, nb_points, radius):
     """-> ascending indices of the kept points (down_sample.cu:317-354)"""
     pts = _f(pts).reshape(-1, 3)

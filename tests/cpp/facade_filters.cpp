@@ -5,6 +5,7 @@
 //   tests/geometry/voxelgrid.cpp:40-68     VoxelGrid.GetVoxel, VoxelGrid.CreateFromPointCloudWithinBounds
 // plus RemoveStatisticalOutliers on a cloud with planted outliers.  Exit code 0 = all expectations met.
 #include <algorithm>
+#include <cmath>
 #include <cstdio>
 #include <vector>
 
@@ -63,6 +64,14 @@ int main() {
         EXPECT(std::is_sorted(idx.begin(), idx.end()));
         for (size_t i : idx) EXPECT(i < n_in);  // the planted outliers are gone
         EXPECT(std::get<0>(res)->GetPoints().size() == idx.size());
+        // GaussianFilter: a lattice point strictly inside keeps its place (symmetric neighbourhood), sizes are kept
+        auto smooth = pcd.GaussianFilter(0.15f, 0.01f, 30);
+        auto sp = smooth->GetPoints();
+        EXPECT(sp.size() == points.size());
+        const size_t mid = (10 * 20 + 10) * 5 + 2;  // lattice node (10, 10, 2)
+        if (sp.size() == points.size())
+            EXPECT(std::fabs(sp[mid][0] - 1.0f) < 1e-4f && std::fabs(sp[mid][1] - 1.0f) < 1e-4f && std::fabs(sp[mid][2] - 0.2f) < 1e-4f);
+        EXPECT(pcd.GaussianFilter(0.0f, 0.01f, 30)->IsEmpty());
     }
     {   // VoxelGrid
         geometry::VoxelGrid g;

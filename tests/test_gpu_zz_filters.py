@@ -125,3 +125,17 @@ def test_facade_known_answers():
     exe = build_facade("facade_filters")
     r = subprocess.run([exe], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stdout + r.stderr
+
+
+def test_gaussian_filter_vs_oracle(orc):
+    """PointCloud::GaussianFilter (pointcloud.cu:387-433): same neighbours, same slot order, same float32 sums; the
+    double-precision exp may differ in its last bit between libm and CUDA, hence 1e-6 relative."""
+    pts, nrm, col = _cloud(30000, 13, outliers=0)
+    pc = cph.geometry.PointCloud(pts)
+    pc.normals, pc.colors = nrm, col
+    out = pc.gaussian_filter(0.06, 0.001, 30)
+    rp, rn, rc = orc.gaussian_filter(pts, 0.06, 0.001, 30, normals=nrm, colors=col)
+    np.testing.assert_allclose(out.points.cpu(), rp, rtol=1e-6, atol=1e-7)
+    np.testing.assert_allclose(out.normals.cpu(), rn, rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(out.colors.cpu(), rc, rtol=1e-6, atol=1e-7)
+    assert len(pc.gaussian_filter(0.0, 0.001, 30)) == 0 and len(pc.gaussian_filter(0.06, -1.0, 30)) == 0

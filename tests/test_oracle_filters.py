@@ -75,3 +75,23 @@ def test_voxel_grid_oracle(orc):
         if lo is not None:
             assert k.min() < 0                                    # points below the bound are not clipped
     assert len(orc.voxel_grid_from_point_cloud(pts, 0.0)[0]) == 0
+
+
+def test_gaussian_filter_oracle(orc):
+    """pointcloud.cu:56-106,387-433 vs a float64 numpy restatement"""
+    rng = np.random.default_rng(6)
+    pts = rng.random((2000, 3), dtype=np.float32)
+    col = rng.random((2000, 3), dtype=np.float32)
+    r, sigma2, k = 0.12, 0.003, 40
+    op, on, oc = orc.gaussian_filter(pts, r, sigma2, k, colors=col)
+    assert on is None and op.shape == pts.shape
+    d2 = _brute_d2(pts)
+    rr = float(np.float32(r) * np.float32(r))
+    for i in range(0, 2000, 37):
+        order = np.argsort(d2[i], kind="stable")[:k]
+        order = order[d2[i][order] < rr]
+        w = np.exp(-0.5 * d2[i][order] / float(np.float32(sigma2)))
+        np.testing.assert_allclose(op[i], (w[:, None] * pts[order]).sum(0) / w.sum(), rtol=2e-5, atol=1e-6)
+        np.testing.assert_allclose(oc[i], (w[:, None] * col[order]).sum(0) / w.sum(), rtol=2e-5, atol=1e-6)
+    for bad in ((0.0, sigma2, k), (r, 0.0, k), (r, sigma2, 0)):
+        assert len(orc.gaussian_filter(pts, *bad)[0]) == 0
