@@ -93,6 +93,48 @@ extern "C" int cphb_estimate_normals(const float *points, size_t n, int knn, flo
     return rc;
 }
 
+// Multi-GPU building block: normals of the points [first, first + count) only, neighbours taken
+// from the whole cloud.  Every rank indexes the full cloud and estimates its own block; the blocks are then
+// all-gathered (cupoch_b200.distributed.estimate_normals).  Same kernels as cphb_estimate_normals: rows of the
+// neighbour table index the full point array, so a block of query rows needs nothing new.
+extern "C" int cphb_estimate_normals_range(const float *points, size_t n, int knn, float radius, int max_nn, size_t first,
+                                           size_t count, float *out_normals, void *stream) {
+    cudaStream_t s = (cudaStream_t)stream;
+    if (count == 0) return CPHB_OK;
+    if (!points || !out_normals || first > n || count > n - first) {
+        cphb_set_error("cphb_estimate_normals_range: invalid argument");
+        return CPHB_ERR_INVALID;
+    }
+    const int k = (knn > 0) ? knn : max_nn;
+    if (k <= 0) {
+        CPHB_LAUNCH(fill_normals_kernel, (unsigned)((count + 255) / 256), 256, 0, s, out_normals, count);
+        CPHB_CHECK_LAUNCH();
+        return CPHB_OK;
+    }
+    cphb_index *ix = nullptr;
+    int rc = cphb_index_create(points, n, stream, &ix);
+    if (rc) return rc;
+    int32_t *idx = nullptr;
+    float *d2 = nullptr;
+    rc = cphb_alloc_async((void **)&idx, sizeof(int32_t) * count * k, s);
+    if (!rc) rc = cphb_alloc_async((void **)&d2, sizeof(float) * count * k, s);
+    if (!rc) {
+        const float *q = points + 3 * first;
+        if (knn > 0) rc = cphb_search_knn(ix, q, count, k, idx, d2, nullptr, stream);
+        else rc = cphb_search_radius(ix, q, count, radius, k, idx, d2, nullptr, stream);
+    }
+    if (!rc) {
+        CPHB_LAUNCH(normals_kernel, (unsigned)((count + 127) / 128), 128, 0, s, points, count, idx, k, out_normals);
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) { cphb_set_error("normals_kernel: %s", cudaGetErrorString(e)); rc = CPHB_ERR_CUDA; }
+    }
+    cphb_free_async(idx, s);
+    cphb_free_async(d2, s);
+    cudaStreamSynchronize(s);
+    cphb_index_destroy(ix);
+    return rc;
+}
+
 // GetRotationFromE1ToX + Rx*diag(eps,1,1)*Rx^T (generalized_icp.cu:18-30,53-60)
 __global__ void __launch_bounds__(256) cov_from_normals_kernel(const float *__restrict__ nrm, size_t n, float eps,
                                                                float *out, int col_major) {

@@ -88,3 +88,53 @@ def gather_correspondences(dist, local_corr, lo, world):
     dist.all_gather_object(out, mine)
     allc = np.concatenate(out, 0) if out else mine
     return allc[np.argsort(allc[:, 0], kind="stable")]
+
+
+def all_gather_rows(dist, local_rows, n_total, world, device=None):
+    """All-gather of contiguous row blocks (rank r holds rows shard_range(n_total, r, world)) into the full
+    [n_total, ...] array, on whatever device the process group works on (gloo: host, nccl: device)."""
+    import numpy as np
+    import torch
+    local_rows = np.ascontiguousarray(local_rows)
+    width = local_rows.shape[1:]
+    biggest = max(shard_range(n_total, r, world)[1] - shard_range(n_total, r, world)[0] for r in range(world))
+    pad = np.zeros((biggest,) + width, local_rows.dtype)
+    pad[:len(local_rows)] = local_rows
+    t = torch.from_numpy(pad)
+    if device is not None:
+        t = t.to(device)
+    parts = [torch.empty_like(t) for _ in range(world)]
+    dist.all_gather(parts, t)
+    out = np.empty((n_total,) + width, local_rows.dtype)
+    for r in range(world):
+        lo, hi = shard_range(n_total, r, world)
+        out[lo:hi] = parts[r][:hi - lo].cpu().numpy()
+    return out
+
+
+def estimate_normals(cloud, search_param, dist, rank, world, device=None, local_fn=None):
+    """PointCloud::EstimateNormals over `world` ranks (SURVEY 8e: replicate the index, shard the queries, no
+    collective in the search; one all-gather of the per-point outputs).  Every rank holds the full cloud, estimates
+    the normals of its contiguous block with cphb_estimate_normals_range and all-gathers the blocks: the result is
+    bit-identical to the single-GPU estimate.  `local_fn(points, first, count) -> [count, 3]` replaces the library
+    call in the gloo/CPU test of this orchestration."""
+    import numpy as np
+    from . import geometry
+    from .utility import DeviceArray
+    n = len(cloud)
+    lo, hi = shard_range(n, rank, world)
+    if local_fn is None:
+        sp = search_param or geometry.KDTreeSearchParamKNN()
+        if isinstance(sp, geometry.KDTreeSearchParamKNN):
+            knn, radius, max_nn = sp.knn, 0.0, 0
+        else:
+            knn, radius, max_nn = 0, sp.radius, sp.max_nn
+        out = DeviceArray((max(hi - lo, 1), 3), np.float32)
+        _lib.check(_lib.lib().cphb_estimate_normals_range(cloud._points.ptr, n, knn, radius, max_nn, lo, hi - lo, out.ptr, None))
+        mine = out.cpu(hi - lo)
+    else:
+        mine = np.asarray(local_fn(cloud, lo, hi - lo), np.float32).reshape(-1, 3)
+    full = all_gather_rows(dist, mine, n, world, device)
+    if hasattr(cloud, "normals"):
+        cloud.normals = full
+    return full

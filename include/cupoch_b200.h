@@ -132,6 +132,11 @@ int cphb_voxel_down_sample(const float *points, const float *normals, const floa
  * (k includes the point itself, default 30); knn<=0: radius + max_nn. */
 int cphb_estimate_normals(const float *points, size_t n, int knn, float radius, int max_nn,
                           float *out_normals, void *stream);
+/* Multi-GPU building block: the normals of points [first, first + count) only (out_normals holds count rows),
+ * neighbours searched in the whole cloud.  Ranks estimate disjoint blocks and all-gather them; the union equals
+ * cphb_estimate_normals bit for bit (same search, same per-point arithmetic). */
+int cphb_estimate_normals_range(const float *points, size_t n, int knn, float radius, int max_nn, size_t first,
+                                size_t count, float *out_normals, void *stream);
 /* InitializePointCloudForGeneralizedICP covariance step (generalized_icp.cu:53-60). */
 int cphb_covariances_from_normals(const float *normals, size_t n, float epsilon,
                                   float *out_cov, int cov_col_major, void *stream);

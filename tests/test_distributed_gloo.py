@@ -87,3 +87,52 @@ def test_sharded_sums_equal_global_sums(orc):
     # float64 sums agree to ~1e-16: the float32 system every rank solves is identical
     a, b = red[:27].astype(np.float32), sums[:27].astype(np.float32)
     assert (np.abs(a.view(np.int32) - b.view(np.int32)) <= 1).all()
+
+
+def _normals_worker(rank, world, port, q):
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    from oracle import oracle_py as orc
+    from cupoch_b200 import distributed
+    from cupoch_b200.testing import datagen
+    pts, _ = datagen.surface(5001, 17)                      # odd size: unequal blocks
+
+    class Cloud:                                            # what the orchestration needs of a PointCloud
+        def __len__(self):
+            return len(pts)
+
+    def local(cloud, first, count):                         # stand-in for cphb_estimate_normals_range
+        idx, _, _ = orc.search(pts, pts[first:first + count], 20, kdtree=True)
+        full = np.full((len(pts), 20), -1, np.int32)
+        full[:count] = idx                                  # rows index the whole cloud
+        return orc.normals_from_neighbors(pts, full)[:count]
+
+    c = Cloud()
+    full = distributed.estimate_normals(c, None, dist, rank, world, local_fn=local)
+    if rank == 1:
+        q.put(full)
+    dist.destroy_process_group()
+
+
+def test_sharded_estimate_normals_equals_single(orc):
+    """replicate the index, shard the queries, all-gather the per-point outputs -- the gathered normals
+    are the single-process normals bit for bit (world 2, blocks of unequal size)."""
+    import torch.multiprocessing as mp
+    from cupoch_b200.testing import datagen
+    world, port = 2, _free_port()
+    ctx = mp.get_context("spawn")
+    q = ctx.SimpleQueue()
+    procs = [ctx.Process(target=_normals_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    got = q.get()
+    for p in procs:
+        p.join(60)
+        assert p.exitcode == 0
+    pts, _ = datagen.surface(5001, 17)
+    ref = orc.estimate_normals(pts, knn=20)
+    np.testing.assert_array_equal(got, ref)

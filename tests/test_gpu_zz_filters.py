@@ -139,3 +139,29 @@ def test_gaussian_filter_vs_oracle(orc):
     np.testing.assert_allclose(out.normals.cpu(), rn, rtol=1e-5, atol=1e-6)
     np.testing.assert_allclose(out.colors.cpu(), rc, rtol=1e-6, atol=1e-7)
     assert len(pc.gaussian_filter(0.0, 0.001, 30)) == 0 and len(pc.gaussian_filter(0.06, -1.0, 30)) == 0
+
+
+def test_estimate_normals_range_blocks_equal_whole():
+    """cphb_estimate_normals_range (the multi-GPU building block): three disjoint blocks estimated separately equal
+    the whole-cloud estimate bit for bit."""
+    import ctypes as C
+    from cupoch_b200 import _lib
+    from cupoch_b200.distributed import shard_range
+    from cupoch_b200.utility import DeviceArray
+    pts, _, _ = _cloud(30001, 17, outliers=0)
+    pc = cph.geometry.PointCloud(pts)
+    pc.estimate_normals(cph.geometry.KDTreeSearchParamKNN(20))
+    whole = pc.normals.cpu()
+    parts = []
+    for r in range(3):
+        lo, hi = shard_range(len(pts), r, 3)
+        out = DeviceArray((hi - lo, 3), np.float32)
+        _lib.check(_lib.lib().cphb_estimate_normals_range(pc.points.ptr, len(pts), 20, 0.0, 0, lo, hi - lo, out.ptr, None))
+        parts.append(out.cpu())
+    np.testing.assert_array_equal(np.concatenate(parts), whole)
+    pc2 = cph.geometry.PointCloud(pts)
+    pc2.estimate_normals(cph.geometry.KDTreeSearchParamRadius(0.05, 30))
+    lo, hi = shard_range(len(pts), 1, 3)
+    out = DeviceArray((hi - lo, 3), np.float32)
+    _lib.check(_lib.lib().cphb_estimate_normals_range(pc2.points.ptr, len(pts), 0, 0.05, 30, lo, hi - lo, out.ptr, None))
+    np.testing.assert_array_equal(out.cpu(), pc2.normals.cpu()[lo:hi])
