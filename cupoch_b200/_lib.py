@@ -55,6 +55,9 @@ _SIGNATURES = {
     "cphb_transform": (C.c_int, [_P, _P, _P, C.c_int, C.c_size_t, C.POINTER(C.c_float), _P]),
     "cphb_min_max_bound": (C.c_int, [_P, C.c_size_t, C.POINTER(C.c_float), C.POINTER(C.c_float), _P]),
     "cphb_voxel_down_sample": (C.c_int, [_P, _P, _P, C.c_size_t, C.c_float, _P, _P, _P, C.POINTER(C.c_size_t), _P]),
+    "cphb_voxel_down_sample_origin": (C.c_int, [_P, _P, _P, C.c_size_t, C.c_float, C.POINTER(C.c_float), _P, _P, _P,
+                                                C.POINTER(C.c_size_t), _P]),
+    "cphb_voxel_indices": (C.c_int, [_P, C.c_size_t, C.c_float, C.POINTER(C.c_float), _P, _P]),
     "cphb_estimate_normals": (C.c_int, [_P, C.c_size_t, C.c_int, C.c_float, C.c_int, _P, _P]),
     "cphb_estimate_normals_range": (C.c_int, [_P, C.c_size_t, C.c_int, C.c_float, C.c_int, C.c_size_t, C.c_size_t, _P, _P]),
     "cphb_remove_radius_outliers": (C.c_int, [_P, C.c_size_t, C.c_int, C.c_float, _P, C.POINTER(C.c_size_t), _P]),

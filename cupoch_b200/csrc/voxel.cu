@@ -164,9 +164,12 @@ static int bits_for(double cells) {
     return b;
 }
 
-extern "C" int cphb_voxel_down_sample(const float *points, const float *normals, const float *colors, size_t n,
-                                      float voxel_size, float *out_points, float *out_normals, float *out_colors,
-                                      size_t *h_n_out, void *stream) {
+// h_origin == nullptr: the reference's origin, min_bound - voxel/2 (down_sample.cu:180).  A caller-supplied origin
+// (<= every point, component-wise) lets several ranks down-sample disjoint parts of one cloud on ONE common grid
+// (cupoch_b200.distributed.voxel_down_sample).
+static int voxel_down_sample_impl(const float *points, const float *normals, const float *colors, size_t n,
+                                  float voxel_size, const float *h_origin, float *out_points, float *out_normals,
+                                  float *out_colors, size_t *h_n_out, void *stream) {
     cudaStream_t s = (cudaStream_t)stream;
     if (!h_n_out) {
         cphb_set_error("cphb_voxel_down_sample: h_n_out is null");
@@ -190,7 +193,11 @@ extern "C" int cphb_voxel_down_sample(const float *points, const float *normals,
     float ext = 0.f;
     double cells = 1.0, dims[3];
     for (int a = 0; a < 3; ++a) {
-        g.org[a] = mn[a] - voxel_size * 0.5f;       // :180
+        g.org[a] = h_origin ? h_origin[a] : mn[a] - voxel_size * 0.5f;       // :180
+        if (h_origin && !(h_origin[a] <= mn[a])) {
+            cphb_set_error("cphb_voxel_down_sample_origin: origin[%d] = %g lies above the cloud's minimum %g", a, h_origin[a], mn[a]);
+            return CPHB_ERR_INVALID;
+        }
         float hi = mx[a] + voxel_size * 0.5f;       // :181
         if (hi - g.org[a] > ext) ext = hi - g.org[a];
         dims[a] = (double)floorf((mx[a] - g.org[a]) / voxel_size) + 1.0;
@@ -255,4 +262,22 @@ extern "C" int cphb_voxel_down_sample(const float *points, const float *normals,
     CPHB_CUDA(cudaStreamSynchronize(s));
     *h_n_out = n_out;
     return CPHB_OK;
+}
+
+extern "C" int cphb_voxel_down_sample(const float *points, const float *normals, const float *colors, size_t n,
+                                      float voxel_size, float *out_points, float *out_normals, float *out_colors,
+                                      size_t *h_n_out, void *stream) {
+    return voxel_down_sample_impl(points, normals, colors, n, voxel_size, nullptr, out_points, out_normals, out_colors, h_n_out,
+                                  stream);
+}
+
+extern "C" int cphb_voxel_down_sample_origin(const float *points, const float *normals, const float *colors, size_t n,
+                                             float voxel_size, const float h_origin[3], float *out_points, float *out_normals,
+                                             float *out_colors, size_t *h_n_out, void *stream) {
+    if (!h_origin) {
+        cphb_set_error("cphb_voxel_down_sample_origin: origin is null");
+        return CPHB_ERR_INVALID;
+    }
+    return voxel_down_sample_impl(points, normals, colors, n, voxel_size, h_origin, out_points, out_normals, out_colors, h_n_out,
+                                  stream);
 }

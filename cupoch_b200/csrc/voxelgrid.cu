@@ -160,3 +160,29 @@ extern "C" int cphb_voxel_grid_from_point_cloud(const float *points, const float
     if (!rc) *h_n_out = n_out;
     return rc;
 }
+
+// Batched VoxelGrid::GetVoxel (voxelgrid.cu:338-341): out[i] = floor((p_i - origin) / voxel_size) per axis, the
+// arithmetic every voxel kernel of this library uses for its keys -- callers that must agree with those keys (the
+// slab partition of the sharded VoxelDownSample) take the indices from here instead of recomputing them.
+__global__ void __launch_bounds__(256) vg_indices_kernel(const float *__restrict__ pts, size_t n, float ox, float oy, float oz,
+                                                         float voxel, int32_t *__restrict__ out) {
+    const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    out[3 * i] = vg_index(pts[3 * i], ox, voxel);
+    out[3 * i + 1] = vg_index(pts[3 * i + 1], oy, voxel);
+    out[3 * i + 2] = vg_index(pts[3 * i + 2], oz, voxel);
+}
+
+extern "C" int cphb_voxel_indices(const float *points, size_t n, float voxel_size, const float h_origin[3], int32_t *out_indices,
+                                  void *stream) {
+    cudaStream_t s = (cudaStream_t)stream;
+    if (n == 0) return CPHB_OK;
+    if (!points || !h_origin || !out_indices || !(voxel_size > 0.f)) {
+        cphb_set_error("cphb_voxel_indices: invalid argument");
+        return CPHB_ERR_INVALID;
+    }
+    CPHB_LAUNCH(vg_indices_kernel, (unsigned)((n + 255) / 256), 256, 0, s, points, n, h_origin[0], h_origin[1], h_origin[2], voxel_size,
+                out_indices);
+    CPHB_CHECK_LAUNCH();
+    return CPHB_OK;
+}

@@ -128,6 +128,16 @@ int cphb_voxel_down_sample(const float *points, const float *normals, const floa
                            size_t n, float voxel_size, float *out_points, float *out_normals,
                            float *out_colors, size_t *h_n_out, void *stream);
 
+/* The same with a caller-supplied grid origin (every component <= the cloud's minimum): several ranks can
+ * down-sample disjoint parts of one cloud on one common grid (cupoch_b200.distributed.voxel_down_sample). */
+int cphb_voxel_down_sample_origin(const float *points, const float *normals, const float *colors,
+                                  size_t n, float voxel_size, const float h_origin[3], float *out_points,
+                                  float *out_normals, float *out_colors, size_t *h_n_out, void *stream);
+/* Batched VoxelGrid::GetVoxel (voxelgrid.cu:338-341): out_indices (device, n x 3 int32) =
+ * floor((p - origin) / voxel_size), the key arithmetic of every voxel kernel in this library. */
+int cphb_voxel_indices(const float *points, size_t n, float voxel_size, const float h_origin[3],
+                       int32_t *out_indices, void *stream);
+
 /* PointCloud::EstimateNormals (estimate_normals.cu:82-127).  knn>0: KNN search
  * (k includes the point itself, default 30); knn<=0: radius + max_nn. */
 int cphb_estimate_normals(const float *points, size_t n, int knn, float radius, int max_nn,

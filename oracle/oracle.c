@@ -314,16 +314,18 @@ static int vkey_cmp(const void *a, const void *b) {
         if (x->k[c] != y->k[c]) return x->k[c] < y->k[c] ? -1 : 1;
     return (x->i < y->i) ? -1 : (x->i > y->i);
 }
-int orc_voxel_down_sample(const float *pts, const float *nrm, const float *col,
-                          int n, float voxel, float *out_pts, float *out_nrm,
-                          float *out_col) {
+/* origin == NULL: the reference's own origin (:180); otherwise a caller-supplied common grid origin (the sharded
+ * down-sample of tests/test_distributed_gloo.py) */
+int orc_voxel_down_sample_origin(const float *pts, const float *nrm, const float *col,
+                                 int n, float voxel, const float *origin, float *out_pts, float *out_nrm,
+                                 float *out_col) {
     if (voxel <= 0.0f || n <= 0) return 0;
     float mn[3], mx[3], org[3];
     orc_min_bound(pts, n, mn);
     orc_max_bound(pts, n, mx);
     float ext = 0.f;
     for (int a = 0; a < 3; ++a) {
-        org[a] = mn[a] - voxel * 0.5f;            /* :180 */
+        org[a] = origin ? origin[a] : mn[a] - voxel * 0.5f;            /* :180 */
         float hi = mx[a] + voxel * 0.5f;          /* :181 */
         if (hi - org[a] > ext) ext = hi - org[a];
     }
@@ -365,6 +367,11 @@ int orc_voxel_down_sample(const float *pts, const float *nrm, const float *col,
     }
     free(keys);
     return n_out;
+}
+int orc_voxel_down_sample(const float *pts, const float *nrm, const float *col,
+                          int n, float voxel, float *out_pts, float *out_nrm,
+                          float *out_col) {
+    return orc_voxel_down_sample_origin(pts, nrm, col, n, voxel, NULL, out_pts, out_nrm, out_col);
 }
 
 /* ======================================================================== */

@@ -129,13 +129,16 @@ def max_bound(p):
     return o
 
 
-def voxel_down_sample(pts, voxel, normals=None, colors=None):
+def voxel_down_sample(pts, voxel, normals=None, colors=None, origin=None):
+    """origin=None: the reference's grid origin (min_bound - voxel/2); else a caller-supplied common origin"""
     pts, normals, colors = _f(pts).reshape(-1, 3), _f(normals), _f(colors)
     n = len(pts)
     op = np.empty((n, 3), np.float32)
     on = np.empty((n, 3), np.float32) if normals is not None else None
     oc = np.empty((n, 3), np.float32) if colors is not None else None
-    m = lib().orc_voxel_down_sample(_p(pts), _p(normals), _p(colors), C.c_int(n), C.c_float(voxel), _p(op), _p(on), _p(oc))
+    org = None if origin is None else _f(origin).reshape(3)
+    m = lib().orc_voxel_down_sample_origin(_p(pts), _p(normals), _p(colors), C.c_int(n), C.c_float(voxel), _p(org), _p(op),
+                                           _p(on), _p(oc))
     return op[:m].copy(), (on[:m].copy() if on is not None else None), (oc[:m].copy() if oc is not None else None)
 
 

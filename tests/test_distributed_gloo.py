@@ -136,3 +136,79 @@ def test_sharded_estimate_normals_equals_single(orc):
     pts, _ = datagen.surface(5001, 17)
     ref = orc.estimate_normals(pts, knn=20)
     np.testing.assert_array_equal(got, ref)
+
+
+class _CpuVoxelOps:
+    """CPU stand-in for the three library calls of distributed.voxel_down_sample (the oracle's arithmetic)"""
+
+    def __init__(self, orc):
+        self.orc = orc
+
+    def bounds(self, points):
+        p = points.numpy()
+        return self.orc.min_bound(p), self.orc.max_bound(p)
+
+    def indices(self, points, voxel, origin):
+        import torch
+        p = points.numpy()
+        return torch.from_numpy(np.floor((p - np.asarray(origin, np.float32)) / np.float32(voxel)).astype(np.int32))
+
+    def down_sample(self, points, normals, colors, voxel, origin):
+        import torch
+        op, on, oc = self.orc.voxel_down_sample(points.numpy(), float(voxel), None if normals is None else normals.numpy(),
+                                                None if colors is None else colors.numpy(), origin=origin)
+        f = (lambda a: None if a is None else torch.from_numpy(a))
+        return f(op), f(on), f(oc)
+
+
+def _voxel_worker(rank, world, port, q):
+    import torch
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    from oracle import oracle_py as orc
+    from cupoch_b200 import distributed
+    rng = np.random.default_rng(5)
+    pts = (rng.random((20011, 3), dtype=np.float32) * np.array([4, 4, 1], np.float32)).astype(np.float32)
+    nrm = rng.standard_normal((20011, 3)).astype(np.float32)
+    col = rng.random((20011, 3), dtype=np.float32)
+    mine = np.arange(len(pts)) % world == rank            # an interleaved (non-spatial) partition of the input
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a[mine]))
+    out = distributed.voxel_down_sample(t(pts), 0.11, dist, rank, world, normals=t(nrm), colors=t(col), ops=_CpuVoxelOps(orc))
+    slab = distributed.voxel_down_sample(t(pts), 0.11, dist, rank, world, ops=_CpuVoxelOps(orc), gather=False)
+    none = distributed.voxel_down_sample(t(pts), 0.0, dist, rank, world, ops=_CpuVoxelOps(orc))
+    q.put((rank, [o.numpy() for o in out], slab[0].numpy(), none[0].shape[0]))
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_sharded_voxel_down_sample_equals_single(orc, world):
+    """common grid by all-reduce, slabs of x-indices, one all-to-all of the points, the ordinary kernel per
+    slab; rank-order concatenation == the single-process VoxelDownSample, bit for bit (points, normals, colours)."""
+    import torch.multiprocessing as mp
+    port = _free_port()
+    ctx = mp.get_context("spawn")
+    q = ctx.SimpleQueue()
+    procs = [ctx.Process(target=_voxel_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted([q.get() for _ in range(world)], key=lambda x: x[0])
+    for p in procs:
+        p.join(60)
+        assert p.exitcode == 0
+    rng = np.random.default_rng(5)
+    pts = (rng.random((20011, 3), dtype=np.float32) * np.array([4, 4, 1], np.float32)).astype(np.float32)
+    nrm = rng.standard_normal((20011, 3)).astype(np.float32)
+    col = rng.random((20011, 3), dtype=np.float32)
+    rp, rn, rc = orc.voxel_down_sample(pts, 0.11, nrm, col)
+    for rank, out, slab, n_none in res:
+        np.testing.assert_array_equal(out[0], rp)
+        np.testing.assert_array_equal(out[1], rn)
+        np.testing.assert_array_equal(out[2], rc)
+        assert n_none == 0
+    np.testing.assert_array_equal(np.concatenate([r[2] for r in res]), rp)      # slabs in rank order
+    sizes = [len(r[2]) for r in res]
+    assert min(sizes) > 0.5 * max(sizes)                                          # slabs are balanced

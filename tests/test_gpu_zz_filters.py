@@ -165,3 +165,44 @@ def test_estimate_normals_range_blocks_equal_whole():
     out = DeviceArray((hi - lo, 3), np.float32)
     _lib.check(_lib.lib().cphb_estimate_normals_range(pc2.points.ptr, len(pts), 0, 0.05, 30, lo, hi - lo, out.ptr, None))
     np.testing.assert_array_equal(out.cpu(), pc2.normals.cpu()[lo:hi])
+
+
+def test_voxel_origin_override_and_indices(orc):
+    """cphb_voxel_down_sample_origin with the reference's own origin == cphb_voxel_down_sample; with a lower common
+    origin == the oracle on that grid; cphb_voxel_indices == floor((p - origin) / voxel) in float32."""
+    import ctypes as C
+    from cupoch_b200 import _lib
+    from cupoch_b200.utility import DeviceArray
+    pts, nrm, col = _cloud(50000, 19, outliers=0)
+    pc = cph.geometry.PointCloud(pts)
+    pc.normals, pc.colors = nrm, col
+    voxel = np.float32(0.07)
+    ref = pc.voxel_down_sample(float(voxel))
+    L = _lib.lib()
+
+    def run(origin):
+        n = len(pts)
+        op, on, oc = (DeviceArray((n, 3), np.float32) for _ in range(3))
+        m = C.c_size_t(0)
+        org = (C.c_float * 3)(*[float(x) for x in origin])
+        _lib.check(L.cphb_voxel_down_sample_origin(pc.points.ptr, pc.normals.ptr, pc.colors.ptr, n, float(voxel), org, op.ptr,
+                                                   on.ptr, oc.ptr, C.byref(m), None))
+        return op.cpu(m.value), on.cpu(m.value), oc.cpu(m.value)
+
+    own = pts.min(0) - voxel * np.float32(0.5)
+    a = run(own)
+    np.testing.assert_array_equal(a[0], ref.points.cpu())
+    np.testing.assert_array_equal(a[1], ref.normals.cpu())
+    np.testing.assert_array_equal(a[2], ref.colors.cpu())
+    low = (own - np.float32(0.333)).astype(np.float32)
+    b = run(low)
+    rp, rn, rc = orc.voxel_down_sample(pts, float(voxel), nrm, col, origin=low)
+    np.testing.assert_array_equal(b[0], rp)
+    np.testing.assert_allclose(b[1], rn, rtol=1e-6, atol=1e-7)
+    np.testing.assert_array_equal(b[2], rc)
+    with pytest.raises(_lib.CphbError):
+        run(pts.min(0) + np.float32(0.01))            # an origin above the cloud's minimum is rejected
+    idx = DeviceArray((len(pts), 3), np.int32)
+    org = (C.c_float * 3)(*[float(x) for x in low])
+    _lib.check(L.cphb_voxel_indices(pc.points.ptr, len(pts), float(voxel), org, idx.ptr, None))
+    np.testing.assert_array_equal(idx.cpu(), np.floor((pts - low) / voxel).astype(np.int32))

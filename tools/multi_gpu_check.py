@@ -63,6 +63,38 @@ def main():
             out[kind]["corr_equal_1gpu"] = bool(np.array_equal(c, full.correspondence_set))
             out[kind].pop("T")
         out["single"] = {"fitness": full.fitness, "rmse": full.inlier_rmse, "loop_ms": full.loop_ms}
+    # ---- sharded pre-processing: VoxelDownSample by slabs + one all-to-all, EstimateNormals by blocks ----
+    try:
+        from cupoch_b200 import distributed
+        import time
+        nv = int(os.environ.get("CHECK_VOXEL_POINTS", "2000000"))
+        pts = datagen.uniform_cube(nv, 21, hi=(4, 4, 1))
+        col = datagen.uniform_cube(nv, 23)
+        mine = slice(*shard_range(nv, rank, world))
+        tp, tc = torch.from_numpy(pts[mine]).cuda(), torch.from_numpy(col[mine]).cuda()
+        distributed.voxel_down_sample(tp, 0.02, dist, rank, world, colors=tc)          # warm-up
+        torch.cuda.synchronize(); dist.barrier(); t0 = time.perf_counter()
+        vp, _, vc = distributed.voxel_down_sample(tp, 0.02, dist, rank, world, colors=tc)
+        torch.cuda.synchronize(); t1 = time.perf_counter()
+        pc = cph.geometry.PointCloud(pts)
+        pc.colors = col
+        ref = pc.voxel_down_sample(0.02)
+        same = bool(np.array_equal(vp.cpu().numpy(), ref.points.cpu()) and np.array_equal(vc.cpu().numpy(), ref.colors.cpu()))
+        nn = 300000
+        cloud = cph.geometry.PointCloud(pts[:nn])
+        full_n = distributed.estimate_normals(cloud, cph.geometry.KDTreeSearchParamKNN(20), dist, rank, world, device="cuda")
+        one = cph.geometry.PointCloud(pts[:nn])
+        one.estimate_normals(cph.geometry.KDTreeSearchParamKNN(20))
+        flags = torch.tensor([int(same), int(np.array_equal(full_n, one.normals.cpu()))], device="cuda")
+        dist.all_reduce(flags, op=dist.ReduceOp.MIN)
+        if rank == 0:
+            out["sharded_voxel_down_sample"] = {"points": nv, "n_out": int(vp.shape[0]), "equals_1gpu_on_every_rank": bool(flags[0].item()),
+                                                "ms": 1e3 * (t1 - t0)}
+            out["sharded_estimate_normals"] = {"points": nn, "equals_1gpu_on_every_rank": bool(flags[1].item())}
+    except Exception as e:  # keep the ICP part of the report even if the newer paths fail
+        if rank == 0:
+            out["sharded_preprocessing_error"] = repr(e)
+    if rank == 0:
         print(json.dumps(out))
     dist.destroy_process_group()
 
