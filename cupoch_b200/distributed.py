@@ -209,11 +209,14 @@ def _exchange_rows(dist, rows, counts, rank, world):
     return torch.cat(parts) if parts else rows[:0]
 
 
-def voxel_down_sample(points, voxel_size, dist, rank, world, normals=None, colors=None, ops=None, gather=True):
+def voxel_down_sample(points, voxel_size, dist, rank, world, normals=None, colors=None, ops=None, gather=True,
+                      replicated=False):
     """PointCloud::VoxelDownSample of a cloud spread over `world` ranks.  points / normals / colors: THIS rank's part,
     torch tensors [m, 3] float32 (CUDA with the nccl backend).  Returns (points, normals, colors) tensors of the
     down-sampled cloud: all of it on every rank (gather=True, the reference's lexicographic order) or only this
-    rank's slab.  voxel_size <= 0 returns empty tensors like the reference (down_sample.cu:173-176)."""
+    rank's slab.  voxel_size <= 0 returns empty tensors like the reference (down_sample.cu:173-176).
+    replicated=True: every rank holds the WHOLE cloud (the pyramid of config 5): bounds and histogram are local, each
+    rank keeps the points of its own slab, and the only collective is the final all-gather."""
     import numpy as np
     import torch
     ops = ops or _GpuVoxelOps()
@@ -232,7 +235,8 @@ def voxel_down_sample(points, voxel_size, dist, rank, world, normals=None, color
     else:
         mn, mx = np.full(3, np.inf, np.float32), np.full(3, -np.inf, np.float32)
     b = torch.from_numpy(np.concatenate([mn, -mx]).astype(np.float32)).to(dev)
-    dist.all_reduce(b, op=dist.ReduceOp.MIN)
+    if not replicated:
+        dist.all_reduce(b, op=dist.ReduceOp.MIN)
     b = b.cpu().numpy()
     gmin = b[:3].astype(np.float32)
     if not np.isfinite(gmin).all():                       # no point anywhere
@@ -241,22 +245,28 @@ def voxel_down_sample(points, voxel_size, dist, rank, world, normals=None, color
     # 2. slabs of consecutive x-indices with about the same number of points
     kx = ops.indices(points, v, origin)[:, 0].to(torch.int64) if m else torch.zeros(0, dtype=torch.int64, device=dev)
     kmax = torch.tensor([int(kx.max()) if m else 0], dtype=torch.int64, device=dev)
-    dist.all_reduce(kmax, op=dist.ReduceOp.MAX)
+    if not replicated:
+        dist.all_reduce(kmax, op=dist.ReduceOp.MAX)
     K = int(kmax.item()) + 1
     hist = torch.bincount(kx, minlength=K)
-    dist.all_reduce(hist)
+    if not replicated:
+        dist.all_reduce(hist)
     cum = torch.cumsum(hist, 0)
     total = int(cum[-1].item())
     targets = torch.tensor([(total * r) // world for r in range(1, world)], dtype=torch.int64, device=dev)
     # cuts[r-1] = first x-index of rank r's slab: the smallest index whose cumulative count exceeds the target
     cuts = torch.searchsorted(cum, targets, right=True)
     owner = torch.searchsorted(cuts, kx, right=True) if world > 1 else torch.zeros_like(kx)
-    # 3. one exchange: rows sorted by owner (stable: original order inside a destination)
-    order = torch.argsort(owner, stable=True)
-    counts = torch.bincount(owner, minlength=world)
     cols = [points] + ([normals] if normals is not None else []) + ([colors] if colors is not None else [])
-    rows = torch.cat(cols, 1)[order]
-    got = _exchange_rows(dist, rows, counts, rank, world)
+    if replicated:
+        # everybody has everything: keep the rows of my own slab, nothing to exchange
+        got = torch.cat(cols, 1)[owner == rank]
+    else:
+        # 3. one exchange: rows sorted by owner (stable: original order inside a destination)
+        order = torch.argsort(owner, stable=True)
+        counts = torch.bincount(owner, minlength=world)
+        rows = torch.cat(cols, 1)[order]
+        got = _exchange_rows(dist, rows, counts, rank, world)
     p = got[:, 0:3].contiguous()
     c0 = 3
     nrm = col = None

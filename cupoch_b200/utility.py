@@ -60,6 +60,12 @@ class DeviceArray:
             obj = obj.numpy()
         return cls.from_numpy(np.asarray(obj), dtype)
 
+    @property
+    def __cuda_array_interface__(self):
+        """zero-copy export (torch.as_tensor(arr, device="cuda"), cupy.asarray(arr)); the reference exports through
+        DLPack (utility/dl_converter.h:32-40)"""
+        return {"shape": self.shape, "typestr": self.dtype.str, "data": (self.ptr, False), "version": 2, "strides": None}
+
     # -- access --------------------------------------------------------------
     def cpu(self, count=None):
         """download (optionally only the first `count` rows)"""

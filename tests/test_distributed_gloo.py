@@ -180,6 +180,11 @@ def _voxel_worker(rank, world, port, q):
     out = distributed.voxel_down_sample(t(pts), 0.11, dist, rank, world, normals=t(nrm), colors=t(col), ops=_CpuVoxelOps(orc))
     slab = distributed.voxel_down_sample(t(pts), 0.11, dist, rank, world, ops=_CpuVoxelOps(orc), gather=False)
     none = distributed.voxel_down_sample(t(pts), 0.0, dist, rank, world, ops=_CpuVoxelOps(orc))
+    whole = lambda a: torch.from_numpy(a)
+    rep = distributed.voxel_down_sample(whole(pts), 0.11, dist, rank, world, normals=whole(nrm), colors=whole(col),
+                                        ops=_CpuVoxelOps(orc), replicated=True)
+    for a, b in zip(rep, out):
+        assert torch.equal(a, b)                          # the replicated-input path gives the same cloud
     q.put((rank, [o.numpy() for o in out], slab[0].numpy(), none[0].shape[0]))
     dist.destroy_process_group()
 

@@ -27,6 +27,8 @@ def main():
     ap.add_argument("--points", type=int, default=0)
     ap.add_argument("--reps", type=int, default=3)
     ap.add_argument("--comm", default="p2p", choices=["p2p", "nccl"])
+    ap.add_argument("--sharded-prep", action="store_true",
+                    help="config 5: shard VoxelDownSample / EstimateNormals over the ranks (cupoch_b200.distributed)")
     args = ap.parse_args()
     import cupoch_b200 as cph
     from cupoch_b200 import _lib
@@ -107,10 +109,28 @@ def main():
             st = []
             for v, iters in ((0.05, 50), (0.025, 30), (0.0125, 14)):
                 t0 = time.perf_counter()
-                td, sd = t_full.voxel_down_sample(v), s_full.voxel_down_sample(v)
-                L.cphb_stream_synchronize(None); t1 = time.perf_counter()
-                td.estimate_normals(G.KDTreeSearchParamRadius(2 * v, 30))
-                sd.estimate_normals(G.KDTreeSearchParamRadius(2 * v, 30))
+                if args.sharded_prep and world > 1:
+                    # every rank down-samples its own slab of the (replicated) clouds, one all-gather;
+                    # normals by blocks of queries against the replicated index, one all-gather
+                    import torch
+                    from cupoch_b200 import distributed as D
+
+                    def down(pc):
+                        tp = torch.as_tensor(pc.points, device="cuda")
+                        tcol = torch.as_tensor(pc.colors, device="cuda")
+                        p_, _, c_ = D.voxel_down_sample(tp, v, dist, rank, world, colors=tcol, replicated=True)
+                        o = G.PointCloud(p_)
+                        o.colors = c_
+                        return o
+                    td, sd = down(t_full), down(s_full)
+                    L.cphb_stream_synchronize(None); t1 = time.perf_counter()
+                    D.estimate_normals(td, G.KDTreeSearchParamRadius(2 * v, 30), dist, rank, world, device="cuda")
+                    D.estimate_normals(sd, G.KDTreeSearchParamRadius(2 * v, 30), dist, rank, world, device="cuda")
+                else:
+                    td, sd = t_full.voxel_down_sample(v), s_full.voxel_down_sample(v)
+                    L.cphb_stream_synchronize(None); t1 = time.perf_counter()
+                    td.estimate_normals(G.KDTreeSearchParamRadius(2 * v, 30))
+                    sd.estimate_normals(G.KDTreeSearchParamRadius(2 * v, 30))
                 L.cphb_stream_synchronize(None); t2 = time.perf_counter()
                 ns = len(sd)
                 res = R.registration_colored_icp(sd, td, v, T, R.ICPConvergenceCriteria(1e-6, 1e-6, iters), comm=comm,
