@@ -284,6 +284,16 @@ def run_native(args, rank, world):
         step_e2e()
     e2e_ms, res_e = timed(step_e2e, args.steps)
     h2d_bytes = h_src.nbytes + h_tgt.nbytes + h_tn.nbytes
+    host_call_ms = None
+    if args.e2e_host_call:
+        # the same end-to-end measurement through ONE C-ABI call that takes the host buffers itself
+        # (cphb_registration_icp_host: uploads on a side stream, overlapped with the index build)
+        def step_host():
+            return R.registration_icp_host(h_src, h_tgt, MAX_DIST, init, est, crit, target_normals=h_tn, comm=comm, shard=shard)
+        for _ in range(args.warmup):
+            step_host()
+        host_call_ms, res_h = timed(step_host, args.steps)
+        assert np.array_equal(res_h.transformation, res_e.transformation), "host-buffer call and device call disagree"
 
     # ---- kNN leg of the metric: SearchRadius(k=1, r) of the 1M source against the 1M target ------
     tree = cph.geometry.KDTreeFlann(t_pc)
@@ -326,6 +336,9 @@ def run_native(args, rank, world):
                                       % (world, args.comm if world > 1 else "none")},
             "e2e": {"value": ITERS * 1e3 / (e2e_ms / args.steps), "unit": "iter/s", "h2d_bytes_per_step": int(h2d_bytes),
                     "d2h_bytes_per_step": int(d2h[0]), "ms_per_step": e2e_ms / args.steps},
+            **({"e2e_host_call": {"value": ITERS * 1e3 / (host_call_ms / args.steps), "unit": "iter/s",
+                                  "ms_per_step": host_call_ms / args.steps, "h2d_bytes_per_step": int(h2d_bytes),
+                                  "call": "cphb_registration_icp_host"}} if host_call_ms else {}),
             "gpu_launches": int(launches),
             "loop": {"iters_per_sec": ITERS * 1e3 / loop_ms, "ms_per_launch": kern_ms, "launches": loop_launches,
                      "correspondences_per_sec": float(res.fitness) * n * (ITERS + 1) * 1e3 / loop_ms},
@@ -379,6 +392,8 @@ def main():
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--points", type=int, default=1_000_000)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--e2e-host-call", action="store_true",
+                    help="also time the end-to-end path through cphb_registration_icp_host (one call, host buffers)")
     ap.add_argument("--comm", default="p2p", choices=["p2p", "nccl"],
                     help="N>1 exchange: p2p = peer-memory stores fused into the reduce kernel, nccl = ncclAllReduce")
     args = ap.parse_args()

@@ -76,6 +76,8 @@ _SIGNATURES = {
     "cphb_icp_step": (C.c_int, [_P, C.POINTER(C.c_float), C.POINTER(C.c_double), _P, _P]),
     "cphb_registration_icp": (C.c_int, [C.POINTER(Cloud), C.POINTER(Cloud), C.POINTER(C.c_float),
                                         C.POINTER(IcpParams), _P, C.POINTER(IcpResult), _P, _P]),
+    "cphb_registration_icp_host": (C.c_int, [C.POINTER(Cloud), C.POINTER(Cloud), C.POINTER(C.c_float),
+                                             C.POINTER(IcpParams), _P, C.POINTER(IcpResult), _P, _P]),
     "cphb_evaluate_registration": (C.c_int, [C.POINTER(Cloud), C.POINTER(Cloud), C.c_float, C.POINTER(C.c_float),
                                              C.POINTER(IcpResult), _P, _P]),
     "cphb_compute_transformation": (C.c_int, [C.c_int, C.POINTER(Cloud), C.POINTER(Cloud), _P, C.c_size_t,

@@ -1503,6 +1503,9 @@ struct HostCache {
     bool in_use = false;
 };
 static thread_local HostCache t_cache;
+// cphb_registration_icp_host: the source arrays are still being uploaded on another stream while the target index is
+// built; cphb_icp_create waits for this event right before it first reads them
+static thread_local cudaEvent_t t_source_ready = nullptr;
 
 static bool is_identity4(const float *T) {  // Eigen isIdentity(1e-5), registration.cu:148
     for (int i = 0; i < 4; ++i)
@@ -1745,6 +1748,10 @@ extern "C" int cphb_icp_create(const cphb_cloud *source, const cphb_cloud *targe
         CPHB_CUDA(cudaMallocHost((void **)&icp->h_st, sizeof(IcpState)));
         CPHB_CUDA(cudaEventCreate(&icp->ev0));
         CPHB_CUDA(cudaEventCreate(&icp->ev1));
+    }
+    if (t_source_ready) {
+        cudaStreamWaitEvent(s, t_source_ready, 0);
+        t_source_ready = nullptr;
     }
     if (n_full) {
         rc = cphb_hilbert_order(source->points, n_full, perm, nullptr, 0, s);
@@ -2051,6 +2058,87 @@ extern "C" int cphb_registration_icp(const cphb_cloud *source, const cphb_cloud 
         fprintf(stderr, "[cphb] registration_icp host ms: create %.3f run %.3f destroy %.3f (loop device %.3f)\n", ms(t0, t1),
                 ms(t1, t2), ms(t2, t3), h_result->loop_ms);
     }
+    return rc;
+}
+
+// One-shot registration from HOST buffers (pinned or pageable): the uploads run on a separate stream and overlap the
+// target index build and the source ordering -- target points first (the index needs nothing else), then the
+// source, then the target attributes that only the first iteration reads.  The clouds' pointers are host pointers;
+// h_corr_out (optional, host, 2 * source.n int32) receives the (i, j) pairs.  Everything is complete on return.
+struct HostUploadCache {
+    cudaStream_t copy = nullptr;
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+};
+static thread_local HostUploadCache t_up;
+
+extern "C" int cphb_registration_icp_host(const cphb_cloud *h_source, const cphb_cloud *h_target, const float h_init[16],
+                                          const cphb_icp_params *params, cphb_comm *comm, cphb_icp_result *h_result,
+                                          int32_t *h_corr_out, void *stream) {
+    cudaStream_t s = (cudaStream_t)stream;
+    if (!h_source || !h_target || !params || !h_result || !h_init) {
+        cphb_set_error("cphb_registration_icp_host: null argument");
+        return CPHB_ERR_INVALID;
+    }
+    if (!t_up.copy) {
+        CPHB_CUDA(cudaStreamCreateWithFlags(&t_up.copy, cudaStreamNonBlocking));
+        for (auto &e : t_up.ev) CPHB_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    }
+    const size_t ns = h_source->n, nt = h_target->n;
+    // device arena: [tgt points | src points, normals, colors, covariances | tgt normals, colors, covariances, gradient | pairs]
+    size_t off = 0;
+    auto take = [&](const void *hp, size_t bytes) { size_t o = off; if (hp) off = cphb_align(off + bytes, 256); return hp ? o : (size_t)-1; };
+    const size_t o_tp = take(h_target->points, 12 * nt);
+    const size_t o_sp = take(h_source->points, 12 * ns), o_sn = take(h_source->normals, 12 * ns), o_sc = take(h_source->colors, 12 * ns),
+                 o_sv = take(h_source->covariances, 36 * ns);
+    const size_t o_tn = take(h_target->normals, 12 * nt), o_tc = take(h_target->colors, 12 * nt),
+                 o_tv = take(h_target->covariances, 36 * nt), o_tg = take(h_target->color_gradient, 12 * nt);
+    const size_t o_pairs = take(h_corr_out, 8 * ns);
+    char *base = nullptr;
+    int rc = cphb_alloc_async((void **)&base, off ? off : 256, s);
+    if (rc) return rc;
+    auto dp = [&](size_t o) { return o == (size_t)-1 ? (float *)nullptr : (float *)(base + o); };
+    cudaStream_t c = t_up.copy;
+    CPHB_CUDA(cudaEventRecord(t_up.ev[0], s));            // the arena exists from here on in stream order
+    CPHB_CUDA(cudaStreamWaitEvent(c, t_up.ev[0], 0));
+    auto up = [&](size_t o, const void *hp, size_t bytes) {
+        if (hp && bytes) cudaMemcpyAsync(base + o, hp, bytes, cudaMemcpyHostToDevice, c);
+    };
+    up(o_tp, h_target->points, 12 * nt);
+    CPHB_CUDA(cudaEventRecord(t_up.ev[1], c));            // target points: all the index build needs
+    up(o_sp, h_source->points, 12 * ns);
+    up(o_sn, h_source->normals, 12 * ns);
+    up(o_sc, h_source->colors, 12 * ns);
+    up(o_sv, h_source->covariances, 36 * ns);
+    CPHB_CUDA(cudaEventRecord(t_up.ev[2], c));            // source: first read by the Hilbert ordering
+    up(o_tn, h_target->normals, 12 * nt);
+    up(o_tc, h_target->colors, 12 * nt);
+    up(o_tv, h_target->covariances, 36 * nt);
+    up(o_tg, h_target->color_gradient, 12 * nt);
+    CPHB_CUDA(cudaEventRecord(t_up.ev[3], c));            // target attributes: first read by the first iteration
+    cphb_cloud ds = *h_source, dt = *h_target;
+    ds.points = dp(o_sp); ds.normals = dp(o_sn); ds.colors = dp(o_sc); ds.covariances = dp(o_sv); ds.color_gradient = nullptr;
+    dt.points = dp(o_tp); dt.normals = dp(o_tn); dt.colors = dp(o_tc); dt.covariances = dp(o_tv); dt.color_gradient = dp(o_tg);
+    CPHB_CUDA(cudaStreamWaitEvent(s, t_up.ev[1], 0));
+    t_source_ready = t_up.ev[2];
+    cphb_icp *icp = nullptr;
+    rc = cphb_icp_create(&ds, &dt, params, stream, &icp);
+    t_source_ready = nullptr;
+    if (!rc) {
+        cudaStreamWaitEvent(s, t_up.ev[2], 0);            // (already waited inside create; harmless if it returned early)
+        cudaStreamWaitEvent(s, t_up.ev[3], 0);
+        int32_t *d_pairs = (int32_t *)dp(o_pairs);
+        rc = cphb_icp_run(icp, h_init, comm, h_result, d_pairs, stream);
+        if (!rc && h_corr_out && h_result->n_local_correspondences > 0) {
+            cudaError_t e = cudaMemcpyAsync(h_corr_out, d_pairs, sizeof(int32_t) * 2 * (size_t)h_result->n_local_correspondences,
+                                            cudaMemcpyDeviceToHost, s);
+            if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+            if (e != cudaSuccess) { cphb_set_error("cphb_registration_icp_host: %s", cudaGetErrorString(e)); rc = CPHB_ERR_CUDA; }
+        }
+        cphb_icp_destroy(icp);
+    }
+    cudaStreamSynchronize(c);                              // no upload may outlive the host buffers or the arena
+    cphb_free_async(base, s);
+    cudaStreamSynchronize(s);
     return rc;
 }
 

@@ -193,6 +193,48 @@ def registration_icp(source, target, max_correspondence_distance, init=None,
     return _result(res, corr, return_correspondences)
 
 
+def registration_icp_host(source_points, target_points, max_correspondence_distance, init=None, estimation_method=None,
+                          criteria=None, source_normals=None, target_normals=None, source_colors=None, target_colors=None,
+                          source_covariances=None, target_covariances=None, target_color_gradient=None, comm=None,
+                          return_correspondences=False, shard=None):
+    """registration::RegistrationICP straight from HOST arrays ([n,3] float32 numpy, ideally in pinned memory):
+    one C-ABI call (cphb_registration_icp_host) uploads both clouds on a side stream, overlapping the copies with
+    the index build and the source ordering, runs the loop and returns the result -- nothing stays on the device."""
+    estimation_method = estimation_method or TransformationEstimationPointToPoint()
+    criteria = criteria or ICPConvergenceCriteria()
+    init = np.eye(4, dtype=np.float32) if init is None else init
+    if estimation_method.get_transformation_estimation_type() == _lib.EST_UNSPECIFIED:
+        raise NotImplementedError("user-defined TransformationEstimation: use the generic loop in the C++ facade")
+    _lib.require_gpu()
+
+    def host(a, cols):
+        if a is None:
+            return None
+        a = np.ascontiguousarray(a, np.float32)   # no copy for contiguous float32 input (keeps pinned memory pinned)
+        if a.ndim < 2 or int(np.prod(a.shape[1:])) != cols:
+            raise ValueError("expected [n, %d] float32" % cols)
+        return a
+
+    keep = [host(source_points, 3), host(target_points, 3), host(source_normals, 3), host(target_normals, 3),
+            host(source_colors, 3), host(target_colors, 3), host(source_covariances, 9), host(target_covariances, 9),
+            host(target_color_gradient, 3)]
+    ptr = (lambda a: None if a is None else a.ctypes.data)
+    sc, tc = _lib.Cloud(), _lib.Cloud()
+    sc.points, sc.normals, sc.colors, sc.covariances, sc.n = ptr(keep[0]), ptr(keep[2]), ptr(keep[4]), ptr(keep[6]), len(keep[0])
+    tc.points, tc.normals, tc.colors, tc.covariances, tc.n = ptr(keep[1]), ptr(keep[3]), ptr(keep[5]), ptr(keep[7]), len(keep[1])
+    tc.color_gradient = ptr(keep[8])
+    sc.cov_col_major = tc.cov_col_major = 0
+    p = _params(estimation_method, max_correspondence_distance, criteria, shard)
+    res = _lib.IcpResult()
+    pairs = np.empty((max(len(keep[0]), 1), 2), np.int32) if return_correspondences else None
+    _lib.check(_lib.lib().cphb_registration_icp_host(C.byref(sc), C.byref(tc), as_f16(init), C.byref(p), comm, C.byref(res),
+                                                     pairs.ctypes.data if pairs is not None else None, None))
+    out = _result(res, None, False)
+    if pairs is not None:
+        out.correspondence_set = pairs[:int(res.n_local_correspondences)]
+    return out
+
+
 def evaluate_registration(source, target, max_correspondence_distance, transformation=None):
     """registration::EvaluateRegistration (registration.cu:106-119)."""
     T = np.eye(4, dtype=np.float32) if transformation is None else transformation

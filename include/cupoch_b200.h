@@ -266,6 +266,14 @@ int cphb_registration_icp(const cphb_cloud *source, const cphb_cloud *target,
                           cphb_comm *comm, cphb_icp_result *h_result, int32_t *corr_out,
                           void *stream);
 
+/* The same from HOST buffers (every pointer of the two clouds is a host pointer, pinned for full speed): the
+ * uploads are issued on a separate stream in the order the loop first needs them (target points, source, target
+ * attributes) and overlap the index build and the source ordering.  h_corr_out (optional, host, 2 * source.n
+ * int32) receives the (i, j) pairs.  Complete on return. */
+int cphb_registration_icp_host(const cphb_cloud *h_source, const cphb_cloud *h_target,
+                               const float h_init[16], const cphb_icp_params *params, cphb_comm *comm,
+                               cphb_icp_result *h_result, int32_t *h_corr_out, void *stream);
+
 /* TransformationEstimation*::ComputeTransformation / ComputeRMSE on an explicit correspondence list
  * (transformation_estimation.h:49-77; corr = device (i, j) pairs).  Synchronise. */
 int cphb_compute_transformation(int estimation, const cphb_cloud *source, const cphb_cloud *target,

@@ -206,3 +206,27 @@ def test_voxel_origin_override_and_indices(orc):
     org = (C.c_float * 3)(*[float(x) for x in low])
     _lib.check(L.cphb_voxel_indices(pc.points.ptr, len(pts), float(voxel), org, idx.ptr, None))
     np.testing.assert_array_equal(idx.cpu(), np.floor((pts - low) / voxel).astype(np.int32))
+
+
+@pytest.mark.parametrize("kind", ["p2plane", "p2p"])
+def test_registration_from_host_buffers_equals_device_call(kind):
+    """cphb_registration_icp_host (uploads overlapped with the index build) returns exactly what the device-resident
+    call returns: same pose bits, fitness, rmse and correspondence pairs."""
+    from cupoch_b200.testing import datagen
+    R = cph.registration
+    n = 120000
+    tgt, tn = datagen.surface(n, 11)
+    src = datagen.make_source(tgt, datagen.gt_transform((-1.0, 1.5, 2.0), (0.01, -0.005, 0.008)), 13, 14, 3e-4)
+    crit = R.ICPConvergenceCriteria(0, 0, 12)
+    est = R.TransformationEstimationPointToPlane() if kind == "p2plane" else R.TransformationEstimationPointToPoint()
+    t_pc = cph.geometry.PointCloud(tgt)
+    if kind == "p2plane":
+        t_pc.normals = tn
+    dev = R.registration_icp(cph.geometry.PointCloud(src), t_pc, 0.02, np.eye(4), est, crit)
+    host = R.registration_icp_host(src, tgt, 0.02, np.eye(4), est, crit, target_normals=tn if kind == "p2plane" else None,
+                                   return_correspondences=True)
+    np.testing.assert_array_equal(host.transformation, dev.transformation)
+    assert host.fitness == dev.fitness and host.inlier_rmse == dev.inlier_rmse and host.iterations == dev.iterations
+    np.testing.assert_array_equal(host.correspondence_set, dev.correspondence_set)
+    again = R.registration_icp_host(src, tgt, 0.02, np.eye(4), est, crit, target_normals=tn if kind == "p2plane" else None)
+    np.testing.assert_array_equal(again.transformation, dev.transformation)      # back-to-back calls reuse the cached stream
