@@ -1,4 +1,4 @@
-"""Soundness of the nearest-neighbour certificates of the ICP loop (cupoch_b200/csrc/icp.cu, "Certificates";
+"""Soundness of the nearest-neighbour certificates of the ICP loop (cupoch_b200/csrc/icp_kernels.cuh, "Certificates";
 cphb_internal.cuh, WarpSearchC), checked on the CPU against exhaustive search.
 
 This is a numpy restatement of the *decision rule* the kernel applies, with every approximation pushed in the

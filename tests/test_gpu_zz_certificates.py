@@ -1,4 +1,4 @@
-"""GPU invariants of the ICP certificates and tile schedules (icp.cu): they may only change how fast a result is
+"""GPU invariants of the ICP certificates and tile schedules (icp_kernels.cuh): they may only change how fast a result is
 found, never a bit of it.  Kept in its own file, last in collection order."""
 import numpy as np
 import pytest
