@@ -253,7 +253,12 @@ extern "C" int cphb_icp_create(const cphb_cloud *source, const cphb_cloud *targe
         unsigned cap = (unsigned)sms * per_sm;
         icp->grid = want < cap ? want : cap;
         unsigned rg = (n_tiles + 63) / 64;
-        icp->reduce_grid = rg < 1 ? 1 : (rg > (unsigned)sms ? (unsigned)sms : rg);
+        unsigned rg_cap = (unsigned)sms;
+        if (const char *e = getenv("CPHB_REDUCE_BLOCKS_PER_SM")) {  // tuning hook: more, shorter chains of tile sums
+            int v = atoi(e);
+            if (v >= 1 && v <= 8) rg_cap = (unsigned)sms * (unsigned)v;
+        }
+        icp->reduce_grid = rg < 1 ? 1 : (rg > rg_cap ? rg_cap : rg);
     }
     const bool want_nrm = params->estimation == CPHB_EST_SYMMETRIC && source->normals;
     const bool want_col = params->estimation == CPHB_EST_COLORED_ICP && source->colors;
