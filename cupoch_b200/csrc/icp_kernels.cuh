@@ -55,9 +55,27 @@ __device__ __forceinline__ void prefetch_target(const IcpArgs &a, size_t j) {
 //   ICP_DUAL    two instances of the kernel per iteration, one compiled for the searching launches (more resident
 //               warps: ICP_MIN_BLOCKS_SEARCH) and one for the launches that run under the static schedule (more
 //               registers, deeper pipeline); the device-side regime flag decides which of the two returns at once
+//   ICP_LANE_ACC  under the static schedule every lane keeps the products of ITS OWN rows in 30 float64 registers over all
+//               the tiles of its warp and the warp reduces them once, at its end: no shared-memory staging, no
+//               per-tile 32-step DFMA chain, W instead of n_tiles rows for the reduce kernel.  The static schedule
+//               makes the order (and so every bit) reproducible; it differs from the per-tile order in the last
+//               bits of the float64 sums only
 #ifndef ICP_DEEP_PIPE
 #define ICP_DEEP_PIPE 0
 #endif
+#ifndef ICP_LANE_ACC
+#define ICP_LANE_ACC 0
+#endif
+// closed forms of c_pair_jtj / c_pair_p2p (icp_types.cuh) for compile-time unrolling
+__host__ __device__ constexpr int pair_jtj_a(int p) {
+    return p < 6 ? 0 : p < 11 ? 1 : p < 15 ? 2 : p < 18 ? 3 : p < 20 ? 4 : p < 21 ? 5 : p < 27 ? p - 21 : p == 27 ? 6 : p == 28 ? 7 : 8;
+}
+__host__ __device__ constexpr int pair_jtj_b(int p) {
+    return p < 6 ? p : p < 11 ? p - 5 : p < 15 ? p - 9 : p < 18 ? p - 12 : p < 20 ? p - 14 : p < 21 ? 5 : p < 28 ? 6 : 8;
+}
+__host__ __device__ constexpr int pair_p2p_a(int p) { return p < 6 ? p : p < 15 ? (p - 6) / 3 : p == 28 ? 7 : 8; }
+__host__ __device__ constexpr int pair_p2p_b(int p) { return p < 6 ? 8 : p < 15 ? 3 + (p - 6) % 3 : 8; }
+__host__ __device__ constexpr bool pair_live(bool p2p, int p) { return p2p ? (p < 15 || p == 28 || p == 29) : p < 30; }
 #ifndef ICP_DUAL
 #define ICP_DUAL 0
 #endif
@@ -174,6 +192,11 @@ __global__ void __launch_bounds__(ICP_SEARCH_WARPS * 32, (MODE == 1) ? ICP_MIN_B
     unsigned pend = 0, pend_sz = 1;  // claim in flight (result in lane 0) and its size
     unsigned csize = 1;              // size of the next claim
     unsigned n_skipped = 0;
+#if ICP_LANE_ACC
+    double lacc[32];
+#pragma unroll
+    for (int p = 0; p < 32; ++p) lacc[p] = 0.0;
+#endif
     if (!static_sched && lane == 0) pend = atomicAdd(&st->tile_counter, 1u);
 #if !ICP_LOWREG
     float4 s_pf = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -387,6 +410,29 @@ __global__ void __launch_bounds__(ICP_SEARCH_WARPS * 32, (MODE == 1) ? ICP_MIN_B
             build_rows<KIND, NROWS>(ta, s.x, s.y, s.z, sn, cs4, Cs, j, J, r);
             drop_nonfinite_rows<NROWS>(J, r);
         }
+#if ICP_LANE_ACC
+        if (static_sched) {
+            // this lane's own rows, every product into its own float64 accumulator (exact products, one rounding per
+            // addition); the warp-wide reduction happens once, after the last tile
+            constexpr bool P2P = (KIND == CPHB_EST_POINT_TO_POINT);
+#pragma unroll
+            for (int q = 0; q < NROWS; ++q) {
+                const double v[9] = {(double)J[q][0], (double)J[q][1], (double)J[q][2], (double)J[q][3], (double)J[q][4],
+                                     (double)J[q][5], (double)r[q], (q == 0 && found) ? (double)d2 : 0.0,
+                                     (q == 0 && found) ? 1.0 : 0.0};
+#pragma unroll
+                for (int p = 0; p < 32; ++p)
+                    if (pair_live(P2P, p))
+                        lacc[p] = fma(v[P2P ? pair_p2p_a(p) : pair_jtj_a(p)], v[P2P ? pair_p2p_b(p) : pair_jtj_b(p)], lacc[p]);
+            }
+#if ICP_DEEP_PIPE
+            continue;  // (the deep pipeline issued this tile's prefetches at its top)
+#else
+            if (tn < n_tiles && pv_pf.x >= 0) prefetch_target<KIND>(a, (size_t)pv_pf.x);
+            continue;
+#endif
+        }
+#endif
         // stage + accumulate: lane L adds column pair (ca, cb) over the 32 staged rows, in row order
         double acc = 0.0;
 #pragma unroll
@@ -416,6 +462,26 @@ __global__ void __launch_bounds__(ICP_SEARCH_WARPS * 32, (MODE == 1) ? ICP_MIN_B
 #endif
     }
     if (a.static_sched && lane == 0 && n_skipped) atomicAdd(&st->cert_tiles, n_skipped);
+#if ICP_LANE_ACC
+    {
+        const unsigned gw = blockIdx.x * ICP_SEARCH_WARPS + warp;
+        if (static_sched && !materialize && gw < n_tiles) {
+            constexpr bool P2P = (KIND == CPHB_EST_POINT_TO_POINT);
+            double out = 0.0;
+#pragma unroll
+            for (int p = 0; p < 32; ++p) {
+                if (!pair_live(P2P, p)) continue;
+                double t = lacc[p];
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(CPHB_FULL, t, o);  // same bits on every lane
+                if (lane == p) out = t;
+            }
+            a.tile_sums[(size_t)gw * 32 + lane] = out;  // one row per warp instead of one per tile
+        }
+        // rows the reduce kernel has to add: one per warp that owned a tile, or one per tile
+        if (gw == 0 && lane == 0 && !materialize) st->sum_rows = static_sched ? min(total_warps, n_tiles) : n_tiles;
+    }
+#endif
 }
 
 // Fixed-order grid sum of the tile sums, then (last block) the host-side part of the loop.
@@ -436,8 +502,13 @@ __global__ void __launch_bounds__(ICP_REDUCE_BLOCK) icp_reduce_kernel(const __gr
         return;
     }
     const unsigned n_tiles = a.n_pad / 32;
-    const unsigned chunk = (n_tiles + gridDim.x - 1) / gridDim.x;
-    const unsigned t0 = blockIdx.x * chunk, t1 = min(n_tiles, t0 + chunk);
+#if ICP_LANE_ACC
+    const unsigned n_rows = *(volatile unsigned *)&st->sum_rows;
+#else
+    const unsigned n_rows = n_tiles;
+#endif
+    const unsigned chunk = (n_rows + gridDim.x - 1) / gridDim.x;
+    const unsigned t0 = blockIdx.x * chunk, t1 = min(n_rows, t0 + chunk);
     const int c = threadIdx.x & 31, g = threadIdx.x >> 5;
     {
         // 8 loads in flight per thread, added in tile order (x + 0.0 is exact, so the padding loads of the

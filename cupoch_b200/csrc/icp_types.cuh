@@ -21,6 +21,10 @@ struct IcpState {
     unsigned tile_counter;
     unsigned cert_tiles;  // tiles skipped by their certificates in the launch just finished
     int static_sched;     // next search launch may use the static tile schedule (see icp_iteration_kernel)
+#if defined(ICP_LANE_ACC) && ICP_LANE_ACC
+    unsigned sum_rows;    // rows of tile_sums the reduce kernel adds for the launch just finished
+    unsigned pad_rows_;
+#endif
     long long n_corr;
     unsigned pad_local;  // host-side staging only (count of locally written correspondence pairs)
     unsigned pad_;

@@ -17,4 +17,6 @@ tools/build_variant.sh deep_fast_pdl_mb4 -DICP_DEEP_PIPE=1 -DICP_FAST_START=1 -D
 tools/build_variant.sh deep_pdl -DICP_DEEP_PIPE=1 -DCPHB_PDL=1
 tools/build_variant.sh pdl_mb6 -DCPHB_PDL=1 -DICP_MIN_BLOCKS=6
 for sb in 6 7 8; do tools/build_variant.sh dual_s$sb -DICP_DUAL=1 -DICP_DEEP_PIPE=1 -DICP_FAST_START=1 -DICP_MIN_BLOCKS=4 -DICP_MIN_BLOCKS_SEARCH=$sb; done
+tools/build_variant.sh lane_dual_s6_b3 -DICP_LANE_ACC=1 -DICP_DUAL=1 -DICP_DEEP_PIPE=1 -DICP_FAST_START=1 -DICP_MIN_BLOCKS=3 -DICP_MIN_BLOCKS_SEARCH=6
+tools/build_variant.sh lane_dual_s6_b4 -DICP_LANE_ACC=1 -DICP_DUAL=1 -DICP_DEEP_PIPE=1 -DICP_FAST_START=1 -DICP_MIN_BLOCKS=4 -DICP_MIN_BLOCKS_SEARCH=6
 ls -la build_variants
