@@ -82,6 +82,39 @@ class PointCloud:
         c.cov_col_major = 0
         return c
 
+    # -- DLPack exchange (pointcloud.cpp:82-105, utility/dl_converter.h:32-40; examples/python/basic/*torch_tensor.py) --
+    def _to_dlpack(self, arr):
+        import torch
+        from torch.utils.dlpack import to_dlpack
+        if arr is None:
+            raise ValueError("attribute is empty")
+        return to_dlpack(torch.as_tensor(arr, device="cuda"))   # zero-copy view of the device array
+
+    def _from_dlpack(self, capsule):
+        from torch.utils.dlpack import from_dlpack
+        t = from_dlpack(capsule)
+        if not t.is_cuda:
+            t = t.cuda()
+        return DeviceArray.borrow(t.contiguous().float())
+
+    def to_points_dlpack(self):
+        return self._to_dlpack(self._points)
+
+    def to_normals_dlpack(self):
+        return self._to_dlpack(self._normals)
+
+    def to_colors_dlpack(self):
+        return self._to_dlpack(self._colors)
+
+    def from_points_dlpack(self, capsule):
+        self._points = self._from_dlpack(capsule)
+
+    def from_normals_dlpack(self, capsule):
+        self._normals = self._from_dlpack(capsule)
+
+    def from_colors_dlpack(self, capsule):
+        self._colors = self._from_dlpack(capsule)
+
     # -- geometry ops ---------------------------------------------------------
     def transform(self, transformation):
         """PointCloud::Transform (pointcloud.cu:293-299), in place."""
