@@ -230,3 +230,20 @@ def test_registration_from_host_buffers_equals_device_call(kind):
     np.testing.assert_array_equal(host.correspondence_set, dev.correspondence_set)
     again = R.registration_icp_host(src, tgt, 0.02, np.eye(4), est, crit, target_normals=tn if kind == "p2plane" else None)
     np.testing.assert_array_equal(again.transformation, dev.transformation)      # back-to-back calls reuse the cached stream
+
+
+def test_dlpack_round_trip():
+    """to_points_dlpack / from_points_dlpack (pointcloud.cpp:82-105; examples/python/basic/{to,from}_torch_tensor.py):
+    zero-copy exchange with torch in both directions."""
+    import torch
+    from torch.utils.dlpack import from_dlpack, to_dlpack
+    pts, _, _ = _cloud(1000, 23, outliers=0)
+    pc = cph.geometry.PointCloud(pts)
+    t = from_dlpack(pc.to_points_dlpack())
+    assert t.is_cuda and tuple(t.shape) == (1000, 3)
+    np.testing.assert_array_equal(t.cpu().numpy(), pts)
+    assert t.data_ptr() == pc.points.ptr                                     # a view, not a copy
+    pc2 = cph.geometry.PointCloud()
+    pc2.from_points_dlpack(to_dlpack(torch.from_numpy(pts).cuda()))
+    np.testing.assert_array_equal(pc2.points.cpu(), pts)
+    np.testing.assert_array_equal(pc2.get_min_bound(), pts.min(0))
