@@ -112,12 +112,24 @@ def all_gather_rows(dist, local_rows, n_total, world, device=None):
     return out
 
 
+def _all_gather_row_tensors(dist, local_t, n_total, world):
+    """device-side twin of all_gather_rows: torch tensors in, one concatenated tensor out (no host round trip)"""
+    import torch
+    biggest = max(shard_range(n_total, r, world)[1] - shard_range(n_total, r, world)[0] for r in range(world))
+    pad = torch.zeros((max(biggest, 1),) + tuple(local_t.shape[1:]), dtype=local_t.dtype, device=local_t.device)
+    pad[:local_t.shape[0]] = local_t
+    parts = [torch.empty_like(pad) for _ in range(world)]
+    dist.all_gather(parts, pad)
+    return torch.cat([parts[r][:shard_range(n_total, r, world)[1] - shard_range(n_total, r, world)[0]] for r in range(world)])
+
+
 def estimate_normals(cloud, search_param, dist, rank, world, device=None, local_fn=None):
     """PointCloud::EstimateNormals over `world` ranks (SURVEY 8e: replicate the index, shard the queries, no
     collective in the search; one all-gather of the per-point outputs).  Every rank holds the full cloud, estimates
     the normals of its contiguous block with cphb_estimate_normals_range and all-gathers the blocks: the result is
-    bit-identical to the single-GPU estimate.  `local_fn(points, first, count) -> [count, 3]` replaces the library
-    call in the gloo/CPU test of this orchestration."""
+    bit-identical to the single-GPU estimate.  With device="cuda" the blocks stay on the device (NCCL all-gather of
+    the device buffers, the cloud's normals become a view of the gathered tensor).  `local_fn(cloud, first, count)
+    -> [count, 3]` replaces the library call in the gloo/CPU test of this orchestration."""
     import numpy as np
     from . import geometry
     from .utility import DeviceArray
@@ -131,6 +143,13 @@ def estimate_normals(cloud, search_param, dist, rank, world, device=None, local_
             knn, radius, max_nn = 0, sp.radius, sp.max_nn
         out = DeviceArray((max(hi - lo, 1), 3), np.float32)
         _lib.check(_lib.lib().cphb_estimate_normals_range(cloud._points.ptr, n, knn, radius, max_nn, lo, hi - lo, out.ptr, None))
+        if device is not None and str(device).startswith("cuda"):
+            import torch
+            _lib.check(_lib.lib().cphb_stream_synchronize(None))
+            mine_t = torch.as_tensor(out, device="cuda")[:hi - lo]
+            full_t = _all_gather_row_tensors(dist, mine_t, n, world)
+            cloud.normals = full_t                       # zero-copy: the cloud borrows the gathered tensor
+            return full_t
         mine = out.cpu(hi - lo)
     else:
         mine = np.asarray(local_fn(cloud, lo, hi - lo), np.float32).reshape(-1, 3)

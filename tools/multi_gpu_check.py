@@ -85,6 +85,7 @@ def main():
         full_n = distributed.estimate_normals(cloud, cph.geometry.KDTreeSearchParamKNN(20), dist, rank, world, device="cuda")
         one = cph.geometry.PointCloud(pts[:nn])
         one.estimate_normals(cph.geometry.KDTreeSearchParamKNN(20))
+        full_n = full_n.cpu().numpy() if hasattr(full_n, "is_cuda") else full_n
         flags = torch.tensor([int(same), int(np.array_equal(full_n, one.normals.cpu()))], device="cuda")
         dist.all_reduce(flags, op=dist.ReduceOp.MIN)
         if rank == 0:
