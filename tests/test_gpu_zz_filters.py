@@ -1,16 +1,12 @@
 """GPU parity of the kNN consumers added in round 1: RemoveRadiusOutliers,
 RemoveStatisticalOutliers, SelectByIndex -- C ABI through the Python mirror vs the CPU oracle, plus the
-reference's known-answer tests (tests/golden).  Last in collection order: these kernels were written after the
-round's GPU budget was spent and are validated by the driver's round-end run first."""
+reference's known-answer tests (tests/golden)."""
 import numpy as np
 import pytest
 
-# filters.cu / voxelgrid.cu were written after the round-1 GPU budget was spent: everything they rest on is CPU-verified
-# (oracle vs the reference's known answers and numpy, tests/test_oracle_filters.py), but the kernels themselves are
-# first executed by the driver's round-end run.  Non-strict xfail keeps that first run from masking the rest of the
-# suite; a pass shows up as XPASS and the marker goes away with the first validated round.
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.xfail(strict=False, reason="new kernels, not yet executed on hardware when the round closed")]
+# (round 1 carried a non-strict xfail here because these kernels had not run on hardware yet; the driver's round-end
+# run passed all of them, so they are ordinary parity tests now)
+pytestmark = [pytest.mark.gpu]
 
 import cupoch_b200 as cph
 
