@@ -67,6 +67,106 @@ static __device__ void eigvec1(const float *A, const float *e0v, float e1, float
     }
     for (int i = 0; i < 3; ++i) out[i] = __fmaf_rn(cu, U[i], -(cv * V[i]));
 }
+// ---- deterministic acos / cos (specification: oracle/oracle.c "deterministic acos / cos"; tables from
+// tools/gen_trig_coeffs.py).  float64 Horner with explicit fma, IEEE sqrt/add/mul, one rounding to float32: the same bits
+// on the host oracle and on the device, unlike acosf / cosf (libm vs libdevice differ in the last ulp).
+namespace dt {
+static __device__ const double DT_ASIN[26] = {
+    0x1.0000000000000p+0,
+    0x1.5555555555555p-3,
+    0x1.3333333333333p-4,
+    0x1.6db6db6db6db7p-5,
+    0x1.f1c71c71c71c7p-6,
+    0x1.6e8ba2e8ba2e9p-6,
+    0x1.1c4ec4ec4ec4fp-6,
+    0x1.c99999999999ap-7,
+    0x1.7a87878787878p-7,
+    0x1.3fde50d79435ep-7,
+    0x1.12ef3cf3cf3cfp-7,
+    0x1.df3bd37a6f4dfp-8,
+    0x1.a6863d70a3d71p-8,
+    0x1.782dda12f684cp-8,
+    0x1.51ba308d3dcb1p-8,
+    0x1.31683bdef7bdfp-8,
+    0x1.15ee9d45d1746p-8,
+    0x1.fcaf8fb6db6dbp-9,
+    0x1.d3d2a8e0dd67dp-9,
+    0x1.b026f57b13b14p-9,
+    0x1.90cb77f60c7cep-9,
+    0x1.750de64d7d05fp-9,
+    0x1.5c5f56efaaaabp-9,
+    0x1.464c0950f7d47p-9,
+    0x1.3275586c5f2f0p-9,
+    0x1.208d3570ae5a6p-9,
+};
+static __device__ const double DT_COS[12] = {
+    0x1.0000000000000p+0,
+    -0x1.0000000000000p-1,
+    0x1.5555555555555p-5,
+    -0x1.6c16c16c16c17p-10,
+    0x1.a01a01a01a01ap-16,
+    -0x1.27e4fb7789f5cp-22,
+    0x1.1eed8eff8d898p-29,
+    -0x1.93974a8c07c9dp-37,
+    0x1.ae7f3e733b81fp-45,
+    -0x1.6827863b97d97p-53,
+    0x1.e542ba4020225p-62,
+    -0x1.0ce396db7f853p-70,
+};
+static __device__ const double DT_SIN[12] = {
+    0x1.0000000000000p+0,
+    -0x1.5555555555555p-3,
+    0x1.1111111111111p-7,
+    -0x1.a01a01a01a01ap-13,
+    0x1.71de3a556c734p-19,
+    -0x1.ae64567f544e4p-26,
+    0x1.6124613a86d09p-33,
+    -0x1.ae7f3e733b81fp-41,
+    0x1.952c77030ad4ap-49,
+    -0x1.2f49b46814157p-57,
+    0x1.71b8ef6dcf572p-66,
+    -0x1.761b41316381ap-75,
+};
+constexpr double PI = 0x1.921fb54442d18p+1, PI_2 = 0x1.921fb54442d18p+0, PI_4 = 0x1.921fb54442d18p-1;
+__device__ __forceinline__ double asin_p(double z) {
+    const double z2 = __dmul_rn(z, z);
+    double p = DT_ASIN[25];
+#pragma unroll
+    for (int k = 24; k >= 0; --k) p = fma(p, z2, DT_ASIN[k]);
+    return __dmul_rn(z, p);
+}
+__device__ __forceinline__ double cos_p(double u) {
+    const double u2 = __dmul_rn(u, u);
+    double p = DT_COS[11];
+#pragma unroll
+    for (int k = 10; k >= 0; --k) p = fma(p, u2, DT_COS[k]);
+    return p;
+}
+__device__ __forceinline__ double sin_p(double u) {
+    const double u2 = __dmul_rn(u, u);
+    double p = DT_SIN[11];
+#pragma unroll
+    for (int k = 10; k >= 0; --k) p = fma(p, u2, DT_SIN[k]);
+    return __dmul_rn(u, p);
+}
+}  // namespace dt
+static __device__ float det_acosf(float xf) {  // xf in [-1, 1]
+    const double x = (double)xf;
+    double r;
+    if (x > 0.5) r = __dmul_rn(2.0, dt::asin_p(sqrt(__dmul_rn(__dsub_rn(1.0, x), 0.5))));
+    else if (x < -0.5) r = __dsub_rn(dt::PI, __dmul_rn(2.0, dt::asin_p(sqrt(__dmul_rn(__dadd_rn(1.0, x), 0.5)))));
+    else r = __dsub_rn(dt::PI_2, dt::asin_p(x));
+    return (float)r;
+}
+static __device__ float det_cosf(float yf) {  // yf in [0, 2 pi]
+    double y = (double)yf;
+    if (y > dt::PI) y = __dsub_rn(__dmul_rn(2.0, dt::PI), y);
+    double r;
+    if (y <= dt::PI_4) r = dt::cos_p(y);
+    else if (y <= __dmul_rn(3.0, dt::PI_4)) r = -dt::sin_p(__dsub_rn(y, dt::PI_2));
+    else r = -dt::cos_p(__dsub_rn(dt::PI, y));
+    return (float)r;
+}
 static __device__ void fast_eigen3x3(const float *Ain, float *eval, float *evec) {
     float A[9];
     float mc = Ain[0];
@@ -91,10 +191,10 @@ static __device__ void fast_eigen3x3(const float *Ain, float *eval, float *evec)
         float det = __fmaf_rn(A[2], c02, __fmaf_rn(-A[1], c01, b00 * c00)) / (p * p * p);
         float half_det = det * 0.5f;
         half_det = fminf(fmaxf(half_det, -1.0f), 1.0f);
-        float angle = acosf(half_det) / (float)3;
+        float angle = det_acosf(half_det) / (float)3;
         const float two_thirds_pi = 2.09439510239319549f;
-        float beta2 = cosf(angle) * 2;
-        float beta0 = cosf(angle + two_thirds_pi) * 2;
+        float beta2 = det_cosf(angle) * 2;
+        float beta0 = det_cosf(angle + two_thirds_pi) * 2;
         float beta1 = -(beta0 + beta2);
         eval[0] = __fmaf_rn(p, beta0, q);
         eval[1] = __fmaf_rn(p, beta1, q);

@@ -30,6 +30,16 @@ int orc_num_threads(void) {
     return 1;
 #endif
 }
+/* bench.py sets the thread count explicitly (torchrun exports OMP_NUM_THREADS=1, which would silently turn the
+ * "all host cores" baseline into a single-thread one) */
+void orc_set_num_threads(int n) {
+#ifdef _OPENMP
+    if (n <= 0) n = omp_get_num_procs();
+    omp_set_num_threads(n);
+#else
+    (void)n;
+#endif
+}
 
 static inline float dot3f(float a0, float a1, float a2, float b0, float b1,
                           float b2) {
@@ -477,6 +487,117 @@ static void eigvec1(const float *A, const float *e0v, float e1, float *out) { /*
     }
     for (int i = 0; i < 3; ++i) out[i] = fmaf(cu, U[i], -(cv * V[i]));
 }
+/* ---- deterministic acos / cos for FastEigen3x3 ------------------------------------------------------------
+ * The reference evaluates acosf / cosf of CUDA's --use_fast_math library (eigenvalue.inl:120-123); libm and libdevice
+ * differ from it and from each other in the last ulp, which is enough to flip a near-tie of the GICP search after 30
+ * iterations.  Product and oracle therefore share a SPECIFICATION (not code; the kernel side is
+ * cupoch_b200/csrc/cphb_eigen3.cuh): float64 Taylor polynomials evaluated by Horner with explicit fma, IEEE
+ * sqrt / add / mul only, result rounded once to float32 (error < 1e-16 before the rounding, i.e. correctly rounded
+ * except in astronomically rare cases).  Tables: tools/gen_trig_coeffs.py (exact rationals -> nearest double).
+ *   asin_p(z), |z| <= 0.5   = z * sum_{k<26} DT_ASIN[k] z^2k
+ *   acos(x) = pi/2 - asin_p(x)                     |x| <= 0.5
+ *           = 2 asin_p(sqrt((1 - x)/2))            x > 0.5
+ *           = pi - 2 asin_p(sqrt((1 + x)/2))       x < -0.5
+ *   cos(y), 0 <= y <= 2 pi:  y > pi -> y = 2 pi - y;  y <= pi/4: cos_p(y);  y <= 3pi/4: -sin_p(y - pi/2);
+ *                            else -cos_p(pi - y)     (cos_p / sin_p: 12 Taylor terms on |u| <= pi/4) */
+static const double DT_ASIN[26] = {
+    0x1.0000000000000p+0,
+    0x1.5555555555555p-3,
+    0x1.3333333333333p-4,
+    0x1.6db6db6db6db7p-5,
+    0x1.f1c71c71c71c7p-6,
+    0x1.6e8ba2e8ba2e9p-6,
+    0x1.1c4ec4ec4ec4fp-6,
+    0x1.c99999999999ap-7,
+    0x1.7a87878787878p-7,
+    0x1.3fde50d79435ep-7,
+    0x1.12ef3cf3cf3cfp-7,
+    0x1.df3bd37a6f4dfp-8,
+    0x1.a6863d70a3d71p-8,
+    0x1.782dda12f684cp-8,
+    0x1.51ba308d3dcb1p-8,
+    0x1.31683bdef7bdfp-8,
+    0x1.15ee9d45d1746p-8,
+    0x1.fcaf8fb6db6dbp-9,
+    0x1.d3d2a8e0dd67dp-9,
+    0x1.b026f57b13b14p-9,
+    0x1.90cb77f60c7cep-9,
+    0x1.750de64d7d05fp-9,
+    0x1.5c5f56efaaaabp-9,
+    0x1.464c0950f7d47p-9,
+    0x1.3275586c5f2f0p-9,
+    0x1.208d3570ae5a6p-9,
+};
+static const double DT_COS[12] = {
+    0x1.0000000000000p+0,
+    -0x1.0000000000000p-1,
+    0x1.5555555555555p-5,
+    -0x1.6c16c16c16c17p-10,
+    0x1.a01a01a01a01ap-16,
+    -0x1.27e4fb7789f5cp-22,
+    0x1.1eed8eff8d898p-29,
+    -0x1.93974a8c07c9dp-37,
+    0x1.ae7f3e733b81fp-45,
+    -0x1.6827863b97d97p-53,
+    0x1.e542ba4020225p-62,
+    -0x1.0ce396db7f853p-70,
+};
+static const double DT_SIN[12] = {
+    0x1.0000000000000p+0,
+    -0x1.5555555555555p-3,
+    0x1.1111111111111p-7,
+    -0x1.a01a01a01a01ap-13,
+    0x1.71de3a556c734p-19,
+    -0x1.ae64567f544e4p-26,
+    0x1.6124613a86d09p-33,
+    -0x1.ae7f3e733b81fp-41,
+    0x1.952c77030ad4ap-49,
+    -0x1.2f49b46814157p-57,
+    0x1.71b8ef6dcf572p-66,
+    -0x1.761b41316381ap-75,
+};
+#define DT_PI 0x1.921fb54442d18p+1
+#define DT_PI_2 0x1.921fb54442d18p+0
+#define DT_PI_4 0x1.921fb54442d18p-1
+static double dt_asin_p(double z) {
+    const double z2 = z * z;
+    double p = DT_ASIN[25];
+    for (int k = 24; k >= 0; --k) p = fma(p, z2, DT_ASIN[k]);
+    return z * p;
+}
+static double dt_cos_p(double u) {
+    const double u2 = u * u;
+    double p = DT_COS[11];
+    for (int k = 10; k >= 0; --k) p = fma(p, u2, DT_COS[k]);
+    return p;
+}
+static double dt_sin_p(double u) {
+    const double u2 = u * u;
+    double p = DT_SIN[11];
+    for (int k = 10; k >= 0; --k) p = fma(p, u2, DT_SIN[k]);
+    return u * p;
+}
+static float det_acosf(float xf) { /* xf in [-1, 1] */
+    const double x = (double)xf;
+    double r;
+    if (x > 0.5) r = 2.0 * dt_asin_p(sqrt((1.0 - x) * 0.5));
+    else if (x < -0.5) r = DT_PI - 2.0 * dt_asin_p(sqrt((1.0 + x) * 0.5));
+    else r = DT_PI_2 - dt_asin_p(x);
+    return (float)r;
+}
+static float det_cosf(float yf) { /* yf in [0, 2 pi] */
+    double y = (double)yf;
+    if (y > DT_PI) y = 2.0 * DT_PI - y;
+    double r;
+    if (y <= DT_PI_4) r = dt_cos_p(y);
+    else if (y <= 3.0 * DT_PI_4) r = -dt_sin_p(y - DT_PI_2);
+    else r = -dt_cos_p(DT_PI - y);
+    return (float)r;
+}
+
+float orc_det_acosf(float x) { return det_acosf(x); } /* exported for tests/test_oracle_consistency.py */
+float orc_det_cosf(float y) { return det_cosf(y); }
+
 /* FastEigen3x3 (:93-154).  evec columns: evec[3*r+c].  NOTE (reference quirk,
  * mirrored): in the general branch the eigenvalues are those of A/max_coeff --
  * they are not scaled back. */
@@ -504,10 +625,10 @@ static void fast_eigen3x3(const float *Ain, float *eval, float *evec) {
         float det = fmaf(A[2], c02, fmaf(-A[1], c01, b00 * c00)) / (p * p * p);
         float half_det = det * 0.5f;
         half_det = fminf(fmaxf(half_det, -1.0f), 1.0f);
-        float angle = acosf(half_det) / (float)3;
+        float angle = det_acosf(half_det) / (float)3;
         const float two_thirds_pi = 2.09439510239319549f;
-        float beta2 = cosf(angle) * 2;
-        float beta0 = cosf(angle + two_thirds_pi) * 2;
+        float beta2 = det_cosf(angle) * 2;
+        float beta0 = det_cosf(angle + two_thirds_pi) * 2;
         float beta1 = -(beta0 + beta2);
         eval[0] = fmaf(p, beta0, q);
         eval[1] = fmaf(p, beta1, q);

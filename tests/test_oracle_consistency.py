@@ -109,3 +109,25 @@ def test_covariance_rotation_algebra(orc):
     rot = orc.rotate_covariances(cov, T)
     R = T[:3, :3].astype(np.float64)
     np.testing.assert_allclose(rot, np.einsum("ij,njk,lk->nil", R, cov, R), atol=2e-6)
+
+
+def test_deterministic_acos_cos_are_correctly_rounded(orc):
+    """FastEigen3x3's acos / cos are a float64-polynomial specification shared by oracle and kernel (oracle.c
+    "deterministic acos / cos").  It must also be an accurate acosf / cosf: here, equal to the correctly rounded value."""
+    import ctypes as C
+    L = orc.lib()
+    L.orc_det_acosf.restype = C.c_float
+    L.orc_det_acosf.argtypes = [C.c_float]
+    L.orc_det_cosf.restype = C.c_float
+    L.orc_det_cosf.argtypes = [C.c_float]
+    rng = np.random.default_rng(0)
+    f32 = np.float32
+    xs = np.concatenate([rng.uniform(-1, 1, 20000).astype(f32),
+                         f32([-1, 1, 0, 0.5, -0.5, np.nextafter(f32(0.5), f32(1)), np.nextafter(f32(-0.5), f32(-1)),
+                              0.99999994, -0.99999994, 1e-20, -1e-20])])
+    got = np.array([L.orc_det_acosf(float(x)) for x in xs], f32)
+    np.testing.assert_array_equal(got, np.arccos(xs.astype(np.float64)).astype(f32))
+    ys = np.concatenate([rng.uniform(0, 2 * np.pi, 20000).astype(f32),
+                         f32([0, np.pi / 4, np.pi / 2, 3 * np.pi / 4, np.pi, 2 * np.pi, 3.1415929, 2.0943952, 1.0471976])])
+    got = np.array([L.orc_det_cosf(float(y)) for y in ys], f32)
+    np.testing.assert_array_equal(got, np.cos(ys.astype(np.float64)).astype(f32))
