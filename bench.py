@@ -132,30 +132,71 @@ def make_workload(n):
     return src, tgt, tn
 
 
+def cpu_threads():
+    """threads for the CPU arm: every core this process may run on.  Set explicitly -- torchrun exports
+    OMP_NUM_THREADS=1, which would silently turn the 'all host cores' baseline into a single-thread one."""
+    try:
+        n = max(1, len(os.sched_getaffinity(0)))
+    except Exception:
+        n = max(1, os.cpu_count() or 1)
+    # a container may see every core of the host but be limited by a cgroup CPU quota: more threads than the quota
+    # only adds contention (the round-1 CPU arm varied 8x between two "128-core" boxes)
+    try:
+        with open("/sys/fs/cgroup/cpu.max") as f:
+            q, per = f.read().split()[:2]
+        if q != "max":
+            n = max(1, min(n, int(int(q) / int(per))))
+    except Exception:
+        pass
+    return n
+
+
+def cpu_arm(src, tgt, tn, runs=3, budget_s=30.0, warm=0):
+    """The oracle port of cupoch's RegistrationICP (kd-tree + OpenMP) on the host cores: `runs` full registrations
+    (kd-tree build included), median time; stops early once budget_s is spent.  Returns (median seconds, all
+    seconds, last result, info)."""
+    from oracle import oracle_py as orc
+    L = orc.lib()
+    n_thr = cpu_threads()
+    L.orc_set_num_threads(n_thr)
+
+    def step():
+        return orc.registration_icp(orc.P2PLANE, src, tgt, MAX_DIST, tgt_nrm=tn, relative_fitness=0, relative_rmse=0,
+                                    max_iteration=ITERS)
+    for _ in range(warm):
+        step()
+    times, r, t_all = [], None, time.perf_counter()
+    for _ in range(max(1, runs)):
+        t0 = time.perf_counter()
+        r = step()
+        times.append(time.perf_counter() - t0)
+        if time.perf_counter() - t_all > budget_s:
+            break
+    try:
+        aff = len(os.sched_getaffinity(0))
+    except Exception:
+        aff = None
+    info = {"threads": orc.num_threads(), "nproc": os.cpu_count(), "affinity": aff,
+            "omp_num_threads_env": os.environ.get("OMP_NUM_THREADS"), "runs_s": [round(t, 3) for t in times]}
+    return float(np.median(times)), times, r, info
+
+
 def run_reference(args, rank):
-    """CPU arm: the oracle port of cupoch's RegistrationICP (kd-tree + OpenMP) on the host cores."""
+    """CPU arm: the oracle port of cupoch's RegistrationICP (kd-tree + OpenMP) on ALL host cores (rank 0 only)."""
     if rank != 0:
         return
-    from oracle import oracle_py as orc
     src, tgt, tn = make_workload(args.points)
-    def step():
-        return orc.registration_icp(orc.P2PLANE, src, tgt, MAX_DIST, tgt_nrm=tn, relative_fitness=0,
-                                    relative_rmse=0, max_iteration=ITERS)
-    for _ in range(args.warmup):
-        step()
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        r = step()
-    dt = time.perf_counter() - t0
-    v = ITERS * args.steps / dt
+    med, times, r, info = cpu_arm(src, tgt, tn, runs=max(args.steps, 3), budget_s=120.0, warm=min(args.warmup, 1))
+    v = ITERS / med
     print(json.dumps({
         "impl": "reference", "metric": "icp_iterations_per_sec", "value": v, "unit": "iter/s", "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True,
+        "steps": len(times), "warmup": min(args.warmup, 1), "ms_per_step": 1e3 * med, "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": WORKLOAD, "points": args.points, "iterations": ITERS,
-                   "step": "one RegistrationICP call incl. index (kd-tree) build"},
-        "cpu_baseline": {"value": v, "unit": "iter/s", "cores": orc.num_threads(), "kind": "port",
-                         "sample": "full workload: %d registrations x %d iterations, kd-tree build included" % (args.steps, ITERS)},
+                   "step": "one RegistrationICP call incl. index (kd-tree) build; median of the timed steps"},
+        "cpu_baseline": {"value": v, "unit": "iter/s", "cores": info["threads"], "kind": "port",
+                         "sample": "full workload: %d registrations x %d iterations, kd-tree build included, median" % (len(times), ITERS),
+                         **info},
         "e2e": {"value": v, "unit": "iter/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "final_fitness": r["fitness"], "final_rmse": r["inlier_rmse"],
     }))
@@ -275,25 +316,30 @@ def run_native(args, rank, world):
             L.cphb_stream_synchronize(None)
             sys.stderr.write("e2e upload %.3f ms\n" % (1e3 * (time.perf_counter() - t0)))
         r = R.registration_icp(s2, t2, MAX_DIST, init, est, crit, comm=comm, shard=shard)
-        # D2H: the RegistrationResult scalars (T, fitness, rmse, counts); correspondence_set_ stays on the
-        # device exactly as in the reference's RegistrationResult (registration.h:51-67)
+        # D2H: the RegistrationResult a Python user reads -- T, fitness, rmse AND the correspondence set (the
+        # reference's pybind property copies it to the host, registration.cpp:338-343)
+        cs = r.correspondence_set
         _ = (r.transformation, r.fitness, r.inlier_rmse)
-        d2h[0] = C.sizeof(_lib.IcpResult)
+        d2h[0] = C.sizeof(_lib.IcpResult) + cs.nbytes
         return r
     for _ in range(args.warmup):
         step_e2e()
     e2e_ms, res_e = timed(step_e2e, args.steps)
     h2d_bytes = h_src.nbytes + h_tgt.nbytes + h_tn.nbytes
     host_call_ms = None
-    if args.e2e_host_call:
+    if not args.no_host_call:
         # the same end-to-end measurement through ONE C-ABI call that takes the host buffers itself
-        # (cphb_registration_icp_host: uploads on a side stream, overlapped with the index build)
+        # (cphb_registration_icp_host: uploads on a side stream, overlapped with the index build; the pairs come
+        # back into a pinned host array)
+        h_pairs = np.frombuffer((C.c_int32 * (2 * len(h_src))).from_address(L.cphb_malloc_host(8 * len(h_src))), dtype=np.int32).reshape(-1, 2)
         def step_host():
-            return R.registration_icp_host(h_src, h_tgt, MAX_DIST, init, est, crit, target_normals=h_tn, comm=comm, shard=shard)
+            return R.registration_icp_host(h_src, h_tgt, MAX_DIST, init, est, crit, target_normals=h_tn, comm=comm, shard=shard,
+                                           return_correspondences=True, pairs_out=h_pairs)
         for _ in range(args.warmup):
             step_host()
         host_call_ms, res_h = timed(step_host, args.steps)
         assert np.array_equal(res_h.transformation, res_e.transformation), "host-buffer call and device call disagree"
+        assert np.array_equal(res_h.correspondence_set, res_e.correspondence_set), "host-buffer call and device call disagree"
 
     # ---- kNN leg of the metric: SearchRadius(k=1, r) of the 1M source against the 1M target ------
     tree = cph.geometry.KDTreeFlann(t_pc)
@@ -302,6 +348,23 @@ def run_native(args, rank, world):
         tree.search_radius(q_pc.points, MAX_DIST, 1)
     knn_ms, _ = timed(lambda: tree.search_radius(q_pc.points, MAX_DIST, 1), max(args.steps, 3))
     knn_steps = max(args.steps, 3)
+    # ---- sub-records (N = 1 only; each a few device milliseconds) -----------------------------------
+    extra = {}
+    if world == 1 and not args.no_extras:
+        # (a) the same registration with the certificates switched off (CPHB_CERT_GAIN=0): config 2 forces 30 iterations
+        #     on a problem that converges in ~5, so `value` mostly measures launches whose searches are skipped by their
+        #     certificates; this is the rate when every launch searches
+        os.environ["CPHB_CERT_GAIN"] = "0"
+        for _ in range(2):
+            step_resident()
+        nocert_ms, res_nc = timed(step_resident, max(args.steps, 3))
+        del os.environ["CPHB_CERT_GAIN"]
+        assert np.array_equal(res_nc.transformation, res.transformation), "certificates changed the result"
+        extra["certificates_off"] = {"value": ITERS * 1e3 / (nocert_ms / max(args.steps, 3)), "unit": "iter/s",
+                                     "loop_iters_per_sec": ITERS * 1e3 / res_nc.loop_ms,
+                                     "note": "same workload, every launch searches (CPHB_CERT_GAIN=0); identical result"}
+        # (b) config 3 of BASELINE.json: VoxelDownSample(0.02) + SearchRadius(k=1, r=0.05) on 10 M points
+        extra["config3"] = config3_records(cph, L, timed, peaks()[0], args)
     if rank == 0:
         sampler.stop_flag = True
         sampler.join(timeout=2)
@@ -357,8 +420,18 @@ def run_native(args, rank, world):
             "final": {"fitness": res.fitness, "inlier_rmse": res.inlier_rmse, "iterations": res.iterations,
                       "T": np.asarray(res.transformation).round(6).tolist()},
         }
+        # headline e2e = the faster of the two public entry points (both move the same bytes: clouds in, result and
+        # correspondence set out); both are printed
+        if host_call_ms and host_call_ms < e2e_ms:
+            out["e2e_device_api"] = dict(out["e2e"], call="PointCloud(host) + registration_icp + result.correspondence_set")
+            out["e2e"] = {"value": ITERS * 1e3 / (host_call_ms / args.steps), "unit": "iter/s", "h2d_bytes_per_step": int(h2d_bytes),
+                          "d2h_bytes_per_step": int(d2h[0]), "ms_per_step": host_call_ms / args.steps,
+                          "call": "registration_icp_host (cphb_registration_icp_host: one C-ABI call on host buffers)"}
+        else:
+            out["e2e"]["call"] = "PointCloud(host) + registration_icp + result.correspondence_set"
+        out.update(extra)
         if world == 1 and not args.no_cpu:
-            out["cpu_baseline"] = cpu_baseline(src, tgt, tn)
+            out["cpu_baseline"], out["parity_vs_cpu_baseline"] = cpu_baseline(src, tgt, tn, res_e)
         print(json.dumps(out))
     for p in (p1, p2, p3):
         L.cphb_free_host(p)
@@ -369,19 +442,60 @@ def run_native(args, rank, world):
         dist.destroy_process_group()
 
 
-def cpu_baseline(src, tgt, tn):
-    """Bounded CPU sample: ONE full 30-iteration registration with the oracle port (kd-tree + OpenMP on all host
-    cores), kd-tree build included -- the same unit of work as a GPU step (a few seconds on a many-core host)."""
-    from oracle import oracle_py as orc
-    orc.lib()
-    t0 = time.perf_counter()
-    r = orc.registration_icp(orc.P2PLANE, src, tgt, MAX_DIST, tgt_nrm=tn, relative_fitness=0, relative_rmse=0,
-                             max_iteration=ITERS)
-    dt = time.perf_counter() - t0
-    return {"value": ITERS / dt, "unit": "iter/s", "cores": orc.num_threads(), "kind": "port",
-            "sample": "one full registration: %d -> %d points, %d iterations, kd-tree build included (%.2f s)"
-                      % (len(src), len(tgt), ITERS, dt),
-            "final_fitness": r["fitness"], "final_rmse": r["inlier_rmse"]}
+def cpu_baseline(src, tgt, tn, gpu_res):
+    """Bounded CPU sample: up to 3 full 30-iteration registrations with the oracle port (kd-tree + OpenMP on all host
+    cores), kd-tree build included -- the same unit of work as a GPU step -- median; plus the parity of the GPU result
+    against this very run (BASELINE.md's "pose delta" and "index mismatches" columns)."""
+    med, times, r, info = cpu_arm(src, tgt, tn, runs=3, budget_s=25.0)
+    base = {"value": ITERS / med, "unit": "iter/s", "cores": info["threads"], "kind": "port",
+            "sample": "%d full registrations: %d -> %d points, %d iterations, kd-tree build included; median %.2f s"
+                      % (len(times), len(src), len(tgt), ITERS, med),
+            **info, "final_fitness": r["fitness"], "final_rmse": r["inlier_rmse"]}
+    a, b = gpu_res.correspondence_set, r["correspondence_set"]
+    if a.shape == b.shape and np.array_equal(a, b):
+        mism = 0
+    else:
+        ma, mb = np.full(len(src), -1, np.int64), np.full(len(src), -1, np.int64)
+        ma[a[:, 0]] = a[:, 1]
+        mb[b[:, 0]] = b[:, 1]
+        mism = int((ma != mb).sum())
+    parity = {"pose_delta_frobenius": float(np.linalg.norm(np.asarray(gpu_res.transformation, np.float64) - r["transformation"].astype(np.float64))),
+              "index_mismatches": mism, "correspondences": int(len(b)),
+              "fitness_delta": abs(float(gpu_res.fitness) - float(r["fitness"])),
+              "rmse_delta": abs(float(gpu_res.inlier_rmse) - float(r["inlier_rmse"])),
+              "tolerance": "pose <= 1e-5 Frobenius, indices bit-exact (north_star)"}
+    return base, parity
+
+
+def config3_records(cph, L, timed, peak, args):
+    """BASELINE.json config 3 as sub-records with their own roofline (SURVEY 8d bytes): VoxelDownSample(0.02) of 10 M
+    uniform points in [0,4)x[0,4)x[0,1), then SearchRadius(k=1, r=0.05) of the 10 M points against the down-sampled
+    cloud.  Index build and query ordering are inside the timed search call, as in the reference's KDTreeFlann use."""
+    from cupoch_b200.testing import datagen
+    n3 = args.points3
+    p = datagen.uniform_cube(n3, 21, hi=(4, 4, 1))
+    pc = cph.geometry.PointCloud(p)
+    for _ in range(2):
+        down = pc.voxel_down_sample(0.02)
+    reps = 5
+    v_ms, down = timed(lambda: pc.voxel_down_sample(0.02), reps)
+    v_ms /= reps
+    n_out = len(down)
+    v_bytes = 12 * n3 + 12 * n_out
+    tree = cph.geometry.KDTreeFlann(down)
+    for _ in range(2):
+        tree.search_radius(pc.points, 0.05, 1)
+    s_ms, out = timed(lambda: tree.search_radius(pc.points, 0.05, 1), reps)
+    s_ms /= reps
+    s_bytes = 32 * n3
+    b_ms, _ = timed(lambda: cph.geometry.KDTreeFlann(down), reps)
+    b_ms /= reps
+    rec = lambda ms, by: {"achieved": by / (ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s", "frac": by / (ms * 1e-3) / 1e9 / peak,
+                          "bound": "hbm", "algorithmic_bytes": by}
+    return {"workload": "config3: VoxelDownSample(0.02) + SearchRadius(k=1, r=0.05), %d points" % n3, "points": n3,
+            "voxel": {"ms": v_ms, "mpoints_per_sec": n3 / v_ms * 1e-3, "n_out": int(n_out), "roofline": rec(v_ms, v_bytes)},
+            "knn_10m": {"ms": s_ms, "mqueries_per_sec": n3 / s_ms * 1e-3, "found": int(out[0]), "targets": int(n_out),
+                        "roofline": rec(s_ms, s_bytes), "index_build_ms": b_ms}}
 
 
 def main():
@@ -392,8 +506,10 @@ def main():
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--points", type=int, default=1_000_000)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
-    ap.add_argument("--e2e-host-call", action="store_true",
-                    help="also time the end-to-end path through cphb_registration_icp_host (one call, host buffers)")
+    ap.add_argument("--e2e-host-call", action="store_true", help="(default now; kept for old command lines)")
+    ap.add_argument("--no-host-call", action="store_true", help="skip the cphb_registration_icp_host e2e variant")
+    ap.add_argument("--no-extras", action="store_true", help="skip the certificates-off and config-3 sub-records")
+    ap.add_argument("--points3", type=int, default=10_000_000, help="size of the config-3 sub-records")
     ap.add_argument("--comm", default="p2p", choices=["p2p", "nccl"],
                     help="N>1 exchange: p2p = peer-memory stores fused into the reduce kernel, nccl = ncclAllReduce")
     args = ap.parse_args()

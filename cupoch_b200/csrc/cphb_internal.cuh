@@ -187,10 +187,13 @@ __host__ __device__ __forceinline__ float ord2f(unsigned o) {
 }
 
 // squared distance, fixed operation order (DESIGN.md "arithmetic contract"):
-// d = q - p per axis; d2 = fma(dz,dz, fma(dy,dy, dx*dx))
+// d = q - p per axis; d2 = fma(dz,dz, fma(dx,dx, dy*dy)) -- the order nvcc 12.9 gives the reference's own kernel for
+// sm_100a under its --use_fast_math flags (FLANN CudaL2::dist, kdtree_cuda_3d_index.cu:221-227: SASS of
+// oracle/_ref shows FMUL dy,dy; FFMA dx,dx; FFMA dz,dz; FFMA dw,dw with dw = 0), so squared distances are bit-identical
+// to the reference binary's (tests/test_gpu_flann_ref.py)
 __device__ __forceinline__ float dist2(float qx, float qy, float qz, float px, float py, float pz) {
     float dx = qx - px, dy = qy - py, dz = qz - pz;
-    return __fmaf_rn(dz, dz, __fmaf_rn(dy, dy, __fmul_rn(dx, dx)));
+    return __fmaf_rn(dz, dz, __fmaf_rn(dx, dx, __fmul_rn(dy, dy)));
 }
 __device__ __forceinline__ float dot3(float a0, float a1, float a2, float b0, float b1, float b2) {
     return __fmaf_rn(a2, b2, __fmaf_rn(a1, b1, __fmul_rn(a0, b0)));
@@ -206,7 +209,7 @@ __device__ __forceinline__ float box_dist2(const float4 &lo, const float4 &hi, c
     float dx = fmaxf(0.f, fmaxf(lo.x - qhi[0], qlo[0] - hi.x));
     float dy = fmaxf(0.f, fmaxf(lo.y - qhi[1], qlo[1] - hi.y));
     float dz = fmaxf(0.f, fmaxf(lo.z - qhi[2], qlo[2] - hi.z));
-    return __fmaf_rn(dz, dz, __fmaf_rn(dy, dy, __fmul_rn(dx, dx)));
+    return __fmaf_rn(dz, dz, __fmaf_rn(dx, dx, __fmul_rn(dy, dy)));
 }
 
 // ---- 3-D Hilbert index, 10 bits per axis (Skilling's transpose form) --------
@@ -510,7 +513,7 @@ __device__ __forceinline__ unsigned lanes_needing(const W &w, const Box *bx) {
     float dx = fmaxf(0.f, fmaxf(lo.x - w.qx, w.qx - hi.x));
     float dy = fmaxf(0.f, fmaxf(lo.y - w.qy, w.qy - hi.y));
     float dz = fmaxf(0.f, fmaxf(lo.z - w.qz, w.qz - hi.z));
-    float d = __fmaf_rn(dz, dz, __fmaf_rn(dy, dy, __fmul_rn(dx, dx)));
+    float d = __fmaf_rn(dz, dz, __fmaf_rn(dx, dx, __fmul_rn(dy, dy)));
     return __ballot_sync(CPHB_FULL, w.valid && __float_as_uint(d) <= w.lane_bound());
 }
 

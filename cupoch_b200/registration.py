@@ -196,7 +196,7 @@ def registration_icp(source, target, max_correspondence_distance, init=None,
 def registration_icp_host(source_points, target_points, max_correspondence_distance, init=None, estimation_method=None,
                           criteria=None, source_normals=None, target_normals=None, source_colors=None, target_colors=None,
                           source_covariances=None, target_covariances=None, target_color_gradient=None, comm=None,
-                          return_correspondences=False, shard=None):
+                          return_correspondences=False, shard=None, pairs_out=None):
     """registration::RegistrationICP straight from HOST arrays ([n,3] float32 numpy, ideally in pinned memory):
     one C-ABI call (cphb_registration_icp_host) uploads both clouds on a side stream, overlapping the copies with
     the index build and the source ordering, runs the loop and returns the result -- nothing stays on the device."""
@@ -226,7 +226,12 @@ def registration_icp_host(source_points, target_points, max_correspondence_dista
     sc.cov_col_major = tc.cov_col_major = 0
     p = _params(estimation_method, max_correspondence_distance, criteria, shard)
     res = _lib.IcpResult()
-    pairs = np.empty((max(len(keep[0]), 1), 2), np.int32) if return_correspondences else None
+    pairs = None
+    if return_correspondences:
+        # pairs_out: caller's [n, 2] int32 host array (pinned memory makes the D2H copy run at full PCIe speed)
+        if pairs_out is not None and (pairs_out.dtype != np.int32 or not pairs_out.flags.c_contiguous or pairs_out.size < 2 * len(keep[0])):
+            raise ValueError("pairs_out must be a C-contiguous int32 array of at least [n_source, 2]")
+        pairs = pairs_out if pairs_out is not None else np.empty((max(len(keep[0]), 1), 2), np.int32)
     _lib.check(_lib.lib().cphb_registration_icp_host(C.byref(sc), C.byref(tc), as_f16(init), C.byref(p), comm, C.byref(res),
                                                      pairs.ctypes.data if pairs is not None else None, None))
     out = _result(res, None, False)

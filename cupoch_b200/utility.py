@@ -38,24 +38,56 @@ class DeviceArray:
         return d
 
     @classmethod
-    def borrow(cls, obj):
-        """Zero-copy view of a torch CUDA tensor / CuPy array (must be contiguous)."""
+    def borrow(cls, obj, dtype=None):
+        """Zero-copy view of a torch CUDA tensor / CuPy array (must be contiguous).  With `dtype` the element type is
+        ENFORCED: the kernels read raw float32 / int32 memory, so a float64 tensor must never be handed over as it is
+        -- torch tensors of another dtype are converted (a copy, kept alive by the view), other CUDA arrays are
+        rejected."""
+        want = None if dtype is None else np.dtype(dtype)
         if hasattr(obj, "data_ptr") and hasattr(obj, "is_cuda"):
-            if not obj.is_cuda or not obj.is_contiguous():
-                raise ValueError("need a contiguous CUDA tensor")
-            dt = {"torch.float32": np.float32, "torch.int32": np.int32, "torch.float64": np.float64}[str(obj.dtype)]
-            return cls(tuple(obj.shape), dt, ptr=obj.data_ptr(), base=obj)
+            if not obj.is_cuda:
+                raise ValueError("need a CUDA tensor")
+            names = {"torch.float32": np.float32, "torch.int32": np.int32, "torch.float64": np.float64,
+                     "torch.int64": np.int64, "torch.uint8": np.uint8, "torch.float16": np.float16}
+            have = names.get(str(obj.dtype))
+            if want is not None and (have is None or np.dtype(have) != want):
+                import torch
+                tdt = {"float32": torch.float32, "int32": torch.int32, "float64": torch.float64, "int64": torch.int64,
+                       "uint8": torch.uint8}.get(want.name)
+                if tdt is None:
+                    raise ValueError("cannot convert a %s tensor to %s" % (obj.dtype, want))
+                obj, have = obj.to(tdt), want.type
+            if have is None:
+                raise ValueError("unsupported tensor dtype %s" % obj.dtype)
+            if not obj.is_contiguous():
+                obj = obj.contiguous()
+            return cls(tuple(obj.shape), have, ptr=obj.data_ptr(), base=obj)
         cai = obj.__cuda_array_interface__
-        return cls(cai["shape"], np.dtype(cai["typestr"]), ptr=cai["data"][0], base=obj)
+        have = np.dtype(cai["typestr"])
+        if want is not None and have != want:
+            raise ValueError("expected a %s CUDA array, got %s" % (want, have))
+        if cai.get("strides") is not None:
+            st, expect = tuple(cai["strides"]), []
+            acc = have.itemsize
+            for d in reversed(tuple(cai["shape"])):
+                expect.insert(0, acc)
+                acc *= d
+            if st != tuple(expect):
+                raise ValueError("need a C-contiguous CUDA array")
+        return cls(cai["shape"], have, ptr=cai["data"][0], base=obj)
 
     @classmethod
     def wrap(cls, obj, dtype=np.float32):
-        if obj is None or isinstance(obj, DeviceArray):
+        if obj is None:
+            return obj
+        if isinstance(obj, DeviceArray):
+            if dtype is not None and obj.dtype != np.dtype(dtype):
+                raise ValueError("expected a %s device array, got %s" % (np.dtype(dtype), obj.dtype))
             return obj
         if hasattr(obj, "is_cuda") and obj.is_cuda:
-            return cls.borrow(obj)
+            return cls.borrow(obj, dtype)
         if hasattr(obj, "__cuda_array_interface__"):
-            return cls.borrow(obj)
+            return cls.borrow(obj, dtype)
         if hasattr(obj, "numpy") and not isinstance(obj, np.ndarray):
             obj = obj.numpy()
         return cls.from_numpy(np.asarray(obj), dtype)

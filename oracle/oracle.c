@@ -52,7 +52,7 @@ static inline float det2f(float a, float b, float c, float d) {
  * float4 with w=0, FMA-contracted under --use_fast_math. */
 static inline float dist2f(const float *a, const float *b) {
     float dx = a[0] - b[0], dy = a[1] - b[1], dz = a[2] - b[2];
-    return fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+    return fmaf(dz, dz, fmaf(dx, dx, dy * dy));
 }
 
 /* ======================================================================== */

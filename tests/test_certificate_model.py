@@ -33,11 +33,11 @@ def down(x):
 
 
 def d2_of(a, b):
-    """the kernels' distance arithmetic: fma(dz,dz, fma(dy,dy, dx*dx)) in float32 (emulated in float64: products of
+    """the kernels' distance arithmetic: fma(dz,dz, fma(dx,dx, dy*dy)) in float32 (emulated in float64: products of
     float32 differences are exact in float64, one rounding per fma)"""
     d = (a.astype(F) - b.astype(F)).astype(np.float64)
-    t = (d[:, 0] * d[:, 0]).astype(F).astype(np.float64)
-    t = (d[:, 1] * d[:, 1] + t).astype(F).astype(np.float64)
+    t = (d[:, 1] * d[:, 1]).astype(F).astype(np.float64)
+    t = (d[:, 0] * d[:, 0] + t).astype(F).astype(np.float64)
     return (d[:, 2] * d[:, 2] + t).astype(F)
 
 
