@@ -50,6 +50,7 @@ struct cphb_icp {
     float4 *pristine_xyz, *pristine_nrm, *pristine_cov;  // Hilbert-ordered source as given
     float4 *work_xyz, *work_nrm, *work_cov;
     float4 *src_col;
+    float4 *tix_nrm, *tix_grad, *tix_cov;  // target attributes in index order (icp_types.cuh)
     float4 *alt_xyz, *alt_nrm, *alt_cov, *alt_col, *cur_col;  // re-tiling ping-pong buffers
     int2 *alt_prev;
     uint32_t *rt_keys, *rt_keys2, *rt_vals, *rt_order;
@@ -66,7 +67,6 @@ struct cphb_icp {
     unsigned *dbg = nullptr;  // CPHB_DEBUG_CERT statistics
     cudaEvent_t *dbg_ev = nullptr;  // CPHB_DEBUG_EVENTS: 3 events per launch (before, between, after)
     unsigned grid, reduce_grid;
-    unsigned grid_search;  // ICP_DUAL: grid of the search-regime instance
     cudaStream_t stream;
 };
 
@@ -92,26 +92,25 @@ static bool is_identity4(const float *T) {  // Eigen isIdentity(1e-5), registrat
     return true;
 }
 
-// resident blocks / SM of the iteration kernel instance a context will launch (register-limited)
-template <int KIND, int MODE>
+// resident blocks / SM of the iteration kernel (register-limited)
+template <int KIND>
 static int iteration_occupancy(bool top3) {
     int nb = 0;
-    cudaError_t e = top3 ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, icp_iteration_kernel<KIND, 3, MODE>, ICP_SEARCH_WARPS * 32, 0)
-                         : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, icp_iteration_kernel<KIND, 5, MODE>, ICP_SEARCH_WARPS * 32, 0);
+    cudaError_t e = top3 ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, icp_iteration_kernel<KIND, 3>, ICP_SEARCH_WARPS * 32, 0)
+                         : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, icp_iteration_kernel<KIND, 5>, ICP_SEARCH_WARPS * 32, 0);
     if (e != cudaSuccess) { cudaGetLastError(); return 0; }
     return nb;
 }
-template <int MODE>
 static int iteration_occupancy_kind(int kind, bool top3) {
     static int cache[8][2] = {};  // 0 = not queried yet
     int &c = cache[kind & 7][top3 ? 0 : 1];
     if (c == 0) {
         switch (kind) {
-            case CPHB_EST_POINT_TO_POINT: c = iteration_occupancy<CPHB_EST_POINT_TO_POINT, MODE>(top3); break;
-            case CPHB_EST_POINT_TO_PLANE: c = iteration_occupancy<CPHB_EST_POINT_TO_PLANE, MODE>(top3); break;
-            case CPHB_EST_SYMMETRIC: c = iteration_occupancy<CPHB_EST_SYMMETRIC, MODE>(top3); break;
-            case CPHB_EST_COLORED_ICP: c = iteration_occupancy<CPHB_EST_COLORED_ICP, MODE>(top3); break;
-            case CPHB_EST_GENERALIZED_ICP: c = iteration_occupancy<CPHB_EST_GENERALIZED_ICP, MODE>(top3); break;
+            case CPHB_EST_POINT_TO_POINT: c = iteration_occupancy<CPHB_EST_POINT_TO_POINT>(top3); break;
+            case CPHB_EST_POINT_TO_PLANE: c = iteration_occupancy<CPHB_EST_POINT_TO_PLANE>(top3); break;
+            case CPHB_EST_SYMMETRIC: c = iteration_occupancy<CPHB_EST_SYMMETRIC>(top3); break;
+            case CPHB_EST_COLORED_ICP: c = iteration_occupancy<CPHB_EST_COLORED_ICP>(top3); break;
+            case CPHB_EST_GENERALIZED_ICP: c = iteration_occupancy<CPHB_EST_GENERALIZED_ICP>(top3); break;
         }
         if (c <= 0) c = -1;
     }
@@ -141,7 +140,7 @@ static void launch_pdl(K kernel, unsigned grid, unsigned block, cudaStream_t s, 
 
 template <int KIND>
 static void launch_iteration(const cphb_icp *icp, const IcpArgs &a, cudaStream_t s) {
-#if CPHB_PDL && !ICP_DUAL
+#if CPHB_PDL
     static const bool pdl = getenv("CPHB_NO_PDL") == nullptr;
     if (pdl && !a.defer_finalize && !a.step_mode && !icp->dbg_ev) {
         if (icp->index->v.top <= 3) launch_pdl(icp_iteration_kernel<KIND, 3>, icp->grid, ICP_SEARCH_WARPS * 32, s, a);
@@ -150,18 +149,8 @@ static void launch_iteration(const cphb_icp *icp, const IcpArgs &a, cudaStream_t
         return;
     }
 #endif
-#if ICP_DUAL
-    if (icp->index->v.top <= 3) {
-        CPHB_LAUNCH((icp_iteration_kernel<KIND, 3, 1>), icp->grid_search, ICP_SEARCH_WARPS * 32, 0, s, a);
-        CPHB_LAUNCH((icp_iteration_kernel<KIND, 3, 2>), icp->grid, ICP_SEARCH_WARPS * 32, 0, s, a);
-    } else {
-        CPHB_LAUNCH((icp_iteration_kernel<KIND, 5, 1>), icp->grid_search, ICP_SEARCH_WARPS * 32, 0, s, a);
-        CPHB_LAUNCH((icp_iteration_kernel<KIND, 5, 2>), icp->grid, ICP_SEARCH_WARPS * 32, 0, s, a);
-    }
-#else
     if (icp->index->v.top <= 3) CPHB_LAUNCH((icp_iteration_kernel<KIND, 3>), icp->grid, ICP_SEARCH_WARPS * 32, 0, s, a);
     else CPHB_LAUNCH((icp_iteration_kernel<KIND, 5>), icp->grid, ICP_SEARCH_WARPS * 32, 0, s, a);
-#endif
     if (icp->dbg_ev) cudaEventRecord(icp->dbg_ev[3 * a.launch_idx + 1], s);
     CPHB_LAUNCH(icp_reduce_kernel<KIND>, icp->reduce_grid, ICP_REDUCE_BLOCK, 0, s, a);
 }
@@ -233,18 +222,7 @@ extern "C" int cphb_icp_create(const cphb_cloud *source, const cphb_cloud *targe
         // every block must be resident: warps start on a static tile, and a block waiting for an SM slot
         // would hold its four tiles back until the dynamic queue has drained
         unsigned per_sm = 9u;
-#if ICP_DUAL
-        const int occ = iteration_occupancy_kind<2>(params->estimation, icp->index->v.top <= 3);
-        {
-            unsigned ps = 9u;
-            const int occ_s = iteration_occupancy_kind<1>(params->estimation, icp->index->v.top <= 3);
-            if (occ_s > 0 && (unsigned)occ_s < ps) ps = (unsigned)occ_s;
-            const unsigned cap_s = (unsigned)sms * ps;
-            icp->grid_search = want < cap_s ? want : cap_s;
-        }
-#else
-        const int occ = iteration_occupancy_kind<0>(params->estimation, icp->index->v.top <= 3);
-#endif
+        const int occ = iteration_occupancy_kind(params->estimation, icp->index->v.top <= 3);
         if (occ > 0 && (unsigned)occ < per_sm) per_sm = (unsigned)occ;
         if (const char *e = getenv("CPHB_ICP_BLOCKS_PER_SM")) {  // tuning hook
             int v = atoi(e);
@@ -270,7 +248,15 @@ extern "C" int cphb_icp_create(const cphb_cloud *source, const cphb_cloud *targe
     size_t o_pcov = want_cov ? take(sizeof(float4) * 3 * n_pad) : 0, o_wcov = want_cov ? take(sizeof(float4) * 3 * n_pad) : 0;
     size_t o_col = want_col ? take(sizeof(float4) * n_pad) : 0;
     size_t o_st = take(sizeof(IcpState));
-    size_t o_part = take(sizeof(double) * 32 * icp->reduce_grid);
+    size_t o_part = take(sizeof(double) * 32 * (icp->reduce_grid > icp->grid ? icp->reduce_grid : icp->grid));
+    // private copies of the target attributes in index order (nothing of the caller's target is retained)
+    const size_t nt_pad = (size_t)icp->index->v.n_leaves * CPHB_LEAF;
+    const int est = params->estimation;
+    const bool t_nrm = target->normals && (est == CPHB_EST_POINT_TO_PLANE || est == CPHB_EST_SYMMETRIC || est == CPHB_EST_COLORED_ICP);
+    const bool t_grad = target->color_gradient && est == CPHB_EST_COLORED_ICP;
+    const bool t_cov = target->covariances && est == CPHB_EST_GENERALIZED_ICP;
+    size_t o_tn = t_nrm ? take(sizeof(float4) * (nt_pad ? nt_pad : 1)) : 0, o_tg = t_grad ? take(sizeof(float4) * (nt_pad ? nt_pad : 1)) : 0;
+    size_t o_tc = t_cov ? take(sizeof(float4) * 3 * (nt_pad ? nt_pad : 1)) : 0;
     size_t o_ts = take(sizeof(double) * n_pad);
     size_t o_prev = take(sizeof(int2) * n_pad);
     size_t o_axyz = take(sizeof(float4) * n_pad), o_aprev = take(sizeof(int2) * n_pad);
@@ -296,6 +282,9 @@ extern "C" int cphb_icp_create(const cphb_cloud *source, const cphb_cloud *targe
     icp->src_col = want_col ? (float4 *)(b + o_col) : nullptr;
     icp->st = (IcpState *)(b + o_st);
     icp->partials = (double *)(b + o_part);
+    icp->tix_nrm = t_nrm ? (float4 *)(b + o_tn) : nullptr;
+    icp->tix_grad = t_grad ? (float4 *)(b + o_tg) : nullptr;
+    icp->tix_cov = t_cov ? (float4 *)(b + o_tc) : nullptr;
     icp->tile_sums = (double *)(b + o_ts);
     icp->prev = (int2 *)(b + o_prev);
     icp->alt_xyz = (float4 *)(b + o_axyz);
@@ -340,6 +329,10 @@ extern "C" int cphb_icp_create(const cphb_cloud *source, const cphb_cloud *targe
     CPHB_LAUNCH(gather_source_kernel, n_pad / 256, 256, 0, s, source->points, source->normals, source->colors,
                 source->covariances, source->cov_col_major, perm, lo, n, n_pad, icp->pristine_xyz, icp->pristine_nrm,
                 icp->src_col, icp->pristine_cov);
+    if ((t_nrm || t_grad || t_cov) && nt_pad)
+        CPHB_LAUNCH(gather_target_kernel, (unsigned)((nt_pad + 255) / 256), 256, 0, s, icp->index->v.pts, nt_pad, target->normals,
+                    (est == CPHB_EST_COLORED_ICP) ? target->colors : nullptr, target->color_gradient, target->covariances,
+                    target->cov_col_major, icp->tix_nrm, icp->tix_grad, icp->tix_cov);
     CPHB_CHECK_LAUNCH();
     *out = icp;
     return CPHB_OK;
@@ -367,12 +360,10 @@ static void fill_args(const cphb_icp *icp, IcpArgs &a) {
     a.src_nrm = icp->work_nrm;
     a.src_cov = icp->work_cov;
     a.src_col = icp->src_col;
-    a.tgt_xyz = icp->tgt.points;
-    a.tgt_nrm = icp->tgt.normals;
-    a.tgt_col = icp->tgt.colors;
-    a.tgt_grad = icp->tgt.color_gradient;
-    a.tgt_cov = icp->tgt.covariances;
-    a.tgt_cov_col_major = icp->tgt.cov_col_major;
+    a.tgt_nrm = icp->tix_nrm;
+    a.tgt_grad = icp->tix_grad;
+    a.tgt_cov = icp->tix_cov;
+    a.has_tgt_col = icp->tgt.colors != nullptr;
     a.st = icp->st;
     a.partials = icp->partials;
     a.tile_sums = icp->tile_sums;
@@ -434,8 +425,7 @@ static int compact_correspondences(cphb_icp *icp, int32_t *corr_out, cudaStream_
 static int retile(cphb_icp *icp, IcpArgs &a, cudaStream_t s) {
     const unsigned n_pad = icp->n_pad, grid = n_pad / 256;
     const uint32_t n_tgt_pad = (uint32_t)icp->index->v.n_leaves * CPHB_LEAF;
-    CPHB_LAUNCH(retile_key_kernel, grid, 256, 0, s, a.prev, icp->index->v.inv, icp->n_src, n_pad, n_tgt_pad, icp->rt_keys,
-                icp->rt_vals);
+    CPHB_LAUNCH(retile_key_kernel, grid, 256, 0, s, a.prev, icp->n_src, n_pad, n_tgt_pad, icp->rt_keys, icp->rt_vals);
     CPHB_CHECK_LAUNCH();
     // keys are target positions (< n_tgt_pad) or the two sentinels right above them: the stable radix sort only
     // has to look at the bits that can differ (21 for 1 M points: 3 onesweep passes instead of 4)
@@ -476,8 +466,9 @@ extern "C" int cphb_icp_run(cphb_icp *icp, const float h_init[16], cphb_comm *co
     CPHB_CUDA(cudaMemcpyAsync(icp->st, h, sizeof(IcpState), cudaMemcpyHostToDevice, s));
     static const bool dbg_cert = getenv("CPHB_DEBUG_CERT") != nullptr;
     if (dbg_cert) {
-        if (!icp->dbg) CPHB_CUDA(cudaMalloc(&icp->dbg, sizeof(unsigned) * 128));
-        CPHB_CUDA(cudaMemsetAsync(icp->dbg, 0, sizeof(unsigned) * 128, s));
+        if (!icp->dbg) CPHB_CUDA(cudaMalloc(&icp->dbg, sizeof(unsigned) * 256 + 64));
+        CPHB_CUDA(cudaMemsetAsync(icp->dbg, 0, sizeof(unsigned) * 256 + 64, s));
+        CPHB_CUDA(cudaMemsetAsync(icp->dbg + 256, 0xff, 8, s));  // slot 0 takes a minimum
     }
     IcpArgs a;
     fill_args(icp, a);
@@ -581,10 +572,19 @@ extern "C" int cphb_icp_run(cphb_icp *icp, const float h_init[16], cphb_comm *co
         icp->dbg_ev = nullptr;
     }
     if (dbg_cert && icp->dbg) {
-        unsigned hd[128];
+        unsigned hd[256 + 16];
         CPHB_CUDA(cudaMemcpy(hd, icp->dbg, sizeof(hd), cudaMemcpyDeviceToHost));
-        fprintf(stderr, "[cphb] certificates (n_src %u, tiles %u): launch: certified lanes / skipped tiles\n", icp->n_src, icp->n_pad / 32);
-        for (int it = 0; it <= a.max_iter && it < 64; ++it) fprintf(stderr, " %d:%u/%u", it, hd[it], hd[64 + it]);
+        {
+            const unsigned long long *tl = reinterpret_cast<const unsigned long long *>(hd + 256);
+            if (tl[4] && tl[0] != ~0ull)
+                fprintf(stderr, "[cphb] launch 20 timeline (us after the first block started): tile loops done %.1f, last block in %.1f, grid sum done %.1f, solve done %.1f\n",
+                        (tl[1] - tl[0]) * 1e-3, (tl[2] - tl[0]) * 1e-3, (tl[3] - tl[0]) * 1e-3, (tl[4] - tl[0]) * 1e-3);
+        }
+        fprintf(stderr, "[cphb] certificates (n_src %u, tiles %u): launch: certified lanes / skipped tiles [/ deferred tiles, * = certified regime]\n", icp->n_src, icp->n_pad / 32);
+        for (int it = 0; it <= a.max_iter && it < 64; ++it) {
+            if (hd[192 + it]) fprintf(stderr, " %d*:%u/%u/%u", it, hd[it], hd[64 + it], hd[128 + it]);
+            else fprintf(stderr, " %d:%u/%u", it, hd[it], hd[64 + it]);
+        }
         fprintf(stderr, "\n");
     }
     return CPHB_OK;

@@ -37,21 +37,50 @@ __global__ void __launch_bounds__(256) gather_source_kernel(const float *__restr
     }
 }
 
+// Private copies of the target attributes in INDEX order (icp_types.cuh): row p belongs to the point ix.pts[p].
+// Padding rows (w == -1) are zero.  intensity(): colored_icp.cu:176-181, evaluated once here instead of once per row.
+__global__ void __launch_bounds__(256) gather_target_kernel(const float4 *__restrict__ pts, size_t n_pad,
+                                                            const float *__restrict__ nrm, const float *__restrict__ col,
+                                                            const float *__restrict__ grad, const float *__restrict__ cov,
+                                                            int cov_col_major, float4 *o_nrm, float4 *o_grad, float4 *o_cov) {
+    size_t p = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (p >= n_pad) return;
+    const unsigned j = __float_as_uint(pts[p].w);
+    const bool real = j != 0xffffffffu;
+    const size_t j3 = 3 * (size_t)j;
+    if (o_nrm) {
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (real) {
+            v.x = nrm[j3]; v.y = nrm[j3 + 1]; v.z = nrm[j3 + 2];
+            if (col) v.w = intensity(col[j3], col[j3 + 1], col[j3 + 2]);
+        }
+        o_nrm[p] = v;
+    }
+    if (o_grad) o_grad[p] = real ? make_float4(grad[j3], grad[j3 + 1], grad[j3 + 2], 0.f) : make_float4(0.f, 0.f, 0.f, 0.f);
+    if (o_cov) {
+        const float *c = cov + 9 * (size_t)j;
+#pragma unroll
+        for (int r = 0; r < 3; ++r)
+            o_cov[3 * p + r] = !real ? make_float4(0.f, 0.f, 0.f, 0.f)
+                                     : cov_col_major ? make_float4(c[r], c[3 + r], c[6 + r], 0.f)
+                                                     : make_float4(c[3 * r], c[3 * r + 1], c[3 * r + 2], 0.f);
+    }
+}
+
 // ---------------------------------------------------------------------------
 // Re-tiling: once the clouds are roughly aligned, re-order the working copy by the Hilbert position of
 // each point's current match, so that a warp's 32 queries fall into one or two target leaves instead
 // of straddling a dozen.  Pure permutation of the working arrays (w / prev travel with the point): the
 // result set is unchanged, only the order in which exact products are added to the float64 sums.
 // ---------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) retile_key_kernel(const int2 *__restrict__ prev, const uint32_t *__restrict__ inv,
-                                                         unsigned n_src, unsigned n_pad, uint32_t n_tgt_pad, uint32_t *keys,
-                                                         uint32_t *vals) {
+__global__ void __launch_bounds__(256) retile_key_kernel(const int2 *__restrict__ prev, unsigned n_src, unsigned n_pad,
+                                                         uint32_t n_tgt_pad, uint32_t *keys, uint32_t *vals) {
     unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n_pad) return;
     uint32_t k = n_tgt_pad + 1u;  // padding stays last
     if (i < n_src) {
-        const int pj = prev[i].x;
-        k = (pj >= 0) ? inv[pj] : n_tgt_pad;  // unmatched points after the matched ones (target positions < n_tgt_pad)
+        const int pp = prev[i].x;  // index position of the match
+        k = (pp >= 0) ? (uint32_t)pp : n_tgt_pad;  // unmatched points after the matched ones (target positions < n_tgt_pad)
     }
     keys[i] = k;
     vals[i] = i;

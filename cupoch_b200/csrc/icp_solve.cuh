@@ -377,7 +377,7 @@ __device__ void icp_finalize(const IcpArgs &a, IcpState *st, SolveSmem &m) {
             bool have = true;
             if ((KIND == CPHB_EST_POINT_TO_PLANE || KIND == CPHB_EST_COLORED_ICP) && !a.tgt_nrm) have = false;
             if (KIND == CPHB_EST_SYMMETRIC && (!a.tgt_nrm || !a.src_nrm)) have = false;
-            if (KIND == CPHB_EST_COLORED_ICP && (!a.tgt_col || !a.src_col)) have = false;
+            if (KIND == CPHB_EST_COLORED_ICP && (!a.has_tgt_col || !a.src_col)) have = false;
             if (KIND == CPHB_EST_GENERALIZED_ICP && (!a.tgt_cov || !a.src_cov)) have = false;
             if (have) {
                 const float dt = (KIND == CPHB_EST_GENERALIZED_ICP) ? -1.f : a.det_thresh;

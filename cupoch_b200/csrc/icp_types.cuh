@@ -21,10 +21,8 @@ struct IcpState {
     unsigned tile_counter;
     unsigned cert_tiles;  // tiles skipped by their certificates in the launch just finished
     int static_sched;     // next search launch may use the static tile schedule (see icp_iteration_kernel)
-#if defined(ICP_LANE_ACC) && ICP_LANE_ACC
-    unsigned sum_rows;    // rows of tile_sums the reduce kernel adds for the launch just finished
-    unsigned pad_rows_;
-#endif
+    int tail_done;        // launch_idx + 1 of the last search launch that reduced and solved in its own tail
+    unsigned block_ticket;  // arrival counter of that tail
     long long n_corr;
     unsigned pad_local;  // host-side staging only (count of locally written correspondence pairs)
     unsigned pad_;
@@ -36,12 +34,18 @@ struct IcpArgs {
     float4 *src_nrm;        // working normals (Symmetric) or null
     float4 *src_cov;        // working covariances: 3 float4 rows per point, [3][n_pad] (GICP) or null
     const float4 *src_col;  // colors in Hilbert order (Colored) or null
-    const float *tgt_xyz, *tgt_nrm, *tgt_col, *tgt_grad, *tgt_cov;
+    // target attributes, private copies in INDEX order (position p of ix.pts <-> row p here), built once per context:
+    //   tgt_nrm[p]  = (nx, ny, nz, intensity(colour))   P2Plane / Symmetric / Colored, else null
+    //   tgt_grad[p] = (gx, gy, gz, 0)                    Colored, else null
+    //   tgt_cov[3 p + r] = row r of the covariance       GICP (row-major whatever the caller's layout), else null
+    // the matched point itself is ix.pts[p] (xyz, w = original index)
+    const float4 *tgt_nrm, *tgt_grad, *tgt_cov;
+    int has_tgt_col;
     IcpState *st;
     double *partials;     // [reduce grid][32]
     double *tile_sums;    // [n_pad/32][32]
-    int2 *prev;           // [n_pad] per Hilbert position: .x last iteration's match (-1 none), .y float bits of the
-                          // certificate slack (lower bound on the distance to every OTHER target point); or null
+    int2 *prev;           // [n_pad] per source position: .x INDEX POSITION of last iteration's match (-1 none), .y float bits
+                          // of the certificate slack (lower bound on the distance to every OTHER target point); or null
     float cert_gain;      // margin = cert_gain * displacement (0 disables the certificates)
     float cert_cap;       // matched lanes: margins above cert_cap * (point spacing in the match's leaf) are not worth
                           // the wider search (-> plain search)
@@ -56,7 +60,6 @@ struct IcpArgs {
     float r2;
     float rel_fitness, rel_rmse, det_thresh, sg, sp;
     int launch_idx, max_iter;
-    int tgt_cov_col_major;
     int defer_finalize;  // multi-GPU over NCCL: stop after writing st->local
     int use_p2p;         // multi-GPU over the fused peer-memory exchange
     P2pView p2p;

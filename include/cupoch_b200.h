@@ -231,8 +231,11 @@ typedef struct cphb_comm cphb_comm; /* multi-GPU communicator, see the end of th
 
 /* Build the per-call state of RegistrationICP (registration.cu:146-147): the
  * spatial index over target.points and a Hilbert-ordered working copy of the
- * source.  The target attribute pointers (normals, colors, gradient,
- * covariances) are RETAINED until cphb_icp_destroy; points are copied. */
+ * source.  Nothing of either cloud is retained: the target points live in the
+ * index, the target attributes the estimator reads (normals, colour
+ * intensity, colour gradient, covariances) are copied into index order, the
+ * source into its working copy -- both clouds may be freed or overwritten
+ * as soon as this call's work on `stream` has completed. */
 int cphb_icp_create(const cphb_cloud *source, const cphb_cloud *target,
                     const cphb_icp_params *params, void *stream, cphb_icp **out);
 void cphb_icp_destroy(cphb_icp *icp);
