@@ -63,6 +63,8 @@ struct cphb_icp {
     unsigned *cmp_counts;
     unsigned *cmp_total;
     double *tile_sums;
+    unsigned *flag_bits;
+    unsigned flag_words;
     int2 *prev;
     unsigned *dbg = nullptr;  // CPHB_DEBUG_CERT statistics
     cudaEvent_t *dbg_ev = nullptr;  // CPHB_DEBUG_EVENTS: 3 events per launch (before, between, after)
@@ -258,6 +260,8 @@ extern "C" int cphb_icp_create(const cphb_cloud *source, const cphb_cloud *targe
     size_t o_tn = t_nrm ? take(sizeof(float4) * (nt_pad ? nt_pad : 1)) : 0, o_tg = t_grad ? take(sizeof(float4) * (nt_pad ? nt_pad : 1)) : 0;
     size_t o_tc = t_cov ? take(sizeof(float4) * 3 * (nt_pad ? nt_pad : 1)) : 0;
     size_t o_ts = take(sizeof(double) * n_pad);
+    const unsigned flag_words = n_pad / 1024 + 1;
+    size_t o_fb = take(sizeof(unsigned) * 2 * flag_words);
     size_t o_prev = take(sizeof(int2) * n_pad);
     size_t o_axyz = take(sizeof(float4) * n_pad), o_aprev = take(sizeof(int2) * n_pad);
     size_t o_anrm = want_nrm ? take(sizeof(float4) * n_pad) : 0, o_acov = want_cov ? take(sizeof(float4) * 3 * n_pad) : 0;
@@ -286,6 +290,8 @@ extern "C" int cphb_icp_create(const cphb_cloud *source, const cphb_cloud *targe
     icp->tix_grad = t_grad ? (float4 *)(b + o_tg) : nullptr;
     icp->tix_cov = t_cov ? (float4 *)(b + o_tc) : nullptr;
     icp->tile_sums = (double *)(b + o_ts);
+    icp->flag_bits = (unsigned *)(b + o_fb);
+    icp->flag_words = flag_words;
     icp->prev = (int2 *)(b + o_prev);
     icp->alt_xyz = (float4 *)(b + o_axyz);
     icp->alt_prev = (int2 *)(b + o_aprev);
@@ -367,6 +373,11 @@ static void fill_args(const cphb_icp *icp, IcpArgs &a) {
     a.st = icp->st;
     a.partials = icp->partials;
     a.tile_sums = icp->tile_sums;
+    a.flag_bits = icp->flag_bits;
+    a.flag_words = icp->flag_words;
+    // certified regime: 1 block in 32 (at least 2 when the grid allows) only runs the tiles that needed a search last time
+    a.helper_blocks = icp->grid >= 64 ? (icp->grid / 32 > 2 ? icp->grid / 32 : 2) : 0;
+    if (const char *e = getenv("CPHB_HELPER_BLOCKS")) { int v = atoi(e); if (v >= 0 && (unsigned)v < icp->grid / 2) a.helper_blocks = (unsigned)v; }
     a.prev = icp->prev;
     a.n_src = icp->n_src;
     a.n_pad = icp->n_pad;
@@ -401,6 +412,7 @@ static void fill_args(const cphb_icp *icp, IcpArgs &a) {
 }
 
 static int reset_working_copy(cphb_icp *icp, cudaStream_t s) {
+    CPHB_CUDA(cudaMemsetAsync(icp->flag_bits, 0, sizeof(unsigned) * 2 * icp->flag_words, s));
     CPHB_CUDA(cudaMemsetAsync(icp->prev, 0xff, sizeof(int2) * icp->n_pad, s));  // no warm start at launch 0
     CPHB_CUDA(cudaMemcpyAsync(icp->work_xyz, icp->pristine_xyz, sizeof(float4) * icp->n_pad, cudaMemcpyDeviceToDevice, s));
     if (icp->work_nrm)
@@ -427,10 +439,10 @@ static int retile(cphb_icp *icp, IcpArgs &a, cudaStream_t s) {
     const uint32_t n_tgt_pad = (uint32_t)icp->index->v.n_leaves * CPHB_LEAF;
     CPHB_LAUNCH(retile_key_kernel, grid, 256, 0, s, a.prev, icp->n_src, n_pad, n_tgt_pad, icp->rt_keys, icp->rt_vals);
     CPHB_CHECK_LAUNCH();
-    // keys are target positions (< n_tgt_pad) or the two sentinels right above them: the stable radix sort only
-    // has to look at the bits that can differ (21 for 1 M points: 3 onesweep passes instead of 4)
+    // keys are target LEAVES (< n_tgt_pad / 32) or the two sentinels right above them: the stable radix sort only
+    // has to look at the bits that can differ (16 for 1 M points: 2 onesweep passes)
     int bits = 1;
-    while (bits < 32 && ((uint64_t)1 << bits) < (uint64_t)n_tgt_pad + 2u) ++bits;
+    while (bits < 32 && ((uint64_t)1 << bits) < (uint64_t)(n_tgt_pad >> 5) + 2u) ++bits;
     int rc = cphb_sort_pairs_u32(icp->rt_keys, icp->rt_keys2, icp->rt_vals, icp->rt_order, n_pad, bits, s);
     if (rc) return rc;
     float4 *o_xyz = (a.src == icp->work_xyz) ? icp->alt_xyz : icp->work_xyz;
@@ -577,8 +589,10 @@ extern "C" int cphb_icp_run(cphb_icp *icp, const float h_init[16], cphb_comm *co
         {
             const unsigned long long *tl = reinterpret_cast<const unsigned long long *>(hd + 256);
             if (tl[4] && tl[0] != ~0ull)
-                fprintf(stderr, "[cphb] launch 20 timeline (us after the first block started): tile loops done %.1f, last block in %.1f, grid sum done %.1f, solve done %.1f\n",
-                        (tl[1] - tl[0]) * 1e-3, (tl[2] - tl[0]) * 1e-3, (tl[3] - tl[0]) * 1e-3, (tl[4] - tl[0]) * 1e-3);
+                fprintf(stderr, "[cphb] launch 20 timeline (us after the first block started): tile loops done %.1f, last block in %.1f, grid sum done %.1f, "
+                        "[state read %.1f, 6x6 solved %.1f, pose composed %.1f] finalize done %.1f\n",
+                        (tl[1] - tl[0]) * 1e-3, (tl[2] - tl[0]) * 1e-3, (tl[3] - tl[0]) * 1e-3, (tl[5] - tl[0]) * 1e-3, (tl[6] - tl[0]) * 1e-3,
+                        (tl[7] - tl[0]) * 1e-3, (tl[4] - tl[0]) * 1e-3);
         }
         fprintf(stderr, "[cphb] certificates (n_src %u, tiles %u): launch: certified lanes / skipped tiles [/ deferred tiles, * = certified regime]\n", icp->n_src, icp->n_pad / 32);
         for (int it = 0; it <= a.max_iter && it < 64; ++it) {

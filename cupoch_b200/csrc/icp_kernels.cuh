@@ -18,19 +18,6 @@
 // a warp read a few consecutive 512-byte leaves instead of 32 scattered sectors per attribute.
 #pragma once
 
-// CPHB_DEBUG_CERT timeline (globaltimer ns) of launch 20: dbg[256 + 2k .. ] as u64: 0 first block start (min), 1 last warp out
-// of the tile loop (max), 2 last-arriving block enters the grid sum, 3 grid sum done, 4 solve done
-__device__ __forceinline__ unsigned long long gtime() {
-    unsigned long long t;
-    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
-    return t;
-}
-__device__ __forceinline__ void dbg_time(const IcpArgs &a, int slot, bool take_min) {
-    if (!a.dbg || a.launch_idx != 20) return;
-    unsigned long long *p = reinterpret_cast<unsigned long long *>(a.dbg + 256) + slot;
-    if (take_min) atomicMin(p, gtime());
-    else atomicMax(p, gtime());
-}
 __device__ __forceinline__ void prefetch_l1(const void *p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 // cp.async (LDGSTS): global -> shared without a register in between
 __device__ __forceinline__ void cp_async_16(void *smem, const void *gmem) {  // .cg: straight from L2, no L1 allocation
@@ -56,8 +43,11 @@ __device__ __forceinline__ void prefetch_target(const IcpArgs &a, size_t p) {
 #ifndef ICP_MIN_BLOCKS
 #define ICP_MIN_BLOCKS 4  // resident blocks / SM the register allocation targets (128 registers: 16 warps / SM)
 #endif
+// Programmatic dependent launch: the kernels of the loop are launched with stream serialisation relaxed, so the next
+// kernel's blocks are already resident (waiting in griddepcontrol.wait) while the last block of the current one sums and
+// solves: the launch latency of every kernel boundary is hidden (+3.5 % on config 2; -DCPHB_PDL=0 or CPHB_NO_PDL=1 disable)
 #ifndef CPHB_PDL
-#define CPHB_PDL 0
+#define CPHB_PDL 1
 #endif
 __device__ __forceinline__ void grid_dependency_wait() {
 #if CPHB_PDL
@@ -428,13 +418,15 @@ __global__ void __launch_bounds__(ICP_SEARCH_WARPS * 32, ICP_MIN_BLOCKS) icp_ite
         const unsigned *src = (k < 12) ? reinterpret_cast<const unsigned *>(&st->U[k])
                               : (k == 12) ? reinterpret_cast<const unsigned *>(&st->done)
                               : (k == 13) ? reinterpret_cast<const unsigned *>(&st->apply_u)
-                                          : reinterpret_cast<const unsigned *>(&st->static_sched);
+                              : (k == 14) ? reinterpret_cast<const unsigned *>(&st->static_sched)
+                                          : reinterpret_cast<const unsigned *>(&st->flag_parity);
         s_hdr[k] = *(volatile const unsigned *)src;
     }
     __syncthreads();
     const int done = (int)s_hdr[12];
     const int apply_u = (int)s_hdr[13];
     const int static_word = (int)s_hdr[14];
+    const unsigned flag_parity = s_hdr[15] & 1u;
     if (done == 2) return;
     LaunchCtx c;
     c.materialize = (done == 1);
@@ -480,6 +472,41 @@ __global__ void __launch_bounds__(ICP_SEARCH_WARPS * 32, ICP_MIN_BLOCKS) icp_ite
         // and the (match, slack) pair of the tile AFTER NEXT travel global -> shared memory by cp.async while the current
         // tile is processed; at the top of a tile the next tile's match positions are read back from shared memory and
         // the target rows they point to are pulled into L1, so those have a whole tile to arrive.
+        // Tiles that needed a search in the LAST certified launch (a stable set: the same near-equidistant points every
+        // iteration) are flagged in a bitmap.  The last `helper_blocks` blocks of the grid run exactly those tiles, bitmap
+        // word by bitmap word (a fixed assignment), from the first microsecond of the launch; the other warps skip them,
+        // so no warp of the static schedule is held up by a search -- unless a NEW tile needs one, which is handled in line
+        // and flagged for the next launch.  Every tile is processed exactly once either way.
+        const unsigned *flag_cur = a.flag_bits + flag_parity * a.flag_words;
+        unsigned *flag_next = a.flag_bits + (flag_parity ^ 1u) * a.flag_words;
+        const unsigned helper_blocks = (a.helper_blocks < gridDim.x) ? a.helper_blocks : 0u;
+        const unsigned main_blocks = gridDim.x - helper_blocks;
+        const unsigned main_warps = main_blocks * ICP_SEARCH_WARPS;
+        if (blockIdx.x >= main_blocks) {
+            // ---- helper role ----
+            double hrow = 0.0;
+            unsigned n_skip = 0;
+            const unsigned hw = (blockIdx.x - main_blocks) * ICP_SEARCH_WARPS + warp, H = helper_blocks * ICP_SEARCH_WARPS;
+            const unsigned n_words = (n_tiles + 31) / 32;
+            for (unsigned wd = hw; wd < n_words; wd += H) {
+                unsigned bits = __ldg(&flag_cur[wd]);
+                while (bits) {
+                    const unsigned t = wd * 32 + (unsigned)(__ffs(bits) - 1);
+                    bits &= bits - 1;
+                    if (t >= n_tiles) break;
+                    const float4 s = a.src[t * 32 + lane];
+                    const int2 pv = a.prev[t * 32 + lane];
+                    double acc;
+                    const bool skipped = search_tile<KIND, TOP>(a, c, w, s_rows[warp], t, s, pv, acc);
+                    hrow += acc;
+                    if (skipped) ++n_skip;
+                    else if (lane == 0) atomicOr(&flag_next[wd], 1u << (t & 31));  // still needs its search next time
+                }
+            }
+            icp_static_tail<KIND>(a, st, (double(*)[32])s_pipe, s_solve, &s_flag, hrow, c.materialize, n_skip);
+            return;
+        }
+        // ---- main role ----
         double lacc[32];
 #pragma unroll
         for (int p = 0; p < 32; ++p) lacc[p] = 0.0;
@@ -497,18 +524,19 @@ __global__ void __launch_bounds__(ICP_SEARCH_WARPS * 32, ICP_MIN_BLOCKS) icp_ite
         };
         float4 *gat = s_gat[warp];
         stage_load(tile, 0);
-        stage_load(tile + total_warps, 1);
+        stage_load(tile + main_warps, 1);
         cp_async_wait_1();  // stage 0 has landed
         if (tile < n_tiles) gather_issue<KIND>(a, gat, lane, pipe_pv[lane].x);
         cp_async_commit();
         int b = 0;
-        for (; tile < n_tiles; tile += total_warps, b ^= 1) {
+        for (; tile < n_tiles; tile += main_warps, b ^= 1) {
             // everything issued during the previous tile has had that whole tile to arrive: this tile's target rows and
             // the next tile's point / match
             cp_async_wait_0();
-            const unsigned t1 = tile + total_warps, t2 = t1 + total_warps;
+            const unsigned t1 = tile + main_warps, t2 = t1 + main_warps;
             float4 s = pipe_s[b * 32 + lane];
             const int2 pv = pipe_pv[b * 32 + lane];
+            const bool flagged = (__ldg(&flag_cur[tile >> 5]) >> (tile & 31)) & 1u;  // a helper warp runs this tile
             float4 tp = gat[lane];
             TgtVals tv;
             load_tgt_smem<KIND>(a, gat, lane, tp, tv);
@@ -526,9 +554,14 @@ __global__ void __launch_bounds__(ICP_SEARCH_WARPS * 32, ICP_MIN_BLOCKS) icp_ite
             bool cert;
             float slk, margin;
             lane_warm_start<true>(a, c, in_range, s, ox, oy, oz, pv, tp, best, cert, slk, margin);
+            if (flagged) {
+                stage_load(t2, b);
+                continue;
+            }
             const bool need_search = __any_sync(CPHB_FULL, in_range && !cert);
             if (!need_search) stage_load(t2, b);  // refill the stage just read (same lane: the reads above come first)
-            if (need_search) {  // a fraction of a percent of the tiles
+            if (need_search) {  // not predicted by the flags (the first certified launch, or a point that drifted)
+                if (lane == 0) atomicOr(&flag_next[tile >> 5], 1u << (tile & 31));
                 if (!c.materialize) {
 #pragma unroll
                     for (int p = 0; p < 32; ++p) {
@@ -675,6 +708,14 @@ __device__ void icp_static_tail(const IcpArgs &a, IcpState *st, double (*s_rowbu
     __threadfence();
     if (threadIdx.x == 0) dbg_time(a, 2, false);
     const unsigned n_tiles = a.n_pad / 32;
+    {   // every block has finished reading this launch's flag bitmap: clear it (it collects the flags of the launch after
+        // next) and make the one written during this launch current
+        const unsigned par = *(volatile unsigned *)&st->flag_parity & 1u;
+        unsigned *cur = a.flag_bits + par * a.flag_words;
+        for (unsigned k = threadIdx.x; k < a.flag_words; k += blockDim.x) cur[k] = 0u;
+        __syncthreads();
+        if (threadIdx.x == 0) st->flag_parity = par ^ 1u;
+    }
     if (materialize) {  // this launch only wrote the correspondences of an already evaluated pose
         if (threadIdx.x == 0) {
             st->block_ticket = 0; st->tile_counter = 0; st->cert_tiles = 0; st->static_sched = 0; st->done = 2;
@@ -706,6 +747,7 @@ __device__ void icp_static_tail(const IcpArgs &a, IcpState *st, double (*s_rowbu
         if (a.use_p2p) tt = p2p_exchange_sum(a.p2p, tt);  // the collective, fused: NVLink stores + flags
         if (a.defer_finalize) st->local[lane] = tt;
         else st->total[lane] = tt;
+        s_solve.S[lane] = tt;
         __syncwarp();
         if (lane == 0) dbg_time(a, 3, false);
         if (lane == 0) {
@@ -799,6 +841,7 @@ __global__ void __launch_bounds__(ICP_REDUCE_BLOCK) icp_reduce_kernel(const __gr
         if (a.use_p2p) t = p2p_exchange_sum(a.p2p, t);  // the collective, fused: NVLink stores + flags
         if (a.defer_finalize) st->local[threadIdx.x] = t;
         else st->total[threadIdx.x] = t;
+        s_solve.S[threadIdx.x] = t;
         __syncwarp();
         if (threadIdx.x == 0) {
             st->ticket = 0;
@@ -815,5 +858,9 @@ __global__ void __launch_bounds__(ICP_REDUCE_BLOCK) icp_reduce_kernel(const __gr
 template <int KIND>
 __global__ void icp_finalize_kernel(const __grid_constant__ IcpArgs a) {
     __shared__ SolveSmem s_solve;
-    if (threadIdx.x < 32 && a.st->done != 2) icp_finalize<KIND>(a, a.st, s_solve);
+    if (threadIdx.x < 32 && a.st->done != 2) {
+        s_solve.S[threadIdx.x] = a.st->total[threadIdx.x];
+        __syncwarp();
+        icp_finalize<KIND>(a, a.st, s_solve);
+    }
 }

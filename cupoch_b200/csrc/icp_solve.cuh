@@ -6,79 +6,123 @@
 // ===========================================================================
 // finalize: 6x6 solve / Kabsch / convergence (one thread)
 // ===========================================================================
-__device__ float det6_partial_piv(const float *A_in) {
-    float A[36];
-    for (int i = 0; i < 36; ++i) A[i] = A_in[i];
+// Both routines are written with compile-time indices only (pivot rows are brought in by predicated swaps over every
+// candidate row), so the 6x6 matrix lives in registers: no shared / local memory round trip on the dependent chain.
+// The arithmetic -- every operation and its order -- is that of Eigen's PartialPivLU determinant and LDLT
+// (eigen.cu:92,103) as the oracle restates them (oracle.c orc_solve_jtj).
+__device__ __forceinline__ void swapf(float &a, float &b, bool doit) {
+    const float t = a;
+    a = doit ? b : a;
+    b = doit ? t : b;
+}
+__device__ __forceinline__ float det6_partial_piv(const float *A_in) {
+    float A[6][6];
+#pragma unroll
+    for (int i = 0; i < 6; ++i)
+#pragma unroll
+        for (int j = 0; j < 6; ++j) A[i][j] = A_in[6 * i + j];
     float det = 1.f;
+#pragma unroll
     for (int k = 0; k < 6; ++k) {
         int p = k;
-        float best = fabsf(A[6 * k + k]);
+        float best = fabsf(A[k][k]);
+#pragma unroll
         for (int i = k + 1; i < 6; ++i)
-            if (fabsf(A[6 * i + k]) > best) { best = fabsf(A[6 * i + k]); p = i; }
+            if (fabsf(A[i][k]) > best) { best = fabsf(A[i][k]); p = i; }
         if (best == 0.f) return 0.f;
-        if (p != k) {
-            for (int j = 0; j < 6; ++j) { float t = A[6 * k + j]; A[6 * k + j] = A[6 * p + j]; A[6 * p + j] = t; }
-            det = -det;
-        }
-        float piv = A[6 * k + k];
+#pragma unroll
+        for (int i = k + 1; i < 6; ++i)
+#pragma unroll
+            for (int j = 0; j < 6; ++j) swapf(A[k][j], A[i][j], p == i);
+        if (p != k) det = -det;
+        const float piv = A[k][k];
         det = det * piv;
+#pragma unroll
         for (int i = k + 1; i < 6; ++i) {
-            float f = A[6 * i + k] / piv;
-            for (int j = k + 1; j < 6; ++j) A[6 * i + j] = A[6 * i + j] - f * A[6 * k + j];
+            const float f = A[i][k] / piv;
+#pragma unroll
+            for (int j = k + 1; j < 6; ++j) A[i][j] = A[i][j] - f * A[k][j];
         }
     }
     return det;
 }
 // Eigen LDLT (diagonal pivoting, lower) + solve; eigen.cu:103 A.ldlt().solve(b)
-__device__ void ldlt6_solve(const float *A_in, const float *b, float *x) {
-    float A[36];
-    for (int i = 0; i < 36; ++i) A[i] = A_in[i];
+__device__ __forceinline__ void ldlt6_solve(const float *A_in, const float *b, float *x) {
+    float A[6][6];
+#pragma unroll
+    for (int i = 0; i < 6; ++i)
+#pragma unroll
+        for (int j = 0; j < 6; ++j) A[i][j] = A_in[6 * i + j];
     int tr[6];
+#pragma unroll
     for (int k = 0; k < 6; ++k) {
         int ib = k;
-        float big = fabsf(A[6 * k + k]);
+        float big = fabsf(A[k][k]);
+#pragma unroll
         for (int i = k + 1; i < 6; ++i)
-            if (fabsf(A[6 * i + i]) > big) { big = fabsf(A[6 * i + i]); ib = i; }
+            if (fabsf(A[i][i]) > big) { big = fabsf(A[i][i]); ib = i; }
         tr[k] = ib;
-        if (ib != k) {
-            for (int j = 0; j < k; ++j) { float t = A[6 * k + j]; A[6 * k + j] = A[6 * ib + j]; A[6 * ib + j] = t; }
-            for (int i = ib + 1; i < 6; ++i) { float t = A[6 * i + k]; A[6 * i + k] = A[6 * i + ib]; A[6 * i + ib] = t; }
-            { float t = A[6 * k + k]; A[6 * k + k] = A[6 * ib + ib]; A[6 * ib + ib] = t; }
-            for (int i = k + 1; i < ib; ++i) { float t = A[6 * i + k]; A[6 * i + k] = A[6 * ib + i]; A[6 * ib + i] = t; }
+        // symmetric swap of rows / columns k and ib in the lower triangle, for whichever candidate c == ib
+#pragma unroll
+        for (int c = k + 1; c < 6; ++c) {
+            const bool doit = (ib == c);
+#pragma unroll
+            for (int j = 0; j < k; ++j) swapf(A[k][j], A[c][j], doit);
+#pragma unroll
+            for (int i = c + 1; i < 6; ++i) swapf(A[i][k], A[i][c], doit);
+            swapf(A[k][k], A[c][c], doit);
+#pragma unroll
+            for (int i = k + 1; i < c; ++i) swapf(A[i][k], A[c][i], doit);
         }
         float temp[6];
         if (k > 0) {
-            for (int j = 0; j < k; ++j) temp[j] = A[6 * j + j] * A[6 * k + j];
+#pragma unroll
+            for (int j = 0; j < k; ++j) temp[j] = A[j][j] * A[k][j];
             float s = 0.f;
-            for (int j = 0; j < k; ++j) s = s + A[6 * k + j] * temp[j];
-            A[6 * k + k] = A[6 * k + k] - s;
+#pragma unroll
+            for (int j = 0; j < k; ++j) s = s + A[k][j] * temp[j];
+            A[k][k] = A[k][k] - s;
+#pragma unroll
             for (int i = k + 1; i < 6; ++i) {
                 float s2 = 0.f;
-                for (int j = 0; j < k; ++j) s2 = s2 + A[6 * i + j] * temp[j];
-                A[6 * i + k] = A[6 * i + k] - s2;
+#pragma unroll
+                for (int j = 0; j < k; ++j) s2 = s2 + A[i][j] * temp[j];
+                A[i][k] = A[i][k] - s2;
             }
         }
-        float akk = A[6 * k + k];
+        const float akk = A[k][k];
         if (fabsf(akk) > 0.f)
-            for (int i = k + 1; i < 6; ++i) A[6 * i + k] = A[6 * i + k] / akk;
+#pragma unroll
+            for (int i = k + 1; i < 6; ++i) A[i][k] = A[i][k] / akk;
     }
     float y[6];
+#pragma unroll
     for (int i = 0; i < 6; ++i) y[i] = b[i];
+#pragma unroll
     for (int k = 0; k < 6; ++k)
-        if (tr[k] != k) { float t = y[k]; y[k] = y[tr[k]]; y[tr[k]] = t; }
+#pragma unroll
+        for (int c = k + 1; c < 6; ++c) swapf(y[k], y[c], tr[k] == c);
+#pragma unroll
     for (int i = 0; i < 6; ++i) {
         float s = y[i];
-        for (int j = 0; j < i; ++j) s = s - A[6 * i + j] * y[j];
+#pragma unroll
+        for (int j = 0; j < i; ++j) s = s - A[i][j] * y[j];
         y[i] = s;
     }
-    for (int i = 0; i < 6; ++i) y[i] = (fabsf(A[6 * i + i]) > FLT_MIN) ? y[i] / A[6 * i + i] : 0.f;
+#pragma unroll
+    for (int i = 0; i < 6; ++i) y[i] = (fabsf(A[i][i]) > FLT_MIN) ? y[i] / A[i][i] : 0.f;
+#pragma unroll
     for (int i = 5; i >= 0; --i) {
         float s = y[i];
-        for (int j = i + 1; j < 6; ++j) s = s - A[6 * j + i] * y[j];
+#pragma unroll
+        for (int j = i + 1; j < 6; ++j) s = s - A[j][i] * y[j];
         y[i] = s;
     }
+#pragma unroll
     for (int k = 5; k >= 0; --k)
-        if (tr[k] != k) { float t = y[k]; y[k] = y[tr[k]]; y[tr[k]] = t; }
+#pragma unroll
+        for (int c = k + 1; c < 6; ++c) swapf(y[k], y[c], tr[k] == c);
+#pragma unroll
     for (int i = 0; i < 6; ++i) x[i] = y[i];
 }
 __device__ void identity4(float *T) {
@@ -104,9 +148,14 @@ __device__ void se3_exp(const float *x, float *T) {  // eigen.cu:28-50
 }
 __device__ bool solve_jtj(const double *S, float det_thresh, float *T) {
     float A[36], b[6], x[6];
-    int p = 0;
-    for (int a = 0; a < 6; ++a)
-        for (int c = a; c < 6; ++c) { float v = (float)S[p++]; A[6 * a + c] = v; A[6 * c + a] = v; }
+    {
+        int p = 0;
+#pragma unroll
+        for (int a = 0; a < 6; ++a)
+#pragma unroll
+            for (int c = a; c < 6; ++c) { float v = (float)S[p++]; A[6 * a + c] = v; A[6 * c + a] = v; }
+    }
+#pragma unroll
     for (int a = 0; a < 6; ++a) b[a] = -(float)S[21 + a];
     identity4(T);
     if (det_thresh > 0) {  // eigen.cu:88-100
@@ -117,137 +166,10 @@ __device__ bool solve_jtj(const double *S, float det_thresh, float *T) {
     se3_exp(x, T);
     return true;
 }
-// ---------------------------------------------------------------------------
-// Warp-parallel versions of the 6x6 determinant / LDLT / solve above (one warp, matrices in shared memory).
-// Every scalar is produced by exactly the same operations in the same order as in the sequential code
-// (and the oracle); only independent rows / elements are spread over lanes, which shortens the dependent
-// chain of the per-iteration epilogue from ~15 us to a few us.
-// ---------------------------------------------------------------------------
 struct SolveSmem {
-    float A[36], L[36], b[8], y[8], x[8], temp[8];
     float T[16];
-    int piv, ok;
+    double S[32];  // the iteration's 32 sums, staged for the solving lane
 };
-__device__ float det6_warp(SolveSmem &m) {  // on m.L (copy of A), result broadcast to all lanes
-    const int lane = lane_id();
-    float det = 1.f;
-    for (int k = 0; k < 6; ++k) {
-        if (lane == 0) {
-            int p = k;
-            float best = fabsf(m.L[6 * k + k]);
-            for (int i = k + 1; i < 6; ++i)
-                if (fabsf(m.L[6 * i + k]) > best) { best = fabsf(m.L[6 * i + k]); p = i; }
-            m.piv = (best == 0.f) ? -1 : p;
-        }
-        __syncwarp();
-        const int p = m.piv;
-        if (p < 0) return 0.f;
-        if (p != k) {
-            if (lane < 6) { float t = m.L[6 * k + lane]; m.L[6 * k + lane] = m.L[6 * p + lane]; m.L[6 * p + lane] = t; }
-            det = -det;
-        }
-        __syncwarp();
-        const float piv = m.L[6 * k + k];
-        det = det * piv;
-        const int nr = 5 - k;  // rows/cols below/right of the pivot
-        if (lane < nr * nr) {
-            const int i = k + 1 + lane / nr, j = k + 1 + lane % nr;
-            const float f = m.L[6 * i + k] / piv;
-            m.L[6 * i + j] = m.L[6 * i + j] - f * m.L[6 * k + j];
-        }
-        __syncwarp();
-    }
-    return det;
-}
-__device__ void ldlt6_solve_warp(SolveSmem &m) {  // factors m.L (copy of A) in place, solves into m.x
-    const int lane = lane_id();
-    int tr[6];
-    for (int k = 0; k < 6; ++k) {
-        if (lane == 0) {
-            int ib = k;
-            float big = fabsf(m.L[6 * k + k]);
-            for (int i = k + 1; i < 6; ++i)
-                if (fabsf(m.L[6 * i + i]) > big) { big = fabsf(m.L[6 * i + i]); ib = i; }
-            m.piv = ib;
-        }
-        __syncwarp();
-        const int ib = m.piv;
-        tr[k] = ib;
-        if (ib != k) {  // symmetric swap of rows/cols k and ib in the lower triangle (disjoint element sets)
-            if (lane < k) { float t = m.L[6 * k + lane]; m.L[6 * k + lane] = m.L[6 * ib + lane]; m.L[6 * ib + lane] = t; }
-            if (lane > ib && lane < 6) { float t = m.L[6 * lane + k]; m.L[6 * lane + k] = m.L[6 * lane + ib]; m.L[6 * lane + ib] = t; }
-            if (lane == 31) { float t = m.L[6 * k + k]; m.L[6 * k + k] = m.L[6 * ib + ib]; m.L[6 * ib + ib] = t; }
-            if (lane > k && lane < ib) { float t = m.L[6 * lane + k]; m.L[6 * lane + k] = m.L[6 * ib + lane]; m.L[6 * ib + lane] = t; }
-        }
-        __syncwarp();
-        if (k > 0) {
-            if (lane < k) m.temp[lane] = m.L[6 * lane + lane] * m.L[6 * k + lane];
-            __syncwarp();
-            if (lane == 0) {
-                float sacc = 0.f;
-                for (int j = 0; j < k; ++j) sacc = sacc + m.L[6 * k + j] * m.temp[j];
-                m.L[6 * k + k] = m.L[6 * k + k] - sacc;
-            } else if (lane > k && lane < 6) {
-                float s2 = 0.f;
-                for (int j = 0; j < k; ++j) s2 = s2 + m.L[6 * lane + j] * m.temp[j];
-                m.L[6 * lane + k] = m.L[6 * lane + k] - s2;
-            }
-            __syncwarp();
-        }
-        const float akk = m.L[6 * k + k];
-        if (fabsf(akk) > 0.f && lane > k && lane < 6) m.L[6 * lane + k] = m.L[6 * lane + k] / akk;
-        __syncwarp();
-    }
-    if (lane == 0) {  // substitutions: short sequential chains
-        float y[6];
-        for (int i = 0; i < 6; ++i) y[i] = m.b[i];
-        for (int k = 0; k < 6; ++k)
-            if (tr[k] != k) { float t = y[k]; y[k] = y[tr[k]]; y[tr[k]] = t; }
-        for (int i = 0; i < 6; ++i) {
-            float sacc = y[i];
-            for (int j = 0; j < i; ++j) sacc = sacc - m.L[6 * i + j] * y[j];
-            y[i] = sacc;
-        }
-        for (int i = 0; i < 6; ++i) y[i] = (fabsf(m.L[6 * i + i]) > FLT_MIN) ? y[i] / m.L[6 * i + i] : 0.f;
-        for (int i = 5; i >= 0; --i) {
-            float sacc = y[i];
-            for (int j = i + 1; j < 6; ++j) sacc = sacc - m.L[6 * j + i] * y[j];
-            y[i] = sacc;
-        }
-        for (int k = 5; k >= 0; --k)
-            if (tr[k] != k) { float t = y[k]; y[k] = y[tr[k]]; y[tr[k]] = t; }
-        for (int i = 0; i < 6; ++i) m.x[i] = y[i];
-    }
-    __syncwarp();
-}
-// warp version of solve_jtj: result in m.T (all lanes may read after the call), returns success
-__device__ bool solve_jtj_warp(const double *S, float det_thresh, SolveSmem &m) {
-    const int lane = lane_id();
-    if (lane == 0) {
-        int p = 0;
-        for (int a = 0; a < 6; ++a)
-            for (int c = a; c < 6; ++c) { float v = (float)S[p++]; m.A[6 * a + c] = v; m.A[6 * c + a] = v; }
-        for (int a = 0; a < 6; ++a) m.b[a] = -(float)S[21 + a];
-        identity4(m.T);
-    }
-    __syncwarp();
-    if (det_thresh > 0) {
-        for (int e = lane; e < 36; e += 32) m.L[e] = m.A[e];
-        __syncwarp();
-        const float det = det6_warp(m);
-        if (fabsf(det) < det_thresh || isnan(det) || isinf(det)) return false;
-    }
-    for (int e = lane; e < 36; e += 32) m.L[e] = m.A[e];
-    __syncwarp();
-    ldlt6_solve_warp(m);
-    if (lane == 0) {
-        float x[6];
-        for (int i = 0; i < 6; ++i) x[i] = m.x[i];
-        se3_exp(x, m.T);
-    }
-    __syncwarp();
-    return true;
-}
 
 __device__ void matmul4(const float *A, const float *B, float *C) {  // registration.cu:159
     float R[16];
@@ -336,10 +258,11 @@ __device__ void kabsch_from_sums(const double *S, unsigned long long n_model, fl
 }
 
 // registration.cu:71-78,154-172 -- runs in ONE WARP (all 32 lanes call it) after the grid-wide sum.
+// S = m.S: the 32 sums of this iteration, staged in shared memory by the caller (also in st->total for the host)
 template <int KIND>
 __device__ void icp_finalize(const IcpArgs &a, IcpState *st, SolveSmem &m) {
     const int lane = lane_id();
-    const double *S = st->total;
+    const double *S = m.S;
     int action = 0;  // 0 = nothing more, 1 = compute an update
     double cnt = 0.0;
     if (lane == 0) {
@@ -365,6 +288,7 @@ __device__ void icp_finalize(const IcpArgs &a, IcpState *st, SolveSmem &m) {
         }
     }
     action = __shfl_sync(CPHB_FULL, action, 0);
+    if (lane == 0) dbg_time(a, 5, false);
     if (!action) return;
     const bool have_corr = __shfl_sync(CPHB_FULL, (int)(cnt > 0), 0) != 0;
     if (lane == 0) identity4(m.T);
@@ -381,7 +305,14 @@ __device__ void icp_finalize(const IcpArgs &a, IcpState *st, SolveSmem &m) {
             if (KIND == CPHB_EST_GENERALIZED_ICP && (!a.tgt_cov || !a.src_cov)) have = false;
             if (have) {
                 const float dt = (KIND == CPHB_EST_GENERALIZED_ICP) ? -1.f : a.det_thresh;
-                const bool ok = solve_jtj_warp(S, dt, m);
+                // one lane, everything in registers (the warp-parallel shared-memory version this replaces spent 7.4 us
+                // of a 60 us certified launch in __syncwarp-separated steps)
+                bool ok = true;
+                if (lane == 0) {
+                    ok = solve_jtj(S, dt, m.T);
+                    dbg_time(a, 6, false);
+                }
+                ok = __shfl_sync(CPHB_FULL, (int)ok, 0) != 0;
                 if (!ok && lane == 0) identity4(m.T);
                 if (ok && KIND == CPHB_EST_SYMMETRIC && lane == 0) {  // transformation_estimation.cu:319-339
                     double R[9], R2[9];
@@ -405,6 +336,7 @@ __device__ void icp_finalize(const IcpArgs &a, IcpState *st, SolveSmem &m) {
         tn = ((A[4 * i] * B[j] + A[4 * i + 1] * B[4 + j]) + A[4 * i + 2] * B[8 + j]) + A[4 * i + 3] * B[12 + j];
     }
     __syncwarp();
+    if (lane == 0) dbg_time(a, 7, false);
     if (lane < 16) {
         st->T[lane] = tn;
         st->U[lane] = m.T[lane];

@@ -23,6 +23,7 @@ struct IcpState {
     int static_sched;     // next search launch may use the static tile schedule (see icp_iteration_kernel)
     int tail_done;        // launch_idx + 1 of the last search launch that reduced and solved in its own tail
     unsigned block_ticket;  // arrival counter of that tail
+    unsigned flag_parity;   // which of the two tile bitmaps holds the last certified launch's "needed a search" flags
     long long n_corr;
     unsigned pad_local;  // host-side staging only (count of locally written correspondence pairs)
     unsigned pad_;
@@ -44,6 +45,9 @@ struct IcpArgs {
     IcpState *st;
     double *partials;     // [reduce grid][32]
     double *tile_sums;    // [n_pad/32][32]
+    unsigned *flag_bits;  // [2][flag_words] certified regime: bit t = tile t needed a search in the last certified launch
+    unsigned flag_words;  // words per bitmap
+    unsigned helper_blocks;  // certified regime: the last blocks of the grid run the flagged tiles (0 = none)
     int2 *prev;           // [n_pad] per source position: .x INDEX POSITION of last iteration's match (-1 none), .y float bits
                           // of the certificate slack (lower bound on the distance to every OTHER target point); or null
     float cert_gain;      // margin = cert_gain * displacement (0 disables the certificates)
@@ -80,3 +84,18 @@ __constant__ unsigned char c_pair_p2p[32][2] = {
 __constant__ unsigned c_live_jtj = 0x3fffffffu;                          // lanes 0..29
 __constant__ unsigned c_live_p2p = 0x00007fffu | (1u << 28) | (1u << 29);  // 0..14, 28, 29
 
+#ifdef __CUDACC__
+// CPHB_DEBUG_CERT timeline (globaltimer ns) of launch 20: dbg[256 + 2k .. ] as u64: 0 first block start (min), 1 last warp out
+// of the tile loop (max), 2 last-arriving block enters the grid sum, 3 grid sum done, 4 solve done, 5.. inside the solve
+__device__ __forceinline__ unsigned long long gtime() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+__device__ __forceinline__ void dbg_time(const IcpArgs &a, int slot, bool take_min) {
+    if (!a.dbg || a.launch_idx != 20) return;
+    unsigned long long *p = reinterpret_cast<unsigned long long *>(a.dbg + 256) + slot;
+    if (take_min) atomicMin(p, gtime());
+    else atomicMax(p, gtime());
+}
+#endif
