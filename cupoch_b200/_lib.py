@@ -85,6 +85,12 @@ _SIGNATURES = {
     "cphb_compute_rmse": (C.c_int, [C.c_int, C.POINTER(Cloud), C.POINTER(Cloud), _P, C.c_size_t, C.POINTER(IcpParams),
                                     C.POINTER(C.c_float), _P]),
     "cphb_kabsch": (C.c_int, [_P, C.c_size_t, _P, _P, C.c_size_t, C.POINTER(C.c_float), _P]),
+    "cphb_kabsch_weighted": (C.c_int, [_P, _P, _P, C.c_size_t, C.POINTER(C.c_float), _P]),
+    "cphb_compute_jtj_jtr": (C.c_int, [_P, _P, C.c_size_t, C.c_int, C.POINTER(C.c_double), _P]),
+    "cphb_compute_weighted_jtj_jtr": (C.c_int, [_P, _P, C.c_size_t, C.c_int, C.c_float, C.c_float, C.POINTER(C.c_double),
+                                                 C.POINTER(C.c_float), _P]),
+    "cphb_compute_fpfh_feature": (C.c_int, [_P, _P, C.c_size_t, C.c_int, C.c_float, C.c_int, _P, _P]),
+    "cphb_cluster_dbscan": (C.c_int, [_P, C.c_size_t, C.c_float, C.c_int, C.c_int, _P, C.POINTER(C.c_int), _P]),
     "cphb_reserve_pool": (C.c_int, [C.c_size_t]),
     "cphb_malloc": (_P, [C.c_size_t]),
     "cphb_free": (None, [_P]),

@@ -9,7 +9,7 @@
 // Both routines are written with compile-time indices only (pivot rows are brought in by predicated swaps over every
 // candidate row), so the 6x6 matrix lives in registers: no shared / local memory round trip on the dependent chain.
 // The arithmetic -- every operation and its order -- is that of Eigen's PartialPivLU determinant and LDLT
-// (eigen.cu:92,103) as the oracle restates them (oracle.c orc_solve_jtj).
+// (eigen.cu:92,103); the CPU oracle restates the same sequence independently.
 __device__ __forceinline__ void swapf(float &a, float &b, bool doit) {
     const float t = a;
     a = doit ? b : a;

@@ -127,7 +127,10 @@ __global__ void searchk_kernel(IndexView ix, const float *__restrict__ qxyz, con
 // ---------------------------------------------------------------------------
 // host
 // ---------------------------------------------------------------------------
-static int search_impl(const cphb_index *index, const float *query, size_t nq, float r2, int k, int32_t *idx,
+// k_limit: SearchKNN rejects knn > NUM_MAX_NN (kdtree_flann.cu:52-54); SearchRadius has no such check (:70-72) -- DBSCAN's
+// default asks for max_nn = 101 -- so there the limit is what one warp's lists can hold in shared memory
+#define CPHB_RADIUS_MAX_NN 256
+static int search_impl(const cphb_index *index, const float *query, size_t nq, float r2, int k, int k_limit, int32_t *idx,
                        float *d2, int64_t *h_count, cudaStream_t s) {
     if (!index || !query || !idx || !d2) {
         cphb_set_error("search: null argument");
@@ -138,8 +141,8 @@ static int search_impl(const cphb_index *index, const float *query, size_t nq, f
         cphb_set_error("search: empty index or query (reference returns -1)");
         return CPHB_ERR_INVALID;
     }
-    if (k < 0 || k > 100) {  // NUM_MAX_NN, kdtree_search_param.h:26
-        cphb_set_error("search: k=%d outside [0,100]", k);
+    if (k < 0 || k > k_limit) {  // NUM_MAX_NN, kdtree_search_param.h:26
+        cphb_set_error("search: k=%d outside [0,%d]", k, k_limit);
         return CPHB_ERR_INVALID;
     }
     if (h_count) *h_count = 0;
@@ -196,7 +199,7 @@ static int search_impl(const cphb_index *index, const float *query, size_t nq, f
 extern "C" int cphb_search_radius(const cphb_index *index, const float *query, size_t n_query, float radius,
                                   int max_nn, int32_t *idx, float *d2, int64_t *h_count, void *stream) {
     float r2 = radius * radius;  // kdtree_flann.inl:120 float(radius * radius); r2 == 0 matches nothing
-    return search_impl(index, query, n_query, r2, max_nn, idx, d2, h_count, (cudaStream_t)stream);
+    return search_impl(index, query, n_query, r2, max_nn, CPHB_RADIUS_MAX_NN, idx, d2, h_count, (cudaStream_t)stream);
 }
 extern "C" int cphb_search_hybrid(const cphb_index *index, const float *query, size_t n_query, float radius,
                                   int max_nn, int32_t *idx, float *d2, int64_t *h_count, void *stream) {
@@ -204,5 +207,5 @@ extern "C" int cphb_search_hybrid(const cphb_index *index, const float *query, s
 }
 extern "C" int cphb_search_knn(const cphb_index *index, const float *query, size_t n_query, int knn, int32_t *idx,
                                float *d2, int64_t *h_count, void *stream) {
-    return search_impl(index, query, n_query, INFINITY, knn, idx, d2, h_count, (cudaStream_t)stream);
+    return search_impl(index, query, n_query, INFINITY, knn, 100, idx, d2, h_count, (cudaStream_t)stream);
 }

@@ -227,6 +227,18 @@ class PointCloud:
         self.last_outlier_stats = tuple(float(x) for x in stats)  # (cloud mean, std, threshold): diagnostics
         return self._filtered(d_idx, m.value)
 
+    def cluster_dbscan(self, eps, min_points, print_progress=False, max_edges=100):
+        """PointCloud::ClusterDBSCAN (pointcloud_cluster.cu:84-179; bound as cluster_dbscan, pointcloud.cpp:228-245) ->
+        device vector of n int32 labels, -1 = noise."""
+        n = len(self)
+        labels = DeviceArray((n,), np.int32)
+        if n:
+            k = C.c_int(0)
+            _lib.check(_lib.lib().cphb_cluster_dbscan(self._points.ptr, n, float(eps), int(min_points), int(max_edges),
+                                                      labels.ptr, C.byref(k), None))
+            self.last_cluster_count = int(k.value)
+        return labels
+
     def gaussian_filter(self, search_radius, sigma2, num_max_search_points=50):
         """PointCloud::GaussianFilter (pointcloud.cu:387-433) -> new cloud (empty for illegal parameters)"""
         out = PointCloud()

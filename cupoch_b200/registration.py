@@ -314,6 +314,55 @@ def kabsch(model, target, corres=None):
     return np.array(T, np.float32).reshape(4, 4)
 
 
+def kabsch_weighted(model, target, weight):
+    """registration::KabschWeighted(model, target, weight) (kabsch.h:46-49) on device vectors / arrays."""
+    _lib.require_gpu()
+    m, t = DeviceArray.wrap(model), DeviceArray.wrap(target)
+    w = DeviceArray.wrap(np.ascontiguousarray(weight, np.float32).reshape(-1) if not isinstance(weight, DeviceArray) else weight)
+    if len(m) != len(t) or len(w) != len(m):
+        raise ValueError("model, target and weight must have the same length")
+    T = (C.c_float * 16)()
+    _lib.check(_lib.lib().cphb_kabsch_weighted(m.ptr, t.ptr, w.ptr, len(m), T, None))
+    return np.array(T, np.float32).reshape(4, 4)
+
+
+class Feature:
+    """registration::Feature<33> (feature.h): `data` is [n, 33] float32 on the device; .cpu() downloads it.  (The
+    reference stores it dimension-major for Python; here it is one row per point.)"""
+
+    def __init__(self, data):
+        self.data = data
+
+    def dimension(self):
+        return self.data.shape[1]
+
+    def num(self):
+        return self.data.shape[0]
+
+    def cpu(self):
+        return self.data.cpu()
+
+
+def compute_fpfh_feature(input, search_param):
+    """registration::ComputeFPFHFeature (fpfh.cu:192-229)."""
+    from .geometry import KDTreeSearchParamKNN, KDTreeSearchParamRadius
+    _lib.require_gpu()
+    n = len(input)
+    out = DeviceArray((n, 33), np.float32)
+    if n == 0:
+        return Feature(out)
+    if not input.has_normals():
+        raise RuntimeError("[ComputeFPFHFeature] Failed because input point cloud has no normal.")
+    if isinstance(search_param, KDTreeSearchParamKNN):
+        knn, radius, max_nn = int(search_param.knn), 0.0, 0
+    elif isinstance(search_param, KDTreeSearchParamRadius):
+        knn, radius, max_nn = 0, float(search_param.radius), int(search_param.max_nn)
+    else:
+        raise RuntimeError("Unsupport search param type.")
+    _lib.check(_lib.lib().cphb_compute_fpfh_feature(input._points.ptr, input._normals.ptr, n, knn, radius, max_nn, out.ptr, None))
+    return Feature(out)
+
+
 class IcpContext:
     """Reusable RegistrationICP state (index + Hilbert-ordered source), for repeated runs and
     the per-step test hook.  Thin wrapper over cphb_icp_create / _run / _step."""

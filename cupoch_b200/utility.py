@@ -184,3 +184,40 @@ def Matrix3fVector(a=None):
 def as_f16(T):
     T = np.ascontiguousarray(np.asarray(T, dtype=np.float32).reshape(4, 4))
     return (C.c_float * 16)(*T.reshape(16).tolist())
+
+
+def compute_jtj_jtr(J, r):
+    """utility::ComputeJTJandJTr<Matrix6f, Vector6f, NumJ> (eigen.inl:120-145) on explicit rows J [n, num_j, 6], r [n, num_j]
+    -> (JTJ [6, 6] float32, JTr [6] float32, sum r^2)"""
+    Jd = DeviceArray.wrap(J)
+    n = Jd.shape[0]
+    num_j = int(np.prod(Jd.shape[1:])) // 6
+    rd = DeviceArray.wrap(r)
+    S = (C.c_double * 32)()
+    _lib.check(_lib.lib().cphb_compute_jtj_jtr(Jd.ptr, rd.ptr, n, num_j, S, None))
+    return _unpack_sums(S)
+
+
+def compute_weighted_jtj_jtr(J, r, sigma2, nu):
+    """utility::ComputeWeightedJTJandJTr (eigen.inl:147-195) with the RGB-D odometry's Student-t weights
+    (odometry.cu:633-648) -> (JTJ, JTr, sum w r^2, w_sum)"""
+    Jd = DeviceArray.wrap(J)
+    n = Jd.shape[0]
+    num_j = int(np.prod(Jd.shape[1:])) // 6
+    rd = DeviceArray.wrap(r)
+    S = (C.c_double * 32)()
+    w = C.c_float(0)
+    _lib.check(_lib.lib().cphb_compute_weighted_jtj_jtr(Jd.ptr, rd.ptr, n, num_j, float(sigma2), float(nu), S, C.byref(w), None))
+    return _unpack_sums(S) + (float(w.value),)
+
+
+def _unpack_sums(S):
+    S = np.array(S, np.float64)
+    JTJ = np.zeros((6, 6), np.float32)
+    p = 0
+    for a in range(6):
+        for b in range(a, 6):
+            JTJ[a, b] = JTJ[b, a] = np.float32(S[p])
+            p += 1
+    return JTJ, S[21:27].astype(np.float32), float(np.float32(S[27]))
+

@@ -371,6 +371,16 @@ public:
                                                             &m, nullptr, nullptr));
         return finish_filter(kept, m);
     }
+    /// PointCloud::ClusterDBSCAN (pointcloud.h:195-199, pointcloud_cluster.cu:84-179): labels, -1 = noise
+    std::unique_ptr<utility::device_vector<int>> ClusterDBSCAN(float eps, size_t min_points, bool print_progress = false,
+                                                               size_t max_edges = 100) const {
+        (void)print_progress;
+        auto labels = std::make_unique<utility::device_vector<int>>(points_.size());
+        if (!points_.empty())
+            utility::check(cphb_cluster_dbscan(cfp(points_), points_.size(), eps, (int)min_points, (int)max_edges,
+                                               reinterpret_cast<int32_t *>(labels->data()), nullptr, nullptr));
+        return labels;
+    }
     /// PointCloud::GaussianFilter (pointcloud.cu:387-433)
     std::shared_ptr<PointCloud> GaussianFilter(float search_radius, float sigma2, size_t num_max_search_points = 50) const {
         auto out = std::make_shared<PointCloud>();
@@ -724,6 +734,48 @@ inline Eigen::Matrix4f_u Kabsch(const utility::device_vector<Eigen::Vector3f> &m
     utility::check(cphb_kabsch(reinterpret_cast<const float *>(model.data()), model.size(), reinterpret_cast<const float *>(target.data()),
                                nullptr, 0, T, nullptr));
     return utility::from_row_major(T);
+}
+/// registration::KabschWeighted (kabsch.h:46-49, kabsch.cu:138-201)
+inline Eigen::Matrix4f_u KabschWeighted(const utility::device_vector<Eigen::Vector3f> &model,
+                                        const utility::device_vector<Eigen::Vector3f> &target, const utility::device_vector<float> &weight) {
+    float T[16];
+    utility::check(cphb_kabsch_weighted(reinterpret_cast<const float *>(model.data()), reinterpret_cast<const float *>(target.data()),
+                                        weight.data(), model.size(), T, nullptr));
+    return utility::from_row_major(T);
+}
+/// registration::Feature<33> (feature.h): one row of 33 floats per point on the device
+template <int Dim>
+struct Feature {
+    utility::device_vector<float> data_;
+    size_t num_ = 0;
+    void Resize(int n) { num_ = (size_t)n; data_.resize((size_t)n * Dim); }
+    size_t Dimension() const { return Dim; }
+    size_t Num() const { return num_; }
+};
+/// registration::ComputeFPFHFeature (feature.h, fpfh.cu:192-229)
+inline std::shared_ptr<Feature<33>> ComputeFPFHFeature(const geometry::PointCloud &input,
+                                                       const knn::KDTreeSearchParam &search_param = knn::KDTreeSearchParamKNN()) {
+    auto feature = std::make_shared<Feature<33>>();
+    feature->Resize((int)input.points_.size());
+    if (!input.HasNormals()) {
+        utility::LogError("[ComputeFPFHFeature] Failed because input point cloud has no normal.");
+        return feature;
+    }
+    int knn = 0, max_nn = 0;
+    float radius = 0.f;
+    switch (search_param.GetSearchType()) {
+        case knn::KDTreeSearchParam::SearchType::Knn: knn = ((const knn::KDTreeSearchParamKNN &)search_param).knn_; break;
+        case knn::KDTreeSearchParam::SearchType::Radius:
+            radius = ((const knn::KDTreeSearchParamRadius &)search_param).radius_;
+            max_nn = ((const knn::KDTreeSearchParamRadius &)search_param).max_nn_;
+            break;
+        default: utility::LogError("Unsupport search param type."); return feature;
+    }
+    if (!input.points_.empty())
+        utility::check(cphb_compute_fpfh_feature(reinterpret_cast<const float *>(input.points_.data()),
+                                                 reinterpret_cast<const float *>(input.normals_.data()), input.points_.size(), knn, radius,
+                                                 max_nn, feature->data_.data(), nullptr));
+    return feature;
 }
 }  // namespace registration
 }  // namespace cupoch

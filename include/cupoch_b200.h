@@ -289,6 +289,32 @@ int cphb_compute_rmse(int estimation, const cphb_cloud *source, const cphb_cloud
 int cphb_kabsch(const float *model, size_t n_model, const float *target, const int32_t *corr,
                 size_t n_corr, float h_T[16], void *stream);
 
+/* registration::KabschWeighted(model, target, weight) (kabsch.h:46-49, kabsch.cu:138-201; FilterReg's M-step,
+ * filterreg.cu:80): weighted centres, H = sum w^2 (m - mc)(t - tc)^T / sum w^2, R = V diag(1,1,det(UV)) U^T. */
+int cphb_kabsch_weighted(const float *model, const float *target, const float *weight, size_t n,
+                         float h_T[16], void *stream);
+
+/* The other users of the normal-equation reducer, on EXPLICIT rows: J [n][num_j][6] and r [n][num_j]
+ * float32, device.  utility::ComputeJTJandJTr<Matrix6f, Vector6f, NumJ> (eigen.inl:120-145; RGB-D odometry,
+ * odometry.cu:618): h_sums[32] = 21 JTJ upper | 6 JTr | sum r^2 | 0... */
+int cphb_compute_jtj_jtr(const float *J, const float *r, size_t n, int num_j, double h_sums[32], void *stream);
+/* utility::ComputeWeightedJTJandJTr (eigen.inl:147-195) with the Student-t weights of the RGB-D odometry
+ * (odometry.cu:633-648, :688): w_sum = sum_i r2_i (nu + 1) / (nu + r2_i / sigma2), w_i = (nu + 1) / (nu + r2_i / w_sum),
+ * h_sums = sums of w_i * (JTJ_i, JTr_i, r2_i) laid out as above; *h_w_sum = w_sum (the caller's next sigma2). */
+int cphb_compute_weighted_jtj_jtr(const float *J, const float *r, size_t n, int num_j, float sigma2, float nu,
+                                  double h_sums[32], float *h_w_sum, void *stream);
+
+/* registration::ComputeFPFHFeature(input, search_param) (feature.h, fpfh.cu:192-229): out_features [n][33] float32.
+ * knn > 0: KDTreeSearchParamKNN(knn); else KDTreeSearchParamRadius(radius, max_nn).  Normals are required. */
+int cphb_compute_fpfh_feature(const float *points, const float *normals, size_t n, int knn, float radius,
+                              int max_nn, float *out_features, void *stream);
+
+/* geometry::PointCloud::ClusterDBSCAN(eps, min_points, print_progress, max_edges) (pointcloud.h:195-199,
+ * pointcloud_cluster.cu:84-179): labels_out (device, n int32), -1 = noise; *h_n_clusters (optional) = cluster ids
+ * handed out.  max_edges in [1, 255] (reference default NUM_MAX_NN = 100). */
+int cphb_cluster_dbscan(const float *points, size_t n, float eps, int min_points, int max_edges,
+                        int32_t *labels_out, int *h_n_clusters, void *stream);
+
 /* registration::EvaluateRegistration (registration.cu:106-119). */
 int cphb_evaluate_registration(const cphb_cloud *source, const cphb_cloud *target,
                                float max_correspondence_distance, const float h_T[16],

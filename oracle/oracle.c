@@ -1250,6 +1250,269 @@ void orc_kabsch_from_sums(const double S[17], int n_model, float T[16]) {
 }
 
 /* ======================================================================== */
+/* registration::ComputeFPFHFeature (fpfh.cu:34-229)                          */
+/* ======================================================================== */
+/* deterministic atan2f (specification shared with cupoch_b200/csrc/fpfh.cu): float64, IEEE add / mul / div / sqrt only.
+ * atan(t), t >= 0: half-angle reductions t <- t / (1 + sqrt(1 + t^2)) until t <= 0.2 (at most 3), 13 Taylor terms */
+static double dt_atan_pos(double t) {
+    int doubled = 0;
+    for (int k = 0; k < 3; ++k) {
+        if (t > 0.2) {
+            t = t / (1.0 + sqrt(1.0 + t * t));
+            ++doubled;
+        }
+    }
+    const double t2 = t * t;
+    double p = 1.0 / 25.0;
+    for (int k = 11; k >= 0; --k) p = 1.0 / (double)(2 * k + 1) - t2 * p;
+    double a = t * p;
+    for (int k = 0; k < doubled; ++k) a = 2.0 * a;
+    return a;
+}
+static float det_atan2f(float yf, float xf) {
+    const double y = (double)yf, x = (double)xf;
+    if (x == 0.0 && y == 0.0) return copysignf((signbit(xf) ? (float)DT_PI : 0.f), yf);
+    const double ay = fabs(y), ax = fabs(x);
+    double a;
+    if (ay <= ax) a = dt_atan_pos(ay / ax);
+    else a = DT_PI_2 - dt_atan_pos(ax / ay);
+    if (x < 0.0) a = DT_PI - a;
+    return (float)(y < 0.0 ? -a : a);
+}
+float orc_det_atan2f(float y, float x) { return det_atan2f(y, x); }
+/* ComputePairFeatures (fpfh.cu:34-69) */
+static void pair_features(const float *p1, const float *n1, const float *p2, const float *n2, float f[4]) {
+    float d[3] = {p2[0] - p1[0], p2[1] - p1[1], p2[2] - p1[2]};
+    f[0] = f[1] = f[2] = 0.f;
+    f[3] = sqrtf(dot3f(d[0], d[1], d[2], d[0], d[1], d[2]));
+    if (f[3] == 0.f) return;
+    float a[3] = {n1[0], n1[1], n1[2]}, b[3] = {n2[0], n2[1], n2[2]};
+    const float angle1 = dot3f(a[0], a[1], a[2], d[0], d[1], d[2]) / f[3];
+    const float angle2 = dot3f(b[0], b[1], b[2], d[0], d[1], d[2]) / f[3];
+    const float c1 = fabsf(angle1), c2 = fabsf(angle2);
+    /* acos(|x|) is NaN beyond 1 (an un-normalised normal): the reference's comparison is then false */
+    const int swap = (c1 <= 1.f && c2 <= 1.f) && (det_acosf(c1) > det_acosf(c2));
+    if (swap) {
+        for (int k = 0; k < 3; ++k) { const float t = a[k]; a[k] = b[k]; b[k] = t; d[k] = -d[k]; }
+        f[2] = -angle2;
+    } else {
+        f[2] = angle1;
+    }
+    float v[3], w[3];
+    cross3(d, a, v);
+    const float vn = sqrtf(dot3f(v[0], v[1], v[2], v[0], v[1], v[2]));
+    if (vn == 0.f) { f[0] = f[1] = f[2] = f[3] = 0.f; return; }
+    for (int k = 0; k < 3; ++k) v[k] = v[k] / vn;
+    cross3(a, v, w);
+    f[1] = dot3f(v[0], v[1], v[2], b[0], b[1], b[2]);
+    f[0] = det_atan2f(dot3f(w[0], w[1], w[2], b[0], b[1], b[2]), dot3f(a[0], a[1], a[2], b[0], b[1], b[2]));
+}
+static int hist_bin(double x) {
+    int h = (int)floor(x);
+    return h < 0 ? 0 : (h >= 11 ? 10 : h);
+}
+/* knn > 0: KDTreeSearchParamKNN, else Radius(radius, max_nn).  out [n][33].  compute_spfh_functor (:71-112) then
+ * compute_fpfh_functor (:147-190), both over the SAME neighbour table (nearest first) */
+void orc_compute_fpfh_feature(const float *pts, const float *nrm, int n, int knn, float radius, int max_nn, float *out) {
+    const int k = knn > 0 ? knn : max_nn;
+    if (n <= 0 || k <= 0) return;
+    int32_t *idx = (int32_t *)malloc(sizeof(int32_t) * (size_t)n * k);
+    float *d2 = (float *)malloc(sizeof(float) * (size_t)n * k);
+    float *spfh = (float *)calloc((size_t)n * 33, sizeof(float));
+    orc_kdtree *kd = orc_kdtree_build(pts, n);
+    orc_kdtree_search(kd, pts, n, k, knn > 0 ? -1.0f : radius, idx, d2);
+    orc_kdtree_free(kd);
+#pragma omp parallel for schedule(static)
+    for (int i = 0; i < n; ++i) {
+        float *ft = spfh + (size_t)i * 33;
+        int cnt = 0;
+        for (int q = 0; q < k; ++q) cnt += idx[(size_t)i * k + q] >= 0;
+        const float hist_incr = (float)(100.0 / (double)(float)(cnt - 1));
+        for (int q = 0; q < k; ++q) {
+            const int j = idx[(size_t)i * k + q];
+            if (j < 0 || j == i) continue;
+            float pf[4];
+            pair_features(pts + 3 * i, nrm + 3 * i, pts + 3 * j, nrm + 3 * j, pf);
+            const double PI = 3.14159265358979323846;
+            ft[hist_bin(11.0 * ((double)pf[0] + PI) / (2.0 * PI))] += hist_incr;
+            ft[11 + hist_bin(11.0 * ((double)pf[1] + 1.0) * 0.5)] += hist_incr;
+            ft[22 + hist_bin(11.0 * ((double)pf[2] + 1.0) * 0.5)] += hist_incr;
+        }
+    }
+#pragma omp parallel for schedule(static)
+    for (int i = 0; i < n; ++i) {
+        float ft[33], sum[3] = {0.f, 0.f, 0.f};
+        for (int j = 0; j < 33; ++j) ft[j] = 0.f;
+        for (int q = 0; q < k; ++q) {
+            const int nb = idx[(size_t)i * k + q];
+            if (nb < 0 || nb == i) continue;
+            const float dist = d2[(size_t)i * k + q];
+            if (dist == 0.f) continue;
+            for (int j = 0; j < 33; ++j) {
+                const float val = spfh[(size_t)nb * 33 + j] / dist;
+                sum[j / 11] = sum[j / 11] + val;
+                ft[j] = ft[j] + val;
+            }
+        }
+        for (int j = 0; j < 3; ++j)
+            if (sum[j] != 0.f) sum[j] = (float)(100.0 / (double)sum[j]);
+        for (int j = 0; j < 33; ++j) out[(size_t)i * 33 + j] = ft[j] * sum[j / 11] + spfh[(size_t)i * 33 + j];
+    }
+    free(idx);
+    free(d2);
+    free(spfh);
+}
+
+/* ======================================================================== */
+/* PointCloud::ClusterDBSCAN (pointcloud_cluster.cu:30-179)                   */
+/* ======================================================================== */
+/* Restated as the reference runs it: radius search with max_nn = max_edges + 1; degrees (:34-55: the point itself is
+ * dropped, a point with fewer than min_points other neighbours loses all its edges); for i = 0..n-1, if i is unvisited,
+ * BFS from i over the edges WITHOUT regard to earlier labels (:57-82), label the reached set with the next cluster id, or
+ * -1 when it has fewer than min_points members (:150-176).  Returns the number of cluster ids handed out. */
+int orc_cluster_dbscan(const float *pts, int n, float eps, int min_points, int max_edges, int32_t *labels) {
+    if (n <= 0) return 0;
+    const int K = max_edges + 1;
+    int32_t *idx = (int32_t *)malloc(sizeof(int32_t) * (size_t)n * K);
+    float *d2 = (float *)malloc(sizeof(float) * (size_t)n * K);
+    orc_kdtree *kd = orc_kdtree_build(pts, n);
+    orc_kdtree_search(kd, pts, n, K, eps, idx, d2);
+    orc_kdtree_free(kd);
+    int *deg = (int *)malloc(sizeof(int) * n), *xa = (int *)malloc(sizeof(int) * n), *queue = (int *)malloc(sizeof(int) * n);
+    char *visited = (char *)calloc(n, 1);
+    for (int i = 0; i < n; ++i) {
+        int c = 0;
+        for (int k = 0; k < K; ++k) {
+            const int j = idx[(size_t)i * K + k];
+            c += (j >= 0 && j != i);
+        }
+        deg[i] = (c >= min_points) ? c : 0;
+        labels[i] = -1;
+        xa[i] = -1;
+    }
+    int cluster = 0;
+    for (int i = 0; i < n; ++i) {
+        if (visited[i]) continue;
+        int head = 0, tail = 0;
+        queue[tail++] = i;
+        xa[i] = i; /* stamp = seed */
+        while (head < tail) {
+            const int u = queue[head++];
+            if (deg[u] == 0) continue;
+            for (int k = 0; k < K; ++k) {
+                const int v = idx[(size_t)u * K + k];
+                if (v < 0 || v == u || xa[v] == i) continue;
+                xa[v] = i;
+                queue[tail++] = v;
+            }
+        }
+        const int noise = tail < min_points;
+        for (int q = 0; q < tail; ++q) {
+            labels[queue[q]] = noise ? -1 : cluster;
+            visited[queue[q]] = 1;
+        }
+        if (!noise) ++cluster;
+    }
+    free(idx); free(d2); free(deg); free(xa); free(queue); free(visited);
+    return cluster;
+}
+
+/* ======================================================================== */
+/* The other users of the reducer, on explicit rows        */
+/* ======================================================================== */
+/* multiple_jtj_jtr_functor (eigen.inl:48-70): per element, rows in order, float32 */
+static void private_sums(const float *J, const float *r, int i, int num_j, float v[28]) {
+    for (int k = 0; k < 28; ++k) v[k] = 0.f;
+    for (int j = 0; j < num_j; ++j) {
+        const float *x = J + ((size_t)i * num_j + j) * 6;
+        const float rr = r[(size_t)i * num_j + j];
+        int p = 0;
+        for (int a = 0; a < 6; ++a)
+            for (int b = a; b < 6; ++b) { v[p] = v[p] + x[a] * x[b]; ++p; }
+        for (int a = 0; a < 6; ++a) v[21 + a] = v[21 + a] + x[a] * rr;
+        v[27] = v[27] + rr * rr;
+    }
+}
+/* utility::ComputeJTJandJTr<Matrix6f, Vector6f, NumJ> (eigen.inl:120-145): sums[0..20] JTJ upper, [21..26] JTr, [27] r^2;
+ * float32 per-element values accumulated in float64 (the order-independent limit of thrust's float reduction) */
+void orc_jtj_rows(const float *J, const float *r, int n, int num_j, double sums[32]) {
+    for (int k = 0; k < 32; ++k) sums[k] = 0.0;
+    for (int i = 0; i < n; ++i) {
+        float v[28];
+        private_sums(J, r, i, num_j, v);
+        for (int k = 0; k < 28; ++k) sums[k] += (double)v[k];
+    }
+}
+/* utility::ComputeWeightedJTJandJTr (eigen.inl:147-195) with the RGB-D odometry's Student-t weights
+ * (odometry.cu:633-648): w_sum = sum_i r2_i (nu + 1.0) / (nu + r2_i / sigma2)   [double product and quotient: the 1.0
+ * literal], w_i = (nu + 1) / (nu + r2_i / w_sum)   [float], sums of w_i * (JTJ_i, JTr_i, r2_i). */
+float orc_weighted_jtj_rows(const float *J, const float *r, int n, int num_j, float sigma2, float nu, double sums[32]) {
+    double ws = 0.0;
+    for (int i = 0; i < n; ++i) {
+        float v[28];
+        private_sums(J, r, i, num_j, v);
+        const float r2 = v[27];
+        const float den = nu + r2 / sigma2;
+        ws += (double)(float)(((double)r2 * ((double)nu + 1.0)) / (double)den);
+    }
+    const float w_sum = (float)ws;
+    for (int k = 0; k < 32; ++k) sums[k] = 0.0;
+    for (int i = 0; i < n; ++i) {
+        float v[28];
+        private_sums(J, r, i, num_j, v);
+        const float w = (nu + 1.f) / (nu + v[27] / w_sum);
+        for (int k = 0; k < 28; ++k) sums[k] += (double)(v[k] * w);
+    }
+    return w_sum;
+}
+/* registration::KabschWeighted (kabsch.cu:138-201): weighted centres, H = sum w^2 (m - mc)(t - tc)^T / sum w^2,
+ * R = V diag(1, 1, det(U V)) U^T, t = tc - R mc */
+void orc_kabsch_weighted(const float *model, const float *target, const float *weight, int n, float T[16]) {
+    memset(T, 0, 64);
+    T[0] = T[5] = T[10] = T[15] = 1.f;
+    if (n <= 0) return;
+    double sw = 0, sm[3] = {0, 0, 0}, st[3] = {0, 0, 0}, sww = 0;
+    for (int i = 0; i < n; ++i) {
+        const float w = weight[i];
+        sw += (double)w;
+        for (int a = 0; a < 3; ++a) {
+            sm[a] += (double)(model[3 * i + a] * w);
+            st[a] += (double)(target[3 * i + a] * w);
+        }
+        sww += (double)(w * w);
+    }
+    const float divided_by = 1.0f / (float)sw;
+    float mc[3], tc[3];
+    for (int a = 0; a < 3; ++a) { mc[a] = (float)sm[a] * divided_by; tc[a] = (float)st[a] * divided_by; }
+    const float h_weight = (float)sww;
+    double hs[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+    for (int i = 0; i < n; ++i) {
+        const float w = weight[i], ww = w * w;
+        float cx[3], cy[3];
+        for (int a = 0; a < 3; ++a) { cx[a] = ww * (model[3 * i + a] - mc[a]); cy[a] = target[3 * i + a] - tc[a]; }
+        for (int a = 0; a < 3; ++a)
+            for (int b = 0; b < 3; ++b) hs[3 * a + b] += (double)(cx[a] * cy[b]);
+    }
+    double H[9];
+    for (int k = 0; k < 9; ++k) H[k] = (double)((float)hs[k] / h_weight);
+    double U[9], sv[3], V[9], UV[9];
+    svd3(H, U, sv, V);
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j) UV[3 * i + j] = U[3 * i] * V[j] + U[3 * i + 1] * V[3 + j] + U[3 * i + 2] * V[6 + j];
+    double ss[3] = {1.0, 1.0, det3d(UV)};
+    for (int i = 0; i < 3; ++i) {
+        float Rf[3];
+        for (int j = 0; j < 3; ++j) {
+            double rr = 0;
+            for (int k = 0; k < 3; ++k) rr += V[3 * i + k] * ss[k] * U[3 * j + k];
+            Rf[j] = (float)rr;
+            T[4 * i + j] = Rf[j];
+        }
+        T[4 * i + 3] = tc[i] - ((Rf[0] * mc[0] + Rf[1] * mc[1]) + Rf[2] * mc[2]);
+    }
+}
+
+/* ======================================================================== */
 /* registration.cu:33-80 GetRegistrationResultAndCorrespondences             */
 /* ======================================================================== */
 void orc_correspondences(const float *src, int n, const float *tgt, int m,

@@ -251,6 +251,46 @@ def kabsch(src, tgt, corr, n_model=None):
     return T.reshape(4, 4), S
 
 
+def jtj_rows(J, r):
+    """utility::ComputeJTJandJTr<.., NumJ> on explicit rows J [n, num_j, 6], r [n, num_j] -> 32 float64 sums"""
+    J = np.ascontiguousarray(J, np.float32)
+    r = np.ascontiguousarray(r, np.float32).reshape(J.shape[0], -1)
+    sums = np.zeros(32, np.float64)
+    lib().orc_jtj_rows(_p(J), _p(r), C.c_int(J.shape[0]), C.c_int(r.shape[1]), _p(sums))
+    return sums
+
+
+def weighted_jtj_rows(J, r, sigma2, nu):
+    """utility::ComputeWeightedJTJandJTr with the odometry's Student-t weights -> (32 float64 sums, w_sum)"""
+    J = np.ascontiguousarray(J, np.float32)
+    r = np.ascontiguousarray(r, np.float32).reshape(J.shape[0], -1)
+    sums = np.zeros(32, np.float64)
+    lib().orc_weighted_jtj_rows.restype = C.c_float
+    w = lib().orc_weighted_jtj_rows(_p(J), _p(r), C.c_int(J.shape[0]), C.c_int(r.shape[1]), C.c_float(sigma2), C.c_float(nu), _p(sums))
+    return sums, float(w)
+
+
+def kabsch_weighted(model, target, weight):
+    model, target, weight = _f(model).reshape(-1, 3), _f(target).reshape(-1, 3), _f(weight).reshape(-1)
+    T = np.zeros(16, np.float32)
+    lib().orc_kabsch_weighted(_p(model), _p(target), _p(weight), C.c_int(len(model)), _p(T))
+    return T.reshape(4, 4)
+
+
+def compute_fpfh_feature(pts, nrm, knn=0, radius=0.0, max_nn=0):
+    pts, nrm = _f(pts).reshape(-1, 3), _f(nrm).reshape(-1, 3)
+    out = np.zeros((len(pts), 33), np.float32)
+    lib().orc_compute_fpfh_feature(_p(pts), _p(nrm), C.c_int(len(pts)), C.c_int(knn), C.c_float(radius), C.c_int(max_nn), _p(out))
+    return out
+
+
+def cluster_dbscan(pts, eps, min_points, max_edges=100):
+    pts = _f(pts).reshape(-1, 3)
+    labels = np.empty(len(pts), np.int32)
+    n = lib().orc_cluster_dbscan(_p(pts), C.c_int(len(pts)), C.c_float(eps), C.c_int(min_points), C.c_int(max_edges), _p(labels))
+    return labels, int(n)
+
+
 def correspondences(src, tgt, max_distance, kdtree=True):
     src, tgt = _f(src).reshape(-1, 3), _f(tgt).reshape(-1, 3)
     n = len(src)

@@ -93,6 +93,30 @@ int main() {
         auto grid2 = geometry::VoxelGrid::CreateFromPointCloud(pc, 0.5f);
         EXPECT(grid2->voxels_keys_.size() == 1 && grid2->HasVoxels());
     }
+    {   // DBSCAN, FPFH, KabschWeighted: two well separated blobs of 60 points each
+        std::vector<Eigen::Vector3f> pts, nrm;
+        for (int b = 0; b < 2; ++b)
+            for (int i = 0; i < 60; ++i) {
+                pts.push_back(Eigen::Vector3f(10.0f * b + 0.01f * (i % 8), 0.01f * (i / 8), 0.002f * (i % 3)));
+                nrm.push_back(Eigen::Vector3f(0, 0, 1));
+            }
+        geometry::PointCloud pc;
+        pc.SetPoints(pts);
+        pc.SetNormals(nrm);
+        auto labels = pc.ClusterDBSCAN(0.05f, 5);
+        auto hl = labels->to_host();
+        EXPECT(hl.size() == 120 && hl[0] == 0 && hl[59] == 0 && hl[60] == 1 && hl[119] == 1);
+        auto fp = registration::ComputeFPFHFeature(pc, knn::KDTreeSearchParamKNN(10));
+        EXPECT(fp->Num() == 120 && fp->Dimension() == 33);
+        auto hf = fp->data_.to_host();
+        float s0 = 0;
+        for (int j = 0; j < 11; ++j) s0 += hf[j];
+        EXPECT(std::fabs(s0 - 200.0f) < 1e-2f);  // every 11-bin block of an FPFH row sums to 100 (own SPFH) + 100 (neighbours)
+        utility::device_vector<float> w(std::vector<float>(120, 0.5f));
+        utility::device_vector<Eigen::Vector3f> moved(pts);
+        auto T = registration::KabschWeighted(pc.points_, moved, w);
+        EXPECT(std::fabs(T(0, 0) - 1.0f) < 1e-5f && std::fabs(T(0, 3)) < 1e-4f);
+    }
     if (fails) return 1;
     std::printf("facade filters: all expectations met\n");
     return 0;
