@@ -17,6 +17,7 @@
 // The table is sized by min(n, #grid cells) so for dense grids it stays L2 resident.
 #include <float.h>
 #include <math.h>
+#include <stdlib.h>
 
 #include "cphb_internal.cuh"
 
@@ -158,6 +159,210 @@ __global__ void __launch_bounds__(256) voxel_final_kernel(const unsigned *__rest
     }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Dense-grid path.  When the grid has no more cells than about twice the points (config 3 of BASELINE.json: 10 M points
+// in 2.0 M cells), hashing buys nothing: every cell gets one 32-byte-aligned accumulator row [sum x, sum y, sum z, count]
+// (+ the attribute sums) addressed directly by its lexicographic cell number, so
+//   * there is no insert pass, no probe, no dense-id table, and the accumulators of the whole grid (64 MB at config 3)
+//     stay L2-resident instead of competing with a 48 MB key / id table (the hash path's accumulate pass moved 980 MB of
+//     DRAM traffic for 120 MB of points: profiles/r2_ops_launches.md);
+//   * a cell's atomics fall into one sector;
+//   * the cells are already in the reference's output order (helper.h:113-121): an ordered compaction replaces the
+//     radix sort of the voxel keys.
+// Sums are float64 atomics of float32 values exactly as in the hash path (the same, order-independent-to-1e-16 result).
+// ---------------------------------------------------------------------------------------------------------------------
+struct DenseGrid {
+    float org[3];
+    float voxel;
+    unsigned dy, dz;  // cells along y and z: cell = (kx * dy + ky) * dz + kz
+};
+template <int A>
+__host__ __device__ constexpr int dense_stride() { return A == 1 ? 4 : A == 2 ? 8 : 12; }  // doubles per cell (32-B multiples)
+
+template <int A>
+__global__ void __launch_bounds__(256) voxel_dense_accum_kernel(const float *__restrict__ pts, const float *__restrict__ a1,
+                                                                const float *__restrict__ a2, size_t n, DenseGrid g,
+                                                                double *acc) {
+    constexpr int S = dense_stride<A>();
+    // 4 consecutive points per thread: 48 B = three 16-byte loads per array when the base is 16-byte aligned
+    const size_t i0 = (blockIdx.x * (size_t)blockDim.x + threadIdx.x) * 4;
+    if (i0 >= n) return;
+    float p[12], q1[12], q2[12];
+    const bool vec = (i0 + 4 <= n) && ((reinterpret_cast<uintptr_t>(pts) & 15) == 0) &&
+                     (A < 2 || (reinterpret_cast<uintptr_t>(a1) & 15) == 0) && (A < 3 || (reinterpret_cast<uintptr_t>(a2) & 15) == 0);
+    const int cnt = (i0 + 4 <= n) ? 4 : (int)(n - i0);
+    if (vec) {
+#pragma unroll
+        for (int v = 0; v < 3; ++v) {
+            const float4 x = reinterpret_cast<const float4 *>(pts + 3 * i0)[v];
+            p[4 * v] = x.x; p[4 * v + 1] = x.y; p[4 * v + 2] = x.z; p[4 * v + 3] = x.w;
+            if (A >= 2) {
+                const float4 y = reinterpret_cast<const float4 *>(a1 + 3 * i0)[v];
+                q1[4 * v] = y.x; q1[4 * v + 1] = y.y; q1[4 * v + 2] = y.z; q1[4 * v + 3] = y.w;
+            }
+            if (A >= 3) {
+                const float4 z = reinterpret_cast<const float4 *>(a2 + 3 * i0)[v];
+                q2[4 * v] = z.x; q2[4 * v + 1] = z.y; q2[4 * v + 2] = z.z; q2[4 * v + 3] = z.w;
+            }
+        }
+    } else {
+        for (int k = 0; k < 3 * cnt; ++k) {
+            p[k] = pts[3 * i0 + k];
+            if (A >= 2) q1[k] = a1[3 * i0 + k];
+            if (A >= 3) q2[k] = a2[3 * i0 + k];
+        }
+    }
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+        if (t >= cnt) break;
+        // compute_key_functor (down_sample.cu:70-73): floor((pt - min_bound) / voxel_size) cast to int
+        const unsigned kx = (unsigned)(int)floorf(__fdiv_rn(p[3 * t] - g.org[0], g.voxel));
+        const unsigned ky = (unsigned)(int)floorf(__fdiv_rn(p[3 * t + 1] - g.org[1], g.voxel));
+        const unsigned kz = (unsigned)(int)floorf(__fdiv_rn(p[3 * t + 2] - g.org[2], g.voxel));
+        double *c = acc + ((size_t)(kx * g.dy + ky) * g.dz + kz) * S;
+        atomicAdd(c + 0, (double)p[3 * t]);
+        atomicAdd(c + 1, (double)p[3 * t + 1]);
+        atomicAdd(c + 2, (double)p[3 * t + 2]);
+        if (A >= 2) {
+            atomicAdd(c + 3, (double)q1[3 * t]);
+            atomicAdd(c + 4, (double)q1[3 * t + 1]);
+            atomicAdd(c + 5, (double)q1[3 * t + 2]);
+        }
+        if (A >= 3) {
+            atomicAdd(c + 6, (double)q2[3 * t]);
+            atomicAdd(c + 7, (double)q2[3 * t + 1]);
+            atomicAdd(c + 8, (double)q2[3 * t + 2]);
+        }
+        atomicAdd(c + (A == 1 ? 3 : A == 2 ? 6 : 9), 1.0);  // the count, exact in float64
+    }
+}
+
+#define VD_BLOCK 1024
+template <int A>
+__global__ void __launch_bounds__(VD_BLOCK) voxel_dense_count_kernel(const double *__restrict__ acc, size_t cells, unsigned *block_counts) {
+    constexpr int S = dense_stride<A>();
+    __shared__ unsigned s_w[32];
+    const size_t c = blockIdx.x * (size_t)VD_BLOCK + threadIdx.x;
+    const bool occ = c < cells && acc[c * S + (A == 1 ? 3 : A == 2 ? 6 : 9)] > 0.0;
+    const unsigned m = __ballot_sync(CPHB_FULL, occ);
+    if (lane_id() == 0) s_w[threadIdx.x >> 5] = __popc(m);
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        unsigned v = s_w[threadIdx.x];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(CPHB_FULL, v, o);
+        if (threadIdx.x == 0) block_counts[blockIdx.x] = v;
+    }
+}
+// exclusive scan of the block counts (one block; the grid has cells / 1024 entries), total to *total
+__global__ void __launch_bounds__(1024) voxel_dense_scan_kernel(unsigned *block_counts, unsigned nb, unsigned *total) {
+    __shared__ unsigned s_w[32];
+    __shared__ unsigned s_carry;
+    if (threadIdx.x == 0) s_carry = 0;
+    __syncthreads();
+    for (unsigned base = 0; base < nb; base += 1024) {
+        const unsigned i = base + threadIdx.x;
+        const unsigned v = i < nb ? block_counts[i] : 0u;
+        unsigned x = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned y = __shfl_up_sync(CPHB_FULL, x, o);
+            if (lane_id() >= o) x += y;
+        }
+        if (lane_id() == 31) s_w[threadIdx.x >> 5] = x;
+        __syncthreads();
+        if (threadIdx.x < 32) {
+            const unsigned ws = s_w[threadIdx.x];
+            unsigned z = ws;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const unsigned y = __shfl_up_sync(CPHB_FULL, z, o);
+                if (lane_id() >= o) z += y;
+            }
+            s_w[threadIdx.x] = z - ws;
+        }
+        __syncthreads();
+        const unsigned excl = x - v + s_w[threadIdx.x >> 5] + s_carry;
+        if (i < nb) block_counts[i] = excl;
+        __syncthreads();
+        if (threadIdx.x == 1023) s_carry = excl + v;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *total = s_carry;
+}
+template <int A>
+__global__ void __launch_bounds__(VD_BLOCK) voxel_dense_write_kernel(const double *__restrict__ acc, size_t cells,
+                                                                     const unsigned *__restrict__ block_offsets, int a1_is_normal,
+                                                                     float *out_p, float *out_a1, float *out_a2) {
+    constexpr int S = dense_stride<A>();
+    __shared__ unsigned s_w[32];
+    const size_t c = blockIdx.x * (size_t)VD_BLOCK + threadIdx.x;
+    double cntd = 0.0;
+    if (c < cells) cntd = acc[c * S + (A == 1 ? 3 : A == 2 ? 6 : 9)];
+    const bool occ = cntd > 0.0;
+    const unsigned m = __ballot_sync(CPHB_FULL, occ);
+    if (lane_id() == 0) s_w[threadIdx.x >> 5] = __popc(m);
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        const unsigned ws = s_w[threadIdx.x];
+        unsigned z = ws;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned y = __shfl_up_sync(CPHB_FULL, z, o);
+            if (lane_id() >= o) z += y;
+        }
+        s_w[threadIdx.x] = z - ws;
+    }
+    __syncthreads();
+    if (!occ) return;
+    const size_t pos = (size_t)block_offsets[blockIdx.x] + s_w[threadIdx.x >> 5] + __popc(m & ((1u << lane_id()) - 1u));
+    const double *s = acc + c * S;
+    const float cnt = (float)cntd;
+    // divide_tuple_functor: x / (float)count
+    out_p[3 * pos] = __fdiv_rn((float)s[0], cnt);
+    out_p[3 * pos + 1] = __fdiv_rn((float)s[1], cnt);
+    out_p[3 * pos + 2] = __fdiv_rn((float)s[2], cnt);
+    if (A >= 2) {
+        float v[3] = {__fdiv_rn((float)s[3], cnt), __fdiv_rn((float)s[4], cnt), __fdiv_rn((float)s[5], cnt)};
+        if (a1_is_normal) {  // normalize_and_divide_tuple_functor (down_sample.cu:78-90)
+            const float nn = sqrtf(dot3(v[0], v[1], v[2], v[0], v[1], v[2]));
+            if (nn > 0.f) { v[0] = __fdiv_rn(v[0], nn); v[1] = __fdiv_rn(v[1], nn); v[2] = __fdiv_rn(v[2], nn); }
+        }
+        out_a1[3 * pos] = v[0]; out_a1[3 * pos + 1] = v[1]; out_a1[3 * pos + 2] = v[2];
+    }
+    if (A >= 3) {
+        out_a2[3 * pos] = __fdiv_rn((float)s[6], cnt);
+        out_a2[3 * pos + 1] = __fdiv_rn((float)s[7], cnt);
+        out_a2[3 * pos + 2] = __fdiv_rn((float)s[8], cnt);
+    }
+}
+
+template <int A>
+static int voxel_dense(const float *points, const float *a1, const float *a2, size_t n, const DenseGrid &g, size_t cells,
+                       int a1_is_normal, float *out_p, float *out_a1, float *out_a2, size_t *h_n_out, cudaStream_t s) {
+    constexpr int S = dense_stride<A>();
+    const unsigned nb = (unsigned)((cells + VD_BLOCK - 1) / VD_BLOCK);
+    char *base = nullptr;
+    const size_t acc_bytes = cphb_align(sizeof(double) * S * cells, 256);
+    int rc = cphb_alloc_async((void **)&base, acc_bytes + sizeof(unsigned) * ((size_t)nb + 8), s);
+    if (rc) return rc;
+    double *acc = (double *)base;
+    unsigned *bc = (unsigned *)(base + acc_bytes), *total = bc + nb;
+    CPHB_CUDA(cudaMemsetAsync(acc, 0, sizeof(double) * S * cells, s));
+    CPHB_LAUNCH(voxel_dense_accum_kernel<A>, (unsigned)((n + 1023) / 1024), 256, 0, s, points, a1, a2, n, g, acc);
+    CPHB_LAUNCH(voxel_dense_count_kernel<A>, nb, VD_BLOCK, 0, s, acc, cells, bc);
+    CPHB_LAUNCH(voxel_dense_scan_kernel, 1, 1024, 0, s, bc, nb, total);
+    CPHB_LAUNCH(voxel_dense_write_kernel<A>, nb, VD_BLOCK, 0, s, acc, cells, bc, a1_is_normal, out_p, out_a1, out_a2);
+    CPHB_CHECK_LAUNCH();
+    unsigned h = 0;
+    CPHB_CUDA(cudaMemcpyAsync(&h, total, 4, cudaMemcpyDeviceToHost, s));
+    cphb_free_async(base, s);
+    CPHB_CUDA(cudaStreamSynchronize(s));
+    *h_n_out = h;
+    return CPHB_OK;
+}
+
 static int bits_for(double cells) {
     int b = 1;
     while (b < 63 && (double)(1ull << b) < cells) ++b;
@@ -204,6 +409,20 @@ static int voxel_down_sample_impl(const float *points, const float *normals, con
         cells *= dims[a];
     }
     if (voxel_size * (float)2147483647 < ext) return CPHB_OK;  // :183-187 "voxel_size is too small"
+    const int A0 = 1 + (normals ? 1 : 0) + (colors ? 1 : 0);
+    const bool no_dense = getenv("CPHB_VOXEL_NO_DENSE") != nullptr;  // A/B and test hook: force the hash path
+    if (!no_dense && cells <= 2.0 * (double)n + 4096.0 && cells < 2.0e9 && dims[1] * dims[2] < 4.0e9) {
+        DenseGrid dg;
+        for (int a = 0; a < 3; ++a) dg.org[a] = g.org[a];
+        dg.voxel = voxel_size;
+        dg.dy = (unsigned)dims[1];
+        dg.dz = (unsigned)dims[2];
+        const float *d1 = normals ? normals : colors, *d2 = colors;
+        float *o1 = normals ? out_normals : out_colors;
+        if (A0 == 1) return voxel_dense<1>(points, nullptr, nullptr, n, dg, (size_t)cells, 0, out_points, nullptr, nullptr, h_n_out, s);
+        if (A0 == 2) return voxel_dense<2>(points, d1, nullptr, n, dg, (size_t)cells, normals ? 1 : 0, out_points, o1, nullptr, h_n_out, s);
+        return voxel_dense<3>(points, normals, colors, n, dg, (size_t)cells, 1, out_points, out_normals, out_colors, h_n_out, s);
+    }
     int bx = bits_for(dims[0]), by = bits_for(dims[1]), bz = bits_for(dims[2]);
     if (bx + by + bz > 63) {
         cphb_set_error("cphb_voxel_down_sample: grid %gx%gx%g needs %d key bits (> 63)", dims[0], dims[1], dims[2],

@@ -24,16 +24,21 @@ def test_voxel_golden(golden):
     np.testing.assert_allclose(lexsort_rows(out.colors.cpu()), lexsort_rows(g["ref_colors"]), atol=TOL, rtol=0)
 
 
+# voxel 0.05: 16 k cells for 200 k points -> the dense-grid path; 0.004: 31 M cells -> the hash path; "forced": the hash
+# path on the dense case (CPHB_VOXEL_NO_DENSE), so both paths see the same inputs
+@pytest.mark.parametrize("voxel,force_hash", [(0.05, False), (0.05, True), (0.004, False)])
 @pytest.mark.parametrize("attrs", ["p", "pn", "pc", "pnc"])
-def test_voxel_vs_oracle(orc, attrs):
+def test_voxel_vs_oracle(orc, attrs, voxel, force_hash, monkeypatch):
     n = 200000
     p = datagen.uniform_cube(n, 21, hi=(2, 2, 0.5))
     nr = datagen.unit_normals(n, 22) if "n" in attrs else None
     co = datagen.uniform_cube(n, 23) if "c" in attrs else None
     pc = cph.geometry.PointCloud(p)
     pc.normals, pc.colors = nr, co
-    out = pc.voxel_down_sample(0.05)
-    op, on, oc = orc.voxel_down_sample(p, 0.05, nr, co)
+    if force_hash:
+        monkeypatch.setenv("CPHB_VOXEL_NO_DENSE", "1")
+    out = pc.voxel_down_sample(voxel)
+    op, on, oc = orc.voxel_down_sample(p, voxel, nr, co)
     assert len(out) == len(op)
     # same voxel order (lexicographic) and float64-accumulated means: bit-exact
     np.testing.assert_array_equal(out.points.cpu(), op)
