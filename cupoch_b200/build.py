@@ -26,7 +26,7 @@ FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std
          "-Xcompiler", "-fPIC", "-I" + os.path.join(ROOT, "include"), "-I" + SRC]
 
 
-HEADERS = ["cphb_internal.cuh", "cphb_eigen3.cuh", "icp_types.cuh", "icp_solve.cuh", "icp_rows.cuh", "icp_kernels.cuh",
+HEADERS = ["cphb_internal.cuh", "cphb_searchk.cuh", "cphb_eigen3.cuh", "icp_types.cuh", "icp_solve.cuh", "icp_rows.cuh", "icp_kernels.cuh",
            "icp_estimate.cuh", "icp_aux.cuh"]
 MANIFEST = os.path.join(OBJ, "manifest.json")
 

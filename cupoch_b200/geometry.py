@@ -115,6 +115,19 @@ class PointCloud:
     def from_colors_dlpack(self, capsule):
         self._colors = self._from_dlpack(capsule)
 
+    def clone(self):
+        """deep copy (the reference's copy constructor, pointcloud.cu:150-155: all attribute vectors are copied)"""
+        out = PointCloud()
+        for name in ("_points", "_normals", "_colors", "_covariances", "_color_gradient"):
+            a = getattr(self, name)
+            if a is None:
+                continue
+            b = DeviceArray(a.shape, a.dtype)
+            if a.nbytes:
+                _lib.check(_lib.lib().cphb_memcpy_d2d(b.ptr, a.ptr, a.nbytes, None))
+            setattr(out, name, b)
+        return out
+
     # -- geometry ops ---------------------------------------------------------
     def transform(self, transformation):
         """PointCloud::Transform (pointcloud.cu:293-299), in place."""

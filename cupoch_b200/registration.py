@@ -182,7 +182,9 @@ def registration_icp(source, target, max_correspondence_distance, init=None,
     if max_correspondence_distance <= 0.0:
         pass  # registration.cu:130-132 only logs; the search then yields no correspondences
     if estimation_method.get_transformation_estimation_type() == _lib.EST_UNSPECIFIED:
-        raise NotImplementedError("user-defined TransformationEstimation: use the generic loop in the C++ facade")
+        if comm is not None or shard is not None:
+            raise ValueError("user-defined TransformationEstimation runs the generic single-GPU loop")
+        return _registration_icp_generic(source, target, max_correspondence_distance, init, estimation_method, criteria)
     _lib.require_gpu()
     sc, tc = source._cloud(), target._cloud()
     p = _params(estimation_method, max_correspondence_distance, criteria, shard)
@@ -191,6 +193,34 @@ def registration_icp(source, target, max_correspondence_distance, init=None,
     _lib.check(_lib.lib().cphb_registration_icp(C.byref(sc), C.byref(tc), as_f16(init), C.byref(p), comm,
                                                 C.byref(res), corr.ptr if corr else None, None))
     return _result(res, corr, return_correspondences)
+
+
+def _registration_icp_generic(source, target, max_correspondence_distance, init, estimation, criteria):
+    """The reference's loop as written (registration.cu:145-172) for estimators the library has no fused path for:
+    Python subclasses of TransformationEstimation that override compute_transformation(source, target, corres) -- what
+    the reference's pybind trampoline PyTransformationEstimation (registration.cpp:36-60) makes possible.  Search and
+    Transform run on the GPU through the same C ABI; only the user's estimator runs where the user wrote it.  `corres`
+    is handed over as the host [n, 2] int32 array the reference's binding would convert it to."""
+    _lib.require_gpu()
+    T = np.array(np.asarray(init, np.float32).reshape(4, 4))
+    pcd = source.clone()
+    if not np.array_equal(T, np.eye(4, dtype=np.float32)):
+        pcd.transform(T)
+    result = evaluate_registration(pcd, target, max_correspondence_distance)
+    result.transformation = T
+    it = 0
+    for it in range(1, max(criteria.max_iteration, 0) + 1):
+        update = np.asarray(estimation.compute_transformation(pcd, target, result.correspondence_set), np.float32).reshape(4, 4)
+        T = (update @ T).astype(np.float32)
+        pcd.transform(update)
+        backup_f, backup_r = result.fitness, result.inlier_rmse
+        result = evaluate_registration(pcd, target, max_correspondence_distance)
+        result.transformation = T
+        if abs(backup_f - result.fitness) < criteria.relative_fitness and abs(backup_r - result.inlier_rmse) < criteria.relative_rmse:
+            result.converged = True
+            break
+    result.iterations = it
+    return result
 
 
 def registration_icp_host(source_points, target_points, max_correspondence_distance, init=None, estimation_method=None,
@@ -204,7 +234,23 @@ def registration_icp_host(source_points, target_points, max_correspondence_dista
     criteria = criteria or ICPConvergenceCriteria()
     init = np.eye(4, dtype=np.float32) if init is None else init
     if estimation_method.get_transformation_estimation_type() == _lib.EST_UNSPECIFIED:
-        raise NotImplementedError("user-defined TransformationEstimation: use the generic loop in the C++ facade")
+        # user-defined estimator (the reference's trampoline, registration.cpp:36-60): upload, then the generic loop
+        if comm is not None or shard is not None:
+            raise ValueError("user-defined TransformationEstimation runs the generic single-GPU loop")
+        s_pc, t_pc = PointCloud(source_points), PointCloud(target_points)
+        for pc, nrm, col, cov in ((s_pc, source_normals, source_colors, source_covariances),
+                                  (t_pc, target_normals, target_colors, target_covariances)):
+            if nrm is not None:
+                pc.normals = nrm
+            if col is not None:
+                pc.colors = col
+            if cov is not None:
+                pc.covariances = cov
+        out = _registration_icp_generic(s_pc, t_pc, max_correspondence_distance, init, estimation_method, criteria)
+        if return_correspondences and pairs_out is not None:
+            cs = out.correspondence_set
+            pairs_out[:len(cs)] = cs
+        return out
     _lib.require_gpu()
 
     def host(a, cols):

@@ -118,6 +118,34 @@ def test_estimate_normals_vs_oracle(orc):
     np.testing.assert_array_equal(n, o)
 
 
+def test_estimate_normals_fused_equals_two_pass(monkeypatch):
+    """the fused kernel (search + cumulants + eigen-solve, no [n][k] table) against the two-pass form it replaces
+    (CPHB_NORMALS_UNFUSED=1): bit for bit, kNN and radius, including points with < 3 neighbours, a cloud that does not
+    fill its last leaf, and the block form used by the sharded path"""
+    import ctypes as C
+    from cupoch_b200 import _lib
+    from cupoch_b200.utility import DeviceArray
+    p = np.concatenate([datagen.surface(50_017, 6)[0], datagen.uniform_cube(300, 7) * 3 + 2]).astype(np.float32)  # + isolated points
+    for param in (cph.geometry.KDTreeSearchParamKNN(30), cph.geometry.KDTreeSearchParamRadius(0.015, 30),
+                  cph.geometry.KDTreeSearchParamKNN(2)):
+        pc = cph.geometry.PointCloud(p)
+        pc.estimate_normals(param)
+        fused = pc.normals.cpu()
+        monkeypatch.setenv("CPHB_NORMALS_UNFUSED", "1")
+        pc.estimate_normals(param)
+        two = pc.normals.cpu()
+        monkeypatch.delenv("CPHB_NORMALS_UNFUSED")
+        np.testing.assert_array_equal(fused, two)
+    assert (fused[-300:] == [0, 0, 1]).all(1).any()          # knn=2 < 3 neighbours: the (0,0,1) branch ran
+    # block form (queries in the block's Hilbert order instead of index order)
+    d = DeviceArray.from_numpy(p)
+    out = DeviceArray((20_000, 3), np.float32)
+    _lib.check(_lib.lib().cphb_estimate_normals_range(d.ptr, len(p), 30, 0.0, 0, 10_000, 20_000, out.ptr, None))
+    pc = cph.geometry.PointCloud(p)
+    pc.estimate_normals(cph.geometry.KDTreeSearchParamKNN(30))
+    np.testing.assert_array_equal(out.cpu(), pc.normals.cpu()[10_000:30_000])
+
+
 def test_gicp_covariances_bit_exact(orc):
     nrm = datagen.unit_normals(5000, 9)
     nrm[0] = [-1, 0, 0]

@@ -275,3 +275,31 @@ def test_gicp_nonfinite_rows_are_dropped(orc):
     assert np.isfinite(res.transformation).all() and np.isfinite(ref["transformation"]).all()
     assert res.fitness > 0.5
     _compare(res, ref)
+
+
+def test_user_defined_estimator_generic_loop(orc):
+    """A Python subclass of TransformationEstimation (what the reference's trampoline, registration.cpp:36-60, allows)
+    runs the reference's generic loop (registration.cu:145-172): with an estimator that delegates to the built-in
+    point-to-plane solve it must end exactly where the fused path and the oracle end."""
+    src, sn, tgt, tn = small_pair()
+
+    class Mine(R.TransformationEstimation):   # type stays Unspecified
+        calls = 0
+
+        def compute_transformation(self, source, target, corres):
+            Mine.calls += 1
+            assert corres.dtype == np.int32 and corres.shape[1] == 2
+            return R.TransformationEstimationPointToPlane().compute_transformation(source, target, corres)
+
+    init = datagen.gt_transform((-0.3, 0.2, 0.4), (0.002, 0.0, -0.001)).astype(np.float32)
+    crit = R.ICPConvergenceCriteria(0, 0, 6)
+    res = R.registration_icp(cloud(src), cloud(tgt, tn), 0.03, init, Mine(), crit)
+    ref = orc.registration_icp(orc.P2PLANE, src, tgt, 0.03, init=init, tgt_nrm=tn, relative_fitness=0, relative_rmse=0, max_iteration=6)
+    assert Mine.calls == 6
+    _compare(res, ref)
+    fused = R.registration_icp(cloud(src), cloud(tgt, tn), 0.03, init, R.TransformationEstimationPointToPlane(), crit)
+    np.testing.assert_array_equal(res.transformation, fused.transformation)
+    np.testing.assert_array_equal(res.correspondence_set, fused.correspondence_set)
+    # host-buffer entry point takes the same route
+    res_h = R.registration_icp_host(src, tgt, 0.03, init, Mine(), crit, target_normals=tn, return_correspondences=True)
+    np.testing.assert_array_equal(res_h.transformation, fused.transformation)
