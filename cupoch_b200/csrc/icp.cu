@@ -68,7 +68,9 @@ struct cphb_icp {
     int2 *prev;
     unsigned *dbg = nullptr;  // CPHB_DEBUG_CERT statistics
     cudaEvent_t *dbg_ev = nullptr;  // CPHB_DEBUG_EVENTS: 3 events per launch (before, between, after)
-    unsigned grid, reduce_grid;
+    unsigned grid_search;  // ROLE 0 launch (searching regime)
+    unsigned grid;         // ROLE 1 launch (certified regime / sum of a searching launch's tile sums + solve)
+    unsigned reduce_grid;  // blocks of the ROLE 1 launch that take part in that sum
     cudaStream_t stream;
 };
 
@@ -83,6 +85,13 @@ static thread_local HostCache t_cache;
 // cphb_registration_icp_host: the source arrays are still being uploaded on another stream while the target index is
 // built; cphb_icp_create waits for this event right before it first reads them
 static thread_local cudaEvent_t t_source_ready = nullptr;
+// side stream on which cphb_icp_create orders the source while the target index is built
+struct SideStream {
+    cudaStream_t stream = nullptr;
+    cudaEvent_t fork = nullptr, join = nullptr;
+    int device = -1;
+};
+static thread_local SideStream t_side;
 
 static bool is_identity4(const float *T) {  // Eigen isIdentity(1e-5), registration.cu:148
     for (int i = 0; i < 4; ++i)
@@ -94,25 +103,26 @@ static bool is_identity4(const float *T) {  // Eigen isIdentity(1e-5), registrat
     return true;
 }
 
-// resident blocks / SM of the iteration kernel (register-limited)
-template <int KIND>
+// resident blocks / SM of the two instances of the iteration kernel (register-limited)
+template <int KIND, int ROLE>
 static int iteration_occupancy(bool top3) {
     int nb = 0;
-    cudaError_t e = top3 ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, icp_iteration_kernel<KIND, 3>, ICP_SEARCH_WARPS * 32, 0)
-                         : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, icp_iteration_kernel<KIND, 5>, ICP_SEARCH_WARPS * 32, 0);
+    cudaError_t e = top3 ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, icp_iteration_kernel<KIND, 3, ROLE>, ICP_SEARCH_WARPS * 32, 0)
+                         : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, icp_iteration_kernel<KIND, 5, ROLE>, ICP_SEARCH_WARPS * 32, 0);
     if (e != cudaSuccess) { cudaGetLastError(); return 0; }
     return nb;
 }
+template <int ROLE>
 static int iteration_occupancy_kind(int kind, bool top3) {
     static int cache[8][2] = {};  // 0 = not queried yet
     int &c = cache[kind & 7][top3 ? 0 : 1];
     if (c == 0) {
         switch (kind) {
-            case CPHB_EST_POINT_TO_POINT: c = iteration_occupancy<CPHB_EST_POINT_TO_POINT>(top3); break;
-            case CPHB_EST_POINT_TO_PLANE: c = iteration_occupancy<CPHB_EST_POINT_TO_PLANE>(top3); break;
-            case CPHB_EST_SYMMETRIC: c = iteration_occupancy<CPHB_EST_SYMMETRIC>(top3); break;
-            case CPHB_EST_COLORED_ICP: c = iteration_occupancy<CPHB_EST_COLORED_ICP>(top3); break;
-            case CPHB_EST_GENERALIZED_ICP: c = iteration_occupancy<CPHB_EST_GENERALIZED_ICP>(top3); break;
+            case CPHB_EST_POINT_TO_POINT: c = iteration_occupancy<CPHB_EST_POINT_TO_POINT, ROLE>(top3); break;
+            case CPHB_EST_POINT_TO_PLANE: c = iteration_occupancy<CPHB_EST_POINT_TO_PLANE, ROLE>(top3); break;
+            case CPHB_EST_SYMMETRIC: c = iteration_occupancy<CPHB_EST_SYMMETRIC, ROLE>(top3); break;
+            case CPHB_EST_COLORED_ICP: c = iteration_occupancy<CPHB_EST_COLORED_ICP, ROLE>(top3); break;
+            case CPHB_EST_GENERALIZED_ICP: c = iteration_occupancy<CPHB_EST_GENERALIZED_ICP, ROLE>(top3); break;
         }
         if (c <= 0) c = -1;
     }
@@ -144,17 +154,23 @@ template <int KIND>
 static void launch_iteration(const cphb_icp *icp, const IcpArgs &a, cudaStream_t s) {
 #if CPHB_PDL
     static const bool pdl = getenv("CPHB_NO_PDL") == nullptr;
+    // two launches per iteration: the searching-regime instance, then the certified-regime instance (which also sums and
+    // solves after a searching launch); the regime is decided on the device, the instance it does not concern returns
+    // at its first instructions (icp_kernels.cuh)
+    const bool top3 = icp->index->v.top <= 3;
     if (pdl && !a.defer_finalize && !a.step_mode && !icp->dbg_ev) {
-        if (icp->index->v.top <= 3) launch_pdl(icp_iteration_kernel<KIND, 3>, icp->grid, ICP_SEARCH_WARPS * 32, s, a);
-        else launch_pdl(icp_iteration_kernel<KIND, 5>, icp->grid, ICP_SEARCH_WARPS * 32, s, a);
-        launch_pdl(icp_reduce_kernel<KIND>, icp->reduce_grid, ICP_REDUCE_BLOCK, s, a);
+        if (top3) launch_pdl(icp_iteration_kernel<KIND, 3, 0>, icp->grid_search, ICP_SEARCH_WARPS * 32, s, a);
+        else launch_pdl(icp_iteration_kernel<KIND, 5, 0>, icp->grid_search, ICP_SEARCH_WARPS * 32, s, a);
+        if (top3) launch_pdl(icp_iteration_kernel<KIND, 3, 1>, icp->grid, ICP_SEARCH_WARPS * 32, s, a);
+        else launch_pdl(icp_iteration_kernel<KIND, 5, 1>, icp->grid, ICP_SEARCH_WARPS * 32, s, a);
         return;
     }
 #endif
-    if (icp->index->v.top <= 3) CPHB_LAUNCH((icp_iteration_kernel<KIND, 3>), icp->grid, ICP_SEARCH_WARPS * 32, 0, s, a);
-    else CPHB_LAUNCH((icp_iteration_kernel<KIND, 5>), icp->grid, ICP_SEARCH_WARPS * 32, 0, s, a);
+    if (icp->index->v.top <= 3) CPHB_LAUNCH((icp_iteration_kernel<KIND, 3, 0>), icp->grid_search, ICP_SEARCH_WARPS * 32, 0, s, a);
+    else CPHB_LAUNCH((icp_iteration_kernel<KIND, 5, 0>), icp->grid_search, ICP_SEARCH_WARPS * 32, 0, s, a);
     if (icp->dbg_ev) cudaEventRecord(icp->dbg_ev[3 * a.launch_idx + 1], s);
-    CPHB_LAUNCH(icp_reduce_kernel<KIND>, icp->reduce_grid, ICP_REDUCE_BLOCK, 0, s, a);
+    if (icp->index->v.top <= 3) CPHB_LAUNCH((icp_iteration_kernel<KIND, 3, 1>), icp->grid, ICP_SEARCH_WARPS * 32, 0, s, a);
+    else CPHB_LAUNCH((icp_iteration_kernel<KIND, 5, 1>), icp->grid, ICP_SEARCH_WARPS * 32, 0, s, a);
 }
 static void launch_iteration_kind(const cphb_icp *icp, const IcpArgs &a, cudaStream_t s) {
     switch (icp->prm.estimation) {
@@ -196,9 +212,38 @@ extern "C" int cphb_icp_create(const cphb_cloud *source, const cphb_cloud *targe
     icp->prm = *params;
     icp->tgt = *target;
     icp->stream = s;
-    int rc = cphb_index_create(target->points, target->n, s, &icp->index);
-    if (rc) { delete icp; return rc; }
     const unsigned n_full = (unsigned)source->n;
+    // The source's Hilbert ordering (bounds, keys, radix sort) does not depend on the target index: it runs on a side
+    // stream, concurrently with the index build (both are short chains of small kernels: ~0.1 ms and ~0.25 ms at 1 M
+    // points), and joins right before the source is gathered.
+    uint32_t *perm_side = nullptr;
+    int cur_dev = 0;
+    cudaGetDevice(&cur_dev);
+    if (!t_side.stream || t_side.device != cur_dev) {  // (a thread that moved to another device gets a new one)
+        t_side.device = cur_dev;
+        CPHB_CUDA(cudaStreamCreateWithFlags(&t_side.stream, cudaStreamNonBlocking));
+        CPHB_CUDA(cudaEventCreateWithFlags(&t_side.fork, cudaEventDisableTiming));
+        CPHB_CUDA(cudaEventCreateWithFlags(&t_side.join, cudaEventDisableTiming));
+    }
+    int rc = CPHB_OK;
+    if (n_full) {
+        CPHB_CUDA(cudaEventRecord(t_side.fork, s));
+        CPHB_CUDA(cudaStreamWaitEvent(t_side.stream, t_side.fork, 0));
+        if (t_source_ready) {  // (host-buffer call: the source upload is still in flight on the copy stream)
+            cudaStreamWaitEvent(t_side.stream, t_source_ready, 0);
+            t_source_ready = nullptr;
+        }
+        rc = cphb_alloc_async((void **)&perm_side, sizeof(uint32_t) * n_full, t_side.stream);
+        if (!rc) rc = cphb_hilbert_order(source->points, n_full, perm_side, nullptr, 0, t_side.stream);
+        if (rc) { cphb_free_async(perm_side, t_side.stream); delete icp; return rc; }
+        CPHB_CUDA(cudaEventRecord(t_side.join, t_side.stream));
+    }
+    rc = cphb_index_create(target->points, target->n, s, &icp->index);
+    if (rc) {
+        if (perm_side) { cudaStreamWaitEvent(s, t_side.join, 0); cphb_free_async(perm_side, s); }
+        delete icp;
+        return rc;
+    }
     unsigned lo = 0, n = n_full;
     if (params->shard_world > 1) {
         if (params->shard_rank < 0 || params->shard_rank >= params->shard_world) {
@@ -223,15 +268,18 @@ extern "C" int cphb_icp_create(const cphb_cloud *source, const cphb_cloud *targe
         unsigned want = (n_tiles + ICP_SEARCH_WARPS - 1) / ICP_SEARCH_WARPS;
         // every block must be resident: warps start on a static tile, and a block waiting for an SM slot
         // would hold its four tiles back until the dynamic queue has drained
-        unsigned per_sm = 9u;
-        const int occ = iteration_occupancy_kind(params->estimation, icp->index->v.top <= 3);
-        if (occ > 0 && (unsigned)occ < per_sm) per_sm = (unsigned)occ;
-        if (const char *e = getenv("CPHB_ICP_BLOCKS_PER_SM")) {  // tuning hook
-            int v = atoi(e);
-            if (v >= 1 && v <= 32) per_sm = (unsigned)v;
-        }
-        unsigned cap = (unsigned)sms * per_sm;
-        icp->grid = want < cap ? want : cap;
+        auto grid_for = [&](int occ, const char *hook) {
+            unsigned per_sm = 9u;
+            if (occ > 0 && (unsigned)occ < per_sm) per_sm = (unsigned)occ;
+            if (const char *e = getenv(hook)) {  // tuning hook
+                int v = atoi(e);
+                if (v >= 1 && v <= 32) per_sm = (unsigned)v;
+            }
+            const unsigned cap = (unsigned)sms * per_sm;
+            return want < cap ? want : cap;
+        };
+        icp->grid_search = grid_for(iteration_occupancy_kind<0>(params->estimation, icp->index->v.top <= 3), "CPHB_ICP_SEARCH_BLOCKS_PER_SM");
+        icp->grid = grid_for(iteration_occupancy_kind<1>(params->estimation, icp->index->v.top <= 3), "CPHB_ICP_BLOCKS_PER_SM");
         unsigned rg = (n_tiles + 63) / 64;
         unsigned rg_cap = (unsigned)sms;
         if (const char *e = getenv("CPHB_REDUCE_BLOCKS_PER_SM")) {  // tuning hook: more, shorter chains of tile sums
@@ -239,6 +287,7 @@ extern "C" int cphb_icp_create(const cphb_cloud *source, const cphb_cloud *targe
             if (v >= 1 && v <= 8) rg_cap = (unsigned)sms * (unsigned)v;
         }
         icp->reduce_grid = rg < 1 ? 1 : (rg > rg_cap ? rg_cap : rg);
+        if (icp->reduce_grid > icp->grid) icp->reduce_grid = icp->grid;  // the sum runs on blocks of the ROLE 1 launch
     }
     const bool want_nrm = params->estimation == CPHB_EST_SYMMETRIC && source->normals;
     const bool want_col = params->estimation == CPHB_EST_COLORED_ICP && source->colors;
@@ -272,7 +321,6 @@ extern "C" int cphb_icp_create(const cphb_cloud *source, const cphb_cloud *targe
     unsigned cmp_blocks = (nf_pad + CMP_BLOCK - 1) / CMP_BLOCK;
     size_t o_cc = take(sizeof(unsigned) * (cmp_blocks + 1));
     size_t o_ct = take(16);
-    size_t o_perm = take(sizeof(uint32_t) * nf_pad);
     icp->arena_bytes = off;
     rc = cphb_alloc_async(&icp->arena, off, s);
     if (rc) { cphb_index_destroy(icp->index); delete icp; return rc; }
@@ -306,7 +354,6 @@ extern "C" int cphb_icp_create(const cphb_cloud *source, const cphb_cloud *targe
     icp->corr_index = (int32_t *)(b + o_ci);
     icp->cmp_counts = (unsigned *)(b + o_cc);
     icp->cmp_total = (unsigned *)(b + o_ct);
-    uint32_t *perm = (uint32_t *)(b + o_perm);
     if (!t_cache.in_use) {
         if (!t_cache.h_st) {
             CPHB_CUDA(cudaMallocHost((void **)&t_cache.h_st, sizeof(IcpState)));
@@ -324,17 +371,15 @@ extern "C" int cphb_icp_create(const cphb_cloud *source, const cphb_cloud *targe
         CPHB_CUDA(cudaEventCreate(&icp->ev0));
         CPHB_CUDA(cudaEventCreate(&icp->ev1));
     }
-    if (t_source_ready) {
+    if (t_source_ready) {  // (n_full == 0)
         cudaStreamWaitEvent(s, t_source_ready, 0);
         t_source_ready = nullptr;
     }
-    if (n_full) {
-        rc = cphb_hilbert_order(source->points, n_full, perm, nullptr, 0, s);
-        if (rc) { cphb_icp_destroy(icp); return rc; }
-    }
+    if (perm_side) cudaStreamWaitEvent(s, t_side.join, 0);
     CPHB_LAUNCH(gather_source_kernel, n_pad / 256, 256, 0, s, source->points, source->normals, source->colors,
-                source->covariances, source->cov_col_major, perm, lo, n, n_pad, icp->pristine_xyz, icp->pristine_nrm,
+                source->covariances, source->cov_col_major, perm_side, lo, n, n_pad, icp->pristine_xyz, icp->pristine_nrm,
                 icp->src_col, icp->pristine_cov);
+    cphb_free_async(perm_side, s);
     if ((t_nrm || t_grad || t_cov) && nt_pad)
         CPHB_LAUNCH(gather_target_kernel, (unsigned)((nt_pad + 255) / 256), 256, 0, s, icp->index->v.pts, nt_pad, target->normals,
                     (est == CPHB_EST_COLORED_ICP) ? target->colors : nullptr, target->color_gradient, target->covariances,
@@ -375,8 +420,12 @@ static void fill_args(const cphb_icp *icp, IcpArgs &a) {
     a.tile_sums = icp->tile_sums;
     a.flag_bits = icp->flag_bits;
     a.flag_words = icp->flag_words;
-    // certified regime: 1 block in 32 (at least 2 when the grid allows) only runs the tiles that needed a search last time
-    a.helper_blocks = icp->grid >= 64 ? (icp->grid / 32 > 2 ? icp->grid / 32 : 2) : 0;
+    a.reduce_grid = icp->reduce_grid;
+    // certified regime: 1 block in 8 (at least 2 when the grid allows) only runs the tiles that needed a search last time:
+    // a search on an otherwise idle SM is one warp's dependent chain (~10 us), so a helper warp should not get more than
+    // one or two of them (config 2: ~85 flagged tiles; 18 / 36 / 72 / 144 helper blocks -> the helpers finish 36 / 30 / 22 /
+    // 22 us into a launch whose other warps need 31 us, profiles/r2_sweep_cert_helpers.txt)
+    a.helper_blocks = icp->grid >= 64 ? (icp->grid / 8 > 2 ? icp->grid / 8 : 2) : 0;
     if (const char *e = getenv("CPHB_HELPER_BLOCKS")) { int v = atoi(e); if (v >= 0 && (unsigned)v < icp->grid / 2) a.helper_blocks = (unsigned)v; }
     a.prev = icp->prev;
     a.n_src = icp->n_src;
@@ -478,8 +527,8 @@ extern "C" int cphb_icp_run(cphb_icp *icp, const float h_init[16], cphb_comm *co
     CPHB_CUDA(cudaMemcpyAsync(icp->st, h, sizeof(IcpState), cudaMemcpyHostToDevice, s));
     static const bool dbg_cert = getenv("CPHB_DEBUG_CERT") != nullptr;
     if (dbg_cert) {
-        if (!icp->dbg) CPHB_CUDA(cudaMalloc(&icp->dbg, sizeof(unsigned) * 256 + 64));
-        CPHB_CUDA(cudaMemsetAsync(icp->dbg, 0, sizeof(unsigned) * 256 + 64, s));
+        if (!icp->dbg) CPHB_CUDA(cudaMalloc(&icp->dbg, sizeof(unsigned) * 256 + 128));
+        CPHB_CUDA(cudaMemsetAsync(icp->dbg, 0, sizeof(unsigned) * 256 + 128, s));
         CPHB_CUDA(cudaMemsetAsync(icp->dbg + 256, 0xff, 8, s));  // slot 0 takes a minimum
     }
     IcpArgs a;
@@ -584,7 +633,7 @@ extern "C" int cphb_icp_run(cphb_icp *icp, const float h_init[16], cphb_comm *co
         icp->dbg_ev = nullptr;
     }
     if (dbg_cert && icp->dbg) {
-        unsigned hd[256 + 16];
+        unsigned hd[256 + 32];
         CPHB_CUDA(cudaMemcpy(hd, icp->dbg, sizeof(hd), cudaMemcpyDeviceToHost));
         {
             const unsigned long long *tl = reinterpret_cast<const unsigned long long *>(hd + 256);
@@ -593,6 +642,10 @@ extern "C" int cphb_icp_run(cphb_icp *icp, const float h_init[16], cphb_comm *co
                         "[state read %.1f, 6x6 solved %.1f, pose composed %.1f] finalize done %.1f\n",
                         (tl[1] - tl[0]) * 1e-3, (tl[2] - tl[0]) * 1e-3, (tl[3] - tl[0]) * 1e-3, (tl[5] - tl[0]) * 1e-3, (tl[6] - tl[0]) * 1e-3,
                         (tl[7] - tl[0]) * 1e-3, (tl[4] - tl[0]) * 1e-3);
+            if (tl[4] && tl[0] != ~0ull)
+                fprintf(stderr, "[cphb] launch 20 tile loops (us): main warps without an in-line search done %.1f, with one %.1f, helper warps done %.1f, "
+                        "last block start %.1f\n", tl[8] ? (tl[8] - tl[0]) * 1e-3 : 0.0, tl[9] ? (tl[9] - tl[0]) * 1e-3 : 0.0,
+                        tl[10] ? (tl[10] - tl[0]) * 1e-3 : 0.0, tl[11] ? (tl[11] - tl[0]) * 1e-3 : 0.0);
         }
         fprintf(stderr, "[cphb] certificates (n_src %u, tiles %u): launch: certified lanes / skipped tiles [/ deferred tiles, * = certified regime]\n", icp->n_src, icp->n_pad / 32);
         for (int it = 0; it <= a.max_iter && it < 64; ++it) {

@@ -28,7 +28,14 @@ __device__ __forceinline__ void cp_async_8(void *smem, const void *gmem) {
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_0() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
-__device__ __forceinline__ void cp_async_wait_1() { asm volatile("cp.async.wait_group 1;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+// certified regime: software pipeline depth.  Tile T's target rows are requested ICP_GD tiles ahead (that needs tile T's
+// match position, i.e. its stage), the (point, match, slack) stages ICP_NS = 2 * ICP_GD tiles ahead.
+#ifndef ICP_GD
+#define ICP_GD 2
+#endif
+#define ICP_NS (2 * ICP_GD)
 // pull the rows of target position p that a tile reads first into L1 (no register is tied up, nothing waits)
 template <int KIND>
 __device__ __forceinline__ void prefetch_target(const IcpArgs &a, size_t p) {
@@ -40,8 +47,18 @@ __device__ __forceinline__ void prefetch_target(const IcpArgs &a, size_t p) {
 }
 
 #define ICP_SEARCH_WARPS 4
+// Two instances of the kernel, launched back to back every iteration (the regime is decided on the DEVICE, so each
+// instance checks the state and the one whose regime is not current leaves at once):
+//   ROLE 0  searching regime.  The traversal is bound by instruction issue at low occupancy, so it is compiled for MORE
+//           resident warps (96 registers: 5 blocks = 20 warps / SM; ncu of the shared 128-register build: issue slots
+//           52 % busy at 16 warps / SM).
+//   ROLE 1  certified regime (needs the registers: 30 float64 accumulators per lane) -- and, when the launch before it
+//           searched, the fixed-order sum of its tile sums + solve (what used to be a third kernel, icp_reduce_kernel).
 #ifndef ICP_MIN_BLOCKS
-#define ICP_MIN_BLOCKS 4  // resident blocks / SM the register allocation targets (128 registers: 16 warps / SM)
+#define ICP_MIN_BLOCKS 4  // ROLE 1: resident blocks / SM the register allocation targets (128 registers: 16 warps / SM)
+#endif
+#ifndef ICP_MIN_BLOCKS_SEARCH
+#define ICP_MIN_BLOCKS_SEARCH 5  // ROLE 0 (96 registers: 20 warps / SM; A/B of 4 / 5 / 6 / 8 in profiles/r2_ab_search_occupancy.txt)
 #endif
 // Programmatic dependent launch: the kernels of the loop are launched with stream serialisation relaxed, so the next
 // kernel's blocks are already resident (waiting in griddepcontrol.wait) while the last block of the current one sums and
@@ -396,16 +413,20 @@ template <int KIND>
 __device__ void icp_static_tail(const IcpArgs &a, IcpState *st, double (*s_rowbuf)[32], SolveSmem &s_solve, unsigned *s_flag,
                                 const double row, bool materialize, unsigned n_skipped_block);
 
-template <int KIND, int TOP>
-__global__ void __launch_bounds__(ICP_SEARCH_WARPS * 32, ICP_MIN_BLOCKS) icp_iteration_kernel(const __grid_constant__ IcpArgs a) {
+template <int KIND, int BLOCK>
+__device__ void icp_reduce_body(const IcpArgs &a, double (*s_acc)[32], unsigned *s_last, SolveSmem &s_solve);
+
+template <int KIND, int TOP, int ROLE>
+__global__ void __launch_bounds__(ICP_SEARCH_WARPS * 32, ROLE == 0 ? ICP_MIN_BLOCKS_SEARCH : ICP_MIN_BLOCKS)
+icp_iteration_kernel(const __grid_constant__ IcpArgs a) {
     __shared__ __align__(16) float4 s_tile[ICP_SEARCH_WARPS][2 * CPHB_LEAF];
     __shared__ uint64_t s_bar[ICP_SEARCH_WARPS][2];
     __shared__ double s_rows[ICP_SEARCH_WARPS][32 * ROW_STRIDE];
     __shared__ SolveSmem s_solve;
     __shared__ unsigned s_flag;
-    __shared__ __align__(16) unsigned char s_pipe[ICP_SEARCH_WARPS][2 * 32 * 24];  // certified regime: cp.async stages
+    __shared__ __align__(16) unsigned char s_pipe[ICP_SEARCH_WARPS][ICP_NS * 32 * 24];  // certified regime: cp.async stages
     constexpr int NG = (KIND == CPHB_EST_POINT_TO_POINT) ? 1 : (KIND == CPHB_EST_GENERALIZED_ICP) ? 4 : (KIND == CPHB_EST_COLORED_ICP) ? 3 : 2;
-    __shared__ __align__(16) float4 s_gat[ICP_SEARCH_WARPS][NG * 32];  // certified regime: the next tile's target rows
+    __shared__ __align__(16) float4 s_gat[ICP_SEARCH_WARPS][ICP_GD * NG * 32];  // certified regime: target rows of the next tiles
 
     IcpState *st = a.st;
     const int warp = threadIdx.x >> 5, lane = lane_id();
@@ -460,9 +481,15 @@ __global__ void __launch_bounds__(ICP_SEARCH_WARPS * 32, ICP_MIN_BLOCKS) icp_ite
     w.warm = false;
     w.tmax = a.tmax;
 
-    if (static_regime) {
+    if constexpr (ROLE == 1) {
+        if (!static_regime) {
+            // the ROLE 0 launch before this one searched: fixed-order sum of its tile sums + solve
+            static_assert(sizeof(s_pipe) >= sizeof(double) * 8 * 32, "reduce scratch");
+            icp_reduce_body<KIND, ICP_SEARCH_WARPS * 32>(a, (double(*)[32])s_pipe, &s_flag, s_solve);
+            return;
+        }
         if (a.dbg && threadIdx.x == 0 && blockIdx.x == 0) a.dbg[192 + min(a.launch_idx, 63)] = 1u;
-        if (lane == 0) dbg_time(a, 0, true);
+        if (lane == 0) { dbg_time(a, 0, true); dbg_time(a, 11, false); }
         // ======================= certified regime ==================================================================
         // Every tile whose 32 lanes are certified (99.7 % of them on config 2): transform, certificate test, rows, products
         // into this lane's float64 accumulators.  A tile with an uncertified lane goes through the searching regime's
@@ -503,6 +530,7 @@ __global__ void __launch_bounds__(ICP_SEARCH_WARPS * 32, ICP_MIN_BLOCKS) icp_ite
                     else if (lane == 0) atomicOr(&flag_next[wd], 1u << (t & 31));  // still needs its search next time
                 }
             }
+            if (lane == 0) { dbg_time(a, 1, false); dbg_time(a, 10, false); }
             icp_static_tail<KIND>(a, st, (double(*)[32])s_pipe, s_solve, &s_flag, hrow, c.materialize, n_skip);
             return;
         }
@@ -512,37 +540,52 @@ __global__ void __launch_bounds__(ICP_SEARCH_WARPS * 32, ICP_MIN_BLOCKS) icp_ite
         for (int p = 0; p < 32; ++p) lacc[p] = 0.0;
         double wrow = 0.0;  // lane p: column p of what this warp has folded so far
         unsigned n_skipped = 0;
+        bool searched_inline = false;
         unsigned tile = gw;
-        float4 *pipe_s = reinterpret_cast<float4 *>(s_pipe[warp]);                // [2][32] float4, then [2][32] int2
-        int2 *pipe_pv = reinterpret_cast<int2 *>(s_pipe[warp] + 2 * 32 * 16);
-        auto stage_load = [&](unsigned t, int b) {  // tile t -> stage b (this lane's slot only)
+        float4 *pipe_s = reinterpret_cast<float4 *>(s_pipe[warp]);                // [NS][32] float4, then [NS][32] int2
+        int2 *pipe_pv = reinterpret_cast<int2 *>(s_pipe[warp] + ICP_NS * 32 * 16);
+        auto stage_load = [&](unsigned t, int slot) {  // tile t -> stage slot (this lane's entries only)
             if (t < n_tiles) {
-                cp_async_16(&pipe_s[b * 32 + lane], &a.src[t * 32 + lane]);
-                cp_async_8(&pipe_pv[b * 32 + lane], &a.prev[t * 32 + lane]);
+                cp_async_16(&pipe_s[slot * 32 + lane], &a.src[t * 32 + lane]);
+                cp_async_8(&pipe_pv[slot * 32 + lane], &a.prev[t * 32 + lane]);
             }
-            cp_async_commit();
         };
-        float4 *gat = s_gat[warp];
-        stage_load(tile, 0);
-        stage_load(tile + main_warps, 1);
-        cp_async_wait_1();  // stage 0 has landed
-        if (tile < n_tiles) gather_issue<KIND>(a, gat, lane, pipe_pv[lane].x);
-        cp_async_commit();
-        int b = 0;
-        for (; tile < n_tiles; tile += main_warps, b ^= 1) {
-            // everything issued during the previous tile has had that whole tile to arrive: this tile's target rows and
-            // the next tile's point / match
-            cp_async_wait_0();
-            const unsigned t1 = tile + main_warps, t2 = t1 + main_warps;
-            float4 s = pipe_s[b * 32 + lane];
-            const int2 pv = pipe_pv[b * 32 + lane];
-            const bool flagged = (__ldg(&flag_cur[tile >> 5]) >> (tile & 31)) & 1u;  // a helper warp runs this tile
+        // Pipeline (all copies are cp.async, one commit group per tile iteration, so the group arithmetic is uniform):
+        //   iteration i commits G_i = { stage(i + NS), target rows of tile i + GD }   (the latter needs stage(i + GD))
+        //   at its top it needs stage(i), the rows of tile i (G_{i-GD}) and stage(i + GD) (G_{i+GD-NS} = G_{i-GD}):
+        //   everything but the GD - 1 most recent groups -> cp.async.wait_group GD - 1.
+        // A lane only ever reads and refills its own entries, so a buffer may be refilled right after the lane read it.
+#pragma unroll
+        for (int j = 0; j < ICP_NS; ++j) {
+            stage_load(tile + (unsigned)j * main_warps, j);
+            cp_async_commit();
+        }
+        cp_async_wait<ICP_NS - ICP_GD>();  // stages 0 .. GD-1 have landed
+#pragma unroll
+        for (int j = 0; j < ICP_GD; ++j) {
+            if (tile + (unsigned)j * main_warps < n_tiles) gather_issue<KIND>(a, s_gat[warp] + j * NG * 32, lane, pipe_pv[j * 32 + lane].x);
+            cp_async_commit();
+        }
+        unsigned fw = (tile < n_tiles) ? __ldg(&flag_cur[tile >> 5]) : 0u;  // flag word of the next tile, one tile ahead
+        int slot = 0, gslot = 0;
+        for (; tile < n_tiles; tile += main_warps) {
+            cp_async_wait<ICP_GD - 1>();
+            const unsigned t1 = tile + main_warps, tg = tile + ICP_GD * main_warps, tn = tile + ICP_NS * main_warps;
+            float4 *gat = s_gat[warp] + gslot * NG * 32;
+            const float4 s0 = pipe_s[slot * 32 + lane];  // (untransformed point)
+            float4 s = s0;
+            const int2 pv = pipe_pv[slot * 32 + lane];
+            const bool flagged = (fw >> (tile & 31)) & 1u;  // a helper warp runs this tile
+            if (t1 < n_tiles) fw = __ldg(&flag_cur[t1 >> 5]);
             float4 tp = gat[lane];
             TgtVals tv;
             load_tgt_smem<KIND>(a, gat, lane, tp, tv);
-            // (reads above first, same lane: now the buffers may be refilled) the next tile's target rows
-            if (t1 < n_tiles) gather_issue<KIND>(a, gat, lane, pipe_pv[(b ^ 1) * 32 + lane].x);
+            // (reads above first, same lane: now the entries may be refilled) this iteration's group
+            stage_load(tn, slot);
+            if (tg < n_tiles) gather_issue<KIND>(a, gat, lane, pipe_pv[((slot + ICP_GD) % ICP_NS) * 32 + lane].x);
             cp_async_commit();
+            slot = (slot + 1) % ICP_NS;
+            gslot = (gslot + 1) % ICP_GD;
             const unsigned i = tile * 32 + lane;
             const unsigned orig = __float_as_uint(s.w);
             const bool in_range = i < a.n_src;
@@ -554,12 +597,8 @@ __global__ void __launch_bounds__(ICP_SEARCH_WARPS * 32, ICP_MIN_BLOCKS) icp_ite
             bool cert;
             float slk, margin;
             lane_warm_start<true>(a, c, in_range, s, ox, oy, oz, pv, tp, best, cert, slk, margin);
-            if (flagged) {
-                stage_load(t2, b);
-                continue;
-            }
+            if (flagged) continue;
             const bool need_search = __any_sync(CPHB_FULL, in_range && !cert);
-            if (!need_search) stage_load(t2, b);  // refill the stage just read (same lane: the reads above come first)
             if (need_search) {  // not predicted by the flags (the first certified launch, or a point that drifted)
                 if (lane == 0) atomicOr(&flag_next[tile >> 5], 1u << (tile & 31));
                 if (!c.materialize) {
@@ -573,12 +612,12 @@ __global__ void __launch_bounds__(ICP_SEARCH_WARPS * 32, ICP_MIN_BLOCKS) icp_ite
                     }
                 }
                 double acc;
-                search_tile<KIND, TOP>(a, c, w, s_rows[warp], tile, pipe_s[b * 32 + lane], pv, acc);  // (untransformed point)
+                search_tile<KIND, TOP>(a, c, w, s_rows[warp], tile, s0, pv, acc);
+                searched_inline = true;
                 wrow += acc;
 #pragma unroll
                 for (int p = 0; p < 32; ++p) lacc[p] = 0.0;
                 if (a.dbg && lane == 0) atomicAdd(&a.dbg[128 + min(a.launch_idx, 63)], 1u);
-                stage_load(t2, b);
                 continue;
             }
             ++n_skipped;
@@ -613,7 +652,7 @@ __global__ void __launch_bounds__(ICP_SEARCH_WARPS * 32, ICP_MIN_BLOCKS) icp_ite
             }
         }
         cp_async_wait_0();
-        if (lane == 0) dbg_time(a, 1, false);
+        if (lane == 0) { dbg_time(a, 1, false); dbg_time(a, searched_inline ? 9 : 8, false); }
         // warp reduction (xor butterfly: the same bits on every lane), lane p keeps column p
         double row = wrow;
         if (!c.materialize) {
@@ -628,8 +667,8 @@ __global__ void __launch_bounds__(ICP_SEARCH_WARPS * 32, ICP_MIN_BLOCKS) icp_ite
         }
         icp_static_tail<KIND>(a, st, (double(*)[32])s_pipe, s_solve, &s_flag, row, c.materialize, n_skipped);
         return;
-    }
-
+    } else {
+    if (static_regime) return;  // the ROLE 1 launch right behind this one runs the certified regime
     // ======================= searching regime ======================================================================
     // Each warp starts on a static tile (its global warp id) and then claims RANGES of consecutive tiles from an atomic
     // counter: one tile at a time while tiles need a search (cost varies 10x between tiles, fine-grained claims keep
@@ -675,6 +714,7 @@ __global__ void __launch_bounds__(ICP_SEARCH_WARPS * 32, ICP_MIN_BLOCKS) icp_ite
         if (tn < n_tiles && pv_pf.x >= 0) prefetch_target<KIND>(a, (size_t)pv_pf.x);
     }
     if (a.static_sched && lane == 0 && n_skipped) atomicAdd(&st->cert_tiles, n_skipped);
+    }
 }
 
 // Tail of a certified-regime launch: block rows -> last-arriving block adds them in block order -> (multi-GPU exchange) ->
@@ -724,17 +764,18 @@ __device__ void icp_static_tail(const IcpArgs &a, IcpState *st, double (*s_rowbu
         return;
     }
     double t = 0.0;
-    {   // all warps of the block share the grid sum: warp g adds blocks g, g+W, ... with 16 loads in flight
+    {   // all warps of the block share the grid sum: warp g adds blocks g, g+W, ... in that order, with 32 loads in flight
+        // (the accumulators of the tile loop are dead here, so the registers are free)
         const unsigned nb = gridDim.x;
-        for (unsigned b = warp; b < nb; b += 16 * ICP_SEARCH_WARPS) {
-            double v[16];
+        for (unsigned b = warp; b < nb; b += 32 * ICP_SEARCH_WARPS) {
+            double v[32];
 #pragma unroll
-            for (int u = 0; u < 16; ++u) {
+            for (int u = 0; u < 32; ++u) {
                 const unsigned bb = b + u * ICP_SEARCH_WARPS;
                 v[u] = (bb < nb) ? __ldcg(&a.partials[(size_t)bb * 32 + lane]) : 0.0;  // x + 0.0 is exact
             }
 #pragma unroll
-            for (int u = 0; u < 16; ++u) t += v[u];
+            for (int u = 0; u < 32; ++u) t += v[u];
         }
     }
     __syncthreads();
@@ -764,16 +805,16 @@ __device__ void icp_static_tail(const IcpArgs &a, IcpState *st, double (*s_rowbu
 }
 
 // Fixed-order grid sum of the tile sums of a searching-regime launch, then (last block) the host-side part of the loop.
-// grid = R blocks; block b owns a contiguous chunk of tiles.
-#define ICP_REDUCE_BLOCK 256
-template <int KIND>
-__global__ void __launch_bounds__(ICP_REDUCE_BLOCK) icp_reduce_kernel(const __grid_constant__ IcpArgs a) {
-    __shared__ double s_acc[ICP_REDUCE_BLOCK / 32][32];
-    __shared__ unsigned s_last;
-    __shared__ SolveSmem s_solve;
+// Runs on the first a.reduce_grid blocks of the ROLE 1 launch; block b owns a contiguous chunk of tiles.  The summation
+// order is defined for 8 row groups per block and does not depend on BLOCK (a block of fewer than 8 warps takes several
+// groups per warp): group g adds the tiles t0 + g, t0 + g + 8, ... in increasing order, the 8 group sums are added in
+// group order, the block sums in the same two-level order over blocks.
+template <int KIND, int BLOCK>
+__device__ void icp_reduce_body(const IcpArgs &a, double (*s_acc)[32], unsigned *s_last, SolveSmem &s_solve) {
+    constexpr int GROUPS = 8, WARPS = BLOCK / 32;
     IcpState *st = a.st;
-    grid_dependency_wait();     // the search launch has completed: its tile sums and state are visible
-    if (*(volatile int *)&st->tail_done == a.launch_idx + 1) return;  // the search launch reduced and solved by itself
+    if (blockIdx.x >= a.reduce_grid) return;
+    if (*(volatile int *)&st->tail_done == a.launch_idx + 1) return;  // (the search launch reduced and solved by itself)
     const int done = *(volatile int *)&st->done;
     if (done == 2) return;
     if (done == 1) {  // the search launch before this one only materialised correspondences
@@ -781,20 +822,18 @@ __global__ void __launch_bounds__(ICP_REDUCE_BLOCK) icp_reduce_kernel(const __gr
         return;
     }
     const unsigned n_tiles = a.n_pad / 32;
-    const unsigned n_rows = n_tiles;
-    const unsigned chunk = (n_rows + gridDim.x - 1) / gridDim.x;
-    const unsigned t0 = blockIdx.x * chunk, t1 = min(n_rows, t0 + chunk);
-    const int c = threadIdx.x & 31, g = threadIdx.x >> 5;
-    {
+    const unsigned chunk = (n_tiles + a.reduce_grid - 1) / a.reduce_grid;
+    const unsigned t0 = blockIdx.x * chunk, t1 = min(n_tiles, t0 + chunk);
+    const int c = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int g = warp; g < GROUPS; g += WARPS) {
         // 8 loads in flight per thread, added in tile order (x + 0.0 is exact, so the padding loads of the
         // last batch do not change the sum): the naive loop serialises one L2 round trip per tile
         double t = 0.0;
-        constexpr unsigned STRIDE = ICP_REDUCE_BLOCK / 32;
-        for (unsigned k = t0 + g; k < t1; k += 8 * STRIDE) {
+        for (unsigned k = t0 + g; k < t1; k += 8 * GROUPS) {
             double v[8];
 #pragma unroll
             for (int u = 0; u < 8; ++u) {
-                const unsigned kk = k + u * STRIDE;
+                const unsigned kk = k + u * GROUPS;
                 v[u] = (kk < t1) ? __ldcg(&a.tile_sums[(size_t)kk * 32 + c]) : 0.0;
             }
 #pragma unroll
@@ -806,27 +845,26 @@ __global__ void __launch_bounds__(ICP_REDUCE_BLOCK) icp_reduce_kernel(const __gr
     if (threadIdx.x < 32) {
         double t = 0.0;
 #pragma unroll
-        for (int k = 0; k < ICP_REDUCE_BLOCK / 32; ++k) t += s_acc[k][threadIdx.x];
+        for (int k = 0; k < GROUPS; ++k) t += s_acc[k][threadIdx.x];
         a.partials[(size_t)blockIdx.x * 32 + threadIdx.x] = t;
         __threadfence();
     }
     __syncthreads();
     if (threadIdx.x == 0) {
         unsigned t = atomicAdd(&st->ticket, 1u);
-        s_last = (t == gridDim.x - 1) ? 1u : 0u;
+        *s_last = (t == a.reduce_grid - 1) ? 1u : 0u;
     }
     __syncthreads();
-    if (!s_last) return;
+    if (!*s_last) return;
     __threadfence();
-    {   // all 8 warps share the grid sum (fixed order: row groups of 8, then the 8 group sums)
+    for (int g = warp; g < GROUPS; g += WARPS) {  // the grid sum (fixed order: row groups of 8, then the 8 group sums)
         double t = 0.0;
-        constexpr unsigned STRIDE = ICP_REDUCE_BLOCK / 32;
-        for (unsigned b = g; b < gridDim.x; b += 8 * STRIDE) {
+        for (unsigned b = g; b < a.reduce_grid; b += 8 * GROUPS) {
             double v[8];
 #pragma unroll
             for (int u = 0; u < 8; ++u) {
-                const unsigned bb = b + u * STRIDE;
-                v[u] = (bb < gridDim.x) ? __ldcg(&a.partials[(size_t)bb * 32 + c]) : 0.0;
+                const unsigned bb = b + u * GROUPS;
+                v[u] = (bb < a.reduce_grid) ? __ldcg(&a.partials[(size_t)bb * 32 + c]) : 0.0;
             }
 #pragma unroll
             for (int u = 0; u < 8; ++u) t += v[u];
@@ -837,7 +875,7 @@ __global__ void __launch_bounds__(ICP_REDUCE_BLOCK) icp_reduce_kernel(const __gr
     if (threadIdx.x < 32) {
         double t = 0.0;
 #pragma unroll
-        for (int k = 0; k < ICP_REDUCE_BLOCK / 32; ++k) t += s_acc[k][threadIdx.x];
+        for (int k = 0; k < GROUPS; ++k) t += s_acc[k][threadIdx.x];
         if (a.use_p2p) t = p2p_exchange_sum(a.p2p, t);  // the collective, fused: NVLink stores + flags
         if (a.defer_finalize) st->local[threadIdx.x] = t;
         else st->total[threadIdx.x] = t;

@@ -43,11 +43,12 @@ struct IcpArgs {
     const float4 *tgt_nrm, *tgt_grad, *tgt_cov;
     int has_tgt_col;
     IcpState *st;
-    double *partials;     // [reduce grid][32]
+    double *partials;     // [max(reduce grid, ROLE 1 grid)][32]
     double *tile_sums;    // [n_pad/32][32]
     unsigned *flag_bits;  // [2][flag_words] certified regime: bit t = tile t needed a search in the last certified launch
     unsigned flag_words;  // words per bitmap
     unsigned helper_blocks;  // certified regime: the last blocks of the grid run the flagged tiles (0 = none)
+    unsigned reduce_grid;    // blocks of the ROLE 1 launch that sum the tile sums of a searching launch
     int2 *prev;           // [n_pad] per source position: .x INDEX POSITION of last iteration's match (-1 none), .y float bits
                           // of the certificate slack (lower bound on the distance to every OTHER target point); or null
     float cert_gain;      // margin = cert_gain * displacement (0 disables the certificates)

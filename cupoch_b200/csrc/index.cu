@@ -10,6 +10,8 @@
 #include <stdarg.h>
 #include <string.h>
 
+#include <stdlib.h>
+
 #include "cphb_internal.cuh"
 
 // ---------------------------------------------------------------------------
@@ -171,7 +173,7 @@ __global__ void __launch_bounds__(256) bounds_kernel(const float *__restrict__ x
 }
 
 __global__ void __launch_bounds__(256) hilbert_key_kernel(const float *__restrict__ xyz, size_t n,
-                                                          const unsigned *__restrict__ b, uint32_t *keys,
+                                                          const unsigned *__restrict__ b, int shift, uint32_t *keys,
                                                           uint32_t *vals) {
     size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -184,7 +186,7 @@ __global__ void __launch_bounds__(256) hilbert_key_kernel(const float *__restric
         float v = (xyz[3 * i + a] - mn[a]) * scale;
         c[a] = (uint32_t)fminf(fmaxf(v, 0.f), 1023.f);
     }
-    keys[i] = hilbert30(c[0], c[1], c[2]);
+    keys[i] = hilbert30(c[0], c[1], c[2]) >> shift;  // the leading 3 * levels bits ARE the coarser curve's index
     vals[i] = (uint32_t)i;
 }
 
@@ -258,12 +260,26 @@ __global__ void __launch_bounds__(KD_THREADS) kd_refine_kernel(float4 *pts, size
         }
         __syncthreads();
         for (int e = tid; e < KD_GROUP; e += KD_THREADS) {
+            // a warp's 32 consecutive elements lie in ONE segment (segments are aligned runs of >= 64 elements):
+            // warp-wide REDUX first, then one set of shared-memory atomics per warp instead of one per point (at level 0
+            // all 1024 points of the group hit the same six words)
             const float4 q = src[e];
-            if (__float_as_uint(q.w) != 0xffffffffu) {
-                const int sg = e / S;
-                atomicMin(&m.lo[sg][0], f2ord(q.x)); atomicMax(&m.hi[sg][0], f2ord(q.x));
-                atomicMin(&m.lo[sg][1], f2ord(q.y)); atomicMax(&m.hi[sg][1], f2ord(q.y));
-                atomicMin(&m.lo[sg][2], f2ord(q.z)); atomicMax(&m.hi[sg][2], f2ord(q.z));
+            const bool real = __float_as_uint(q.w) != 0xffffffffu;
+            unsigned lo3[3], hi3[3];
+            lo3[0] = real ? f2ord(q.x) : 0xffffffffu; hi3[0] = real ? f2ord(q.x) : 0u;
+            lo3[1] = real ? f2ord(q.y) : 0xffffffffu; hi3[1] = real ? f2ord(q.y) : 0u;
+            lo3[2] = real ? f2ord(q.z) : 0xffffffffu; hi3[2] = real ? f2ord(q.z) : 0u;
+#pragma unroll
+            for (int a = 0; a < 3; ++a) {
+                lo3[a] = __reduce_min_sync(CPHB_FULL, lo3[a]);
+                hi3[a] = __reduce_max_sync(CPHB_FULL, hi3[a]);
+            }
+            if (lane < 3) {
+                const int sg = e / S;  // (same for the whole warp)
+                const unsigned l = lane == 0 ? lo3[0] : lane == 1 ? lo3[1] : lo3[2];
+                const unsigned h = lane == 0 ? hi3[0] : lane == 1 ? hi3[1] : hi3[2];
+                atomicMin(&m.lo[sg][lane], l);
+                atomicMax(&m.hi[sg][lane], h);
             }
         }
         __syncthreads();
@@ -467,9 +483,18 @@ int cphb_hilbert_order(const float *xyz, size_t n, uint32_t *perm_out, float *bo
         if (grid > 148 * 8) grid = 148 * 8;
         CPHB_LAUNCH(bounds_kernel, grid, 256, 0, s, xyz, n, b);
     }
-    CPHB_LAUNCH(hilbert_key_kernel, (unsigned)((n + 255) / 256), 256, 0, s, xyz, n, b, keys, vals);
+    // Curve resolution by cloud size: ceil(log2(n) / 3) + 1 levels (3 bits each), i.e. >= 8 curve cells per point of a
+    // volume-filling cloud; 1 M points -> 8 levels = 24-bit keys = 3 radix passes instead of 4.  The order only has to
+    // cluster (every search is exact whatever the order; groups of 1024 are kd-refined afterwards), equal keys keep their
+    // original order (stable sort).  CPHB_HILBERT_LEVELS overrides (tuning hook).
+    int levels = 1;
+    while (levels < 10 && ((size_t)1 << (3 * levels)) < n) ++levels;
+    levels = levels + 1 > 10 ? 10 : levels + 1;
+    if (levels < 4) levels = 4;
+    if (const char *e = getenv("CPHB_HILBERT_LEVELS")) { int v = atoi(e); if (v >= 1 && v <= 10) levels = v; }
+    CPHB_LAUNCH(hilbert_key_kernel, (unsigned)((n + 255) / 256), 256, 0, s, xyz, n, b, 30 - 3 * levels, keys, vals);
     CPHB_CHECK_LAUNCH();
-    rc = cphb_sort_pairs_u32(keys, keys2, vals, perm_out, n, 30, s);
+    rc = cphb_sort_pairs_u32(keys, keys2, vals, perm_out, n, 3 * levels, s);
     cphb_free_async(scratch, s);
     cphb_free_async(own, s);
     return rc;

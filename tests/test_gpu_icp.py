@@ -298,8 +298,10 @@ def test_user_defined_estimator_generic_loop(orc):
     assert Mine.calls == 6
     _compare(res, ref)
     fused = R.registration_icp(cloud(src), cloud(tgt, tn), 0.03, init, R.TransformationEstimationPointToPlane(), crit)
-    np.testing.assert_array_equal(res.transformation, fused.transformation)
+    # (the standalone ComputeTransformation adds its float64 products in another order than the fused kernel: the
+    # poses agree to the last bits, not necessarily in them)
+    assert np.linalg.norm(res.transformation.astype(np.float64) - fused.transformation) <= POSE_TOL
     np.testing.assert_array_equal(res.correspondence_set, fused.correspondence_set)
     # host-buffer entry point takes the same route
     res_h = R.registration_icp_host(src, tgt, 0.03, init, Mine(), crit, target_normals=tn, return_correspondences=True)
-    np.testing.assert_array_equal(res_h.transformation, fused.transformation)
+    np.testing.assert_array_equal(res_h.transformation, res.transformation)
