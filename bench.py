@@ -365,6 +365,12 @@ def run_native(args, rank, world):
                                      "note": "same workload, every launch searches (CPHB_CERT_GAIN=0); identical result"}
         # (b) config 3 of BASELINE.json: VoxelDownSample(0.02) + SearchRadius(k=1, r=0.05) on 10 M points
         extra["config3"] = config3_records(cph, L, timed, peaks()[0], args)
+    if not args.no_extras and args.points4 > 0:
+        # (c) config 4 of BASELINE.json (the configuration it names for 8 GPUs) at EVERY N, so that the driver's 1 -> 8 runs
+        #     time it: Generalized ICP 5 M -> 5 M, source sharded over the ranks
+        c4 = config4_record(cph, L, timed, peaks()[0], args, rank, world, comm, dist)
+        if rank == 0:
+            extra["config4"] = c4
     if rank == 0:
         sampler.stop_flag = True
         sampler.join(timeout=2)
@@ -467,6 +473,49 @@ def cpu_baseline(src, tgt, tn, gpu_res):
     return base, parity
 
 
+def config4_record(cph, L, timed, peak, args, rank, world, comm, dist):
+    """BASELINE.json config 4 as a sub-record at every N: Generalized ICP, 5 M -> 5 M points (analytic surface, normals
+    given -> covariances), 30 iterations, r = 0.02, the source sharded over the ranks by the library (Hilbert-contiguous
+    blocks), the target and its index replicated, one exchange of 32 float64 per iteration.  value = iterations / s of
+    whole registrations (index build, source ordering, result included), clouds resident; max over ranks."""
+    from cupoch_b200.testing import datagen
+    R, G = cph.registration, cph.geometry
+    n4 = args.points4
+    tgt, tn = datagen.surface(n4, 11)
+    src, sn = datagen.make_source(tgt, datagen.gt_transform(), 13, 14, 5e-4, attrs=[(tn, True)])
+    t_pc, s_pc = G.PointCloud(tgt), G.PointCloud(src)
+    t_pc.normals, s_pc.normals = tn, sn
+    est, crit = R.TransformationEstimationForGeneralizedICP(1e-3), R.ICPConvergenceCriteria(0, 0, ITERS)
+    s_c, t_c = R._with_covariances(s_pc, 1e-3), R._with_covariances(t_pc, 1e-3)
+    shard = (rank, world) if world > 1 else None
+    run = lambda: R.registration_icp(s_c, t_c, MAX_DIST, np.eye(4, dtype=np.float32), est, crit, comm=comm,
+                                     return_correspondences=False, shard=shard)
+    for _ in range(2):
+        run()
+    reps = 3
+    ms, res = timed(run, reps)
+    loop_ms = res.loop_ms
+    if dist is not None:
+        import torch
+        t = torch.tensor([ms, loop_ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms, loop_ms = [float(x) for x in t.tolist()]
+    ms /= reps
+    units = n4 // world
+    launch_ms = loop_ms / (ITERS + 1)
+    ach = 96 * units / (launch_ms * 1e-3) / 1e9
+    gt = datagen.gt_transform()
+    return {"workload": "config4: Generalized ICP %d -> %d, %d iters, r=%.2f, eps=1e-3, source sharded x%d" % (n4, n4, ITERS, MAX_DIST, world),
+            "points": n4, "value": ITERS * 1e3 / ms, "unit": "iter/s", "ms_per_registration": ms,
+            "loop_iters_per_sec": ITERS * 1e3 / loop_ms, "scaling": "strong",
+            "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                         "algorithmic_bytes_per_launch": 96 * units, "launch_ms": launch_ms,
+                         "note": "per GPU: 96 B per source point of this rank's block (SURVEY 8d) / (loop time / 31 launches)"},
+            "final": {"fitness": res.fitness, "inlier_rmse": res.inlier_rmse,
+                      "pose_error_vs_ground_truth": float(np.linalg.norm(np.asarray(res.transformation, np.float64) - gt)),
+                      "T": np.asarray(res.transformation).round(7).tolist()}}
+
+
 def config3_records(cph, L, timed, peak, args):
     """BASELINE.json config 3 as sub-records with their own roofline (SURVEY 8d bytes): VoxelDownSample(0.02) of 10 M
     uniform points in [0,4)x[0,4)x[0,1), then SearchRadius(k=1, r=0.05) of the 10 M points against the down-sampled
@@ -510,6 +559,7 @@ def main():
     ap.add_argument("--no-host-call", action="store_true", help="skip the cphb_registration_icp_host e2e variant")
     ap.add_argument("--no-extras", action="store_true", help="skip the certificates-off and config-3 sub-records")
     ap.add_argument("--points3", type=int, default=10_000_000, help="size of the config-3 sub-records")
+    ap.add_argument("--points4", type=int, default=5_000_000, help="size of the config-4 sub-record (0 = skip)")
     ap.add_argument("--comm", default="p2p", choices=["p2p", "nccl"],
                     help="N>1 exchange: p2p = peer-memory stores fused into the reduce kernel, nccl = ncclAllReduce")
     args = ap.parse_args()

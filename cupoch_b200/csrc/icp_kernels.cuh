@@ -568,6 +568,12 @@ icp_iteration_kernel(const __grid_constant__ IcpArgs a) {
         }
         unsigned fw = (tile < n_tiles) ? __ldg(&flag_cur[tile >> 5]) : 0u;  // flag word of the next tile, one tile ahead
         int slot = 0, gslot = 0;
+        // The hot loop holds no search code: a tile that needs a search breaks out of it, is handled below (cold) and the
+        // loop is re-entered -- the instructions a certified tile executes stay one compact run.
+        float4 cold_s = make_float4(0.f, 0.f, 0.f, 0.f);
+        int2 cold_pv = make_int2(-1, 0);
+        for (;;) {
+        bool cold = false;
         for (; tile < n_tiles; tile += main_warps) {
             cp_async_wait<ICP_GD - 1>();
             const unsigned t1 = tile + main_warps, tg = tile + ICP_GD * main_warps, tn = tile + ICP_NS * main_warps;
@@ -600,25 +606,10 @@ icp_iteration_kernel(const __grid_constant__ IcpArgs a) {
             if (flagged) continue;
             const bool need_search = __any_sync(CPHB_FULL, in_range && !cert);
             if (need_search) {  // not predicted by the flags (the first certified launch, or a point that drifted)
-                if (lane == 0) atomicOr(&flag_next[tile >> 5], 1u << (tile & 31));
-                if (!c.materialize) {
-#pragma unroll
-                    for (int p = 0; p < 32; ++p) {
-                        if (!pair_live(P2P, p)) continue;
-                        double t = lacc[p];
-#pragma unroll
-                        for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(CPHB_FULL, t, o);
-                        if (lane == p) wrow += t;
-                    }
-                }
-                double acc;
-                search_tile<KIND, TOP>(a, c, w, s_rows[warp], tile, s0, pv, acc);
-                searched_inline = true;
-                wrow += acc;
-#pragma unroll
-                for (int p = 0; p < 32; ++p) lacc[p] = 0.0;
-                if (a.dbg && lane == 0) atomicAdd(&a.dbg[128 + min(a.launch_idx, 63)], 1u);
-                continue;
+                cold = true;
+                cold_s = s0;
+                cold_pv = pv;
+                break;
             }
             ++n_skipped;
             lane_writeback<KIND>(a, c, i, s, sn, Cs);
@@ -650,6 +641,31 @@ icp_iteration_kernel(const __grid_constant__ IcpArgs a) {
                     if (pair_live(P2P, p))
                         lacc[p] = fma(v[P2P ? pair_p2p_a(p) : pair_jtj_a(p)], v[P2P ? pair_p2p_b(p) : pair_jtj_b(p)], lacc[p]);
             }
+        }
+        if (!cold) break;
+        // ---- cold: tile `tile` needs its search.  The accumulators are folded into the warp's running row first, so
+        // they are dead while the search runs; then the hot loop resumes with the next tile.
+        if (lane == 0) atomicOr(&flag_next[tile >> 5], 1u << (tile & 31));
+        if (!c.materialize) {
+#pragma unroll
+            for (int p = 0; p < 32; ++p) {
+                if (!pair_live(P2P, p)) continue;
+                double t = lacc[p];
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(CPHB_FULL, t, o);
+                if (lane == p) wrow += t;
+            }
+        }
+        {
+            double acc;
+            search_tile<KIND, TOP>(a, c, w, s_rows[warp], tile, cold_s, cold_pv, acc);
+            searched_inline = true;
+            wrow += acc;
+        }
+#pragma unroll
+        for (int p = 0; p < 32; ++p) lacc[p] = 0.0;
+        if (a.dbg && lane == 0) atomicAdd(&a.dbg[128 + min(a.launch_idx, 63)], 1u);
+        tile += main_warps;
         }
         cp_async_wait_0();
         if (lane == 0) { dbg_time(a, 1, false); dbg_time(a, searched_inline ? 9 : 8, false); }

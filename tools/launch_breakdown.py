@@ -1,5 +1,5 @@
 """Per-kernel breakdown of ONE registration from an ncu launch list (gpu__time_duration.sum CSV).
-usage: python tools/launch_breakdown.py gpurun_out/launches.csv [iterations_per_registration]"""
+usage: python tools/launch_breakdown.py gpurun_out/launches.csv [iteration_kernel_launches_per_registration]"""
 import csv
 import sys
 from collections import OrderedDict
@@ -7,7 +7,7 @@ from collections import OrderedDict
 
 def main():
     path = sys.argv[1]
-    n_it = int(sys.argv[2]) if len(sys.argv) > 2 else 31
+    n_it = int(sys.argv[2]) if len(sys.argv) > 2 else 62  # 31 iterations x 2 instances (searching / certified+sum)
     lines = [l for l in open(path) if not l.startswith("==")]
     rows = [(r["Kernel Name"].split("(")[0].replace("void ", "")[:48], float(r["Metric Value"].replace(",", "")) / 1000)
             for r in csv.DictReader(lines) if r.get("Metric Name") == "gpu__time_duration.sum"]
@@ -33,8 +33,8 @@ def main():
     while e < len(rows) and "compact" in rows[e][0]:
         e += 1
     seg = rows[s0:e]
-    it = [round(rows[i][1], 1) for i in last]
-    print("iteration kernel us per launch:", it)
+    print("searching instance, us per launch:       ", [round(rows[i][1], 1) for i in last if rows[i][0].rstrip().endswith(", 0>")])
+    print("certified / sum+solve instance, us per launch:", [round(rows[i][1], 1) for i in last if rows[i][0].rstrip().endswith(", 1>")])
     agg = OrderedDict()
     for n, t in seg:
         k = agg.setdefault(n, [0, 0.0])
