@@ -38,8 +38,30 @@ class IcpResult(C.Structure):
                 ("loop_ms", C.c_float), ("loop_launches", C.c_int)]
 
 
+class OccGridParams(C.Structure):
+    _fields_ = [("clamping_thres_min", C.c_float), ("clamping_thres_max", C.c_float), ("prob_hit_log", C.c_float),
+                ("prob_miss_log", C.c_float), ("occ_prob_thres_log", C.c_float)]
+
+
 _P = C.c_void_p
+_F3 = C.POINTER(C.c_float)
+_I3 = C.POINTER(C.c_int32)
 _SIGNATURES = {
+    "cphb_occgrid_default_params": (None, [C.POINTER(OccGridParams)]),
+    "cphb_occgrid_create": (C.c_int, [C.c_float, C.c_int, _F3, _P, C.POINTER(_P)]),
+    "cphb_occgrid_destroy": (None, [_P]),
+    "cphb_occgrid_clear": (C.c_int, [_P, _P]),
+    "cphb_occgrid_set_params": (C.c_int, [_P, C.POINTER(OccGridParams)]),
+    "cphb_occgrid_set_geometry": (C.c_int, [_P, C.c_float, _F3]),
+    "cphb_occgrid_data": (_P, [_P]),
+    "cphb_occgrid_resolution": (C.c_int, [_P]),
+    "cphb_occgrid_insert": (C.c_int, [_P, _P, C.c_size_t, _F3, C.c_float, _P]),
+    "cphb_occgrid_add_voxels": (C.c_int, [_P, _P, C.c_size_t, C.c_int, _P]),
+    "cphb_occgrid_add_voxel": (C.c_int, [_P, _I3, C.c_int, _P]),
+    "cphb_occgrid_set_free_area": (C.c_int, [_P, _F3, _F3, _P]),
+    "cphb_occgrid_bounds": (C.c_int, [_P, _I3, _I3, _P]),
+    "cphb_occgrid_extract": (C.c_int, [_P, C.c_int, _P, _P, C.c_size_t, C.POINTER(C.c_size_t), _P]),
+    "cphb_occgrid_get_voxel": (C.c_int, [_P, _F3, C.POINTER(C.c_int), C.POINTER(C.c_float), _I3, _P]),
     # name: (restype, argtypes)
     "cphb_version": (C.c_int, []),
     "cphb_last_error": (C.c_char_p, []),

@@ -228,7 +228,7 @@ __global__ void __launch_bounds__(256) gather_points_kernel(const float *__restr
 // memory) -> stable partition around it.  The split only has to be a valid partition (search correctness
 // never depends on it); quantisation can make sibling boxes overlap by at most 2^-14 of the extent.
 struct KdSmem {
-    float4 p[2][KD_GROUP];
+    float4 p[KD_GROUP];  // partitioned in place: every thread holds its 4 elements in registers across the barrier
     unsigned key[KD_GROUP];
     unsigned hist[16][256];
     unsigned lo[16][3], hi[16][3];
@@ -244,14 +244,13 @@ __global__ void __launch_bounds__(KD_THREADS) kd_refine_kernel(float4 *pts, size
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     for (int e = tid; e < KD_GROUP; e += KD_THREADS) {
         size_t i = base + e;
-        m.p[0][e] = (i < n_pad) ? pts[i] : make_float4(FLT_MAX, FLT_MAX, FLT_MAX, __uint_as_float(0xffffffffu));
+        m.p[e] = (i < n_pad) ? pts[i] : make_float4(FLT_MAX, FLT_MAX, FLT_MAX, __uint_as_float(0xffffffffu));
     }
     __syncthreads();
-    int cur = 0;
     for (int level = 0; level < 5; ++level) {
         const int S = KD_GROUP >> level, n_seg = 1 << level, half = S >> 1;
-        const float4 *src = m.p[cur];
-        float4 *dst = m.p[cur ^ 1];
+        const float4 *src = m.p;
+        float4 *dst = m.p;
         if (tid < n_seg) {
 #pragma unroll
             for (int a = 0; a < 3; ++a) { m.lo[tid][a] = 0xffffffffu; m.hi[tid][a] = 0u; }
@@ -373,7 +372,10 @@ __global__ void __launch_bounds__(KD_THREADS) kd_refine_kernel(float4 *pts, size
                 run += f[r4];
             }
             if (tid == KD_THREADS - 1) m.scan[KD_GROUP] = run;
-            __syncthreads();
+            float4 mine[4];
+#pragma unroll
+            for (int r4 = 0; r4 < 4; ++r4) mine[r4] = src[4 * tid + r4];
+            __syncthreads();  // scan complete AND every element is in a register: the array may be overwritten
 #pragma unroll
             for (int r4 = 0; r4 < 4; ++r4) {
                 const int e = 4 * tid + r4;
@@ -381,15 +383,14 @@ __global__ void __launch_bounds__(KD_THREADS) kd_refine_kernel(float4 *pts, size
                 const unsigned lower_before = m.scan[e] - m.scan[s0];
                 const unsigned pos_in_seg = (unsigned)(e - s0);
                 const unsigned d = f[r4] ? (unsigned)s0 + lower_before : (unsigned)s0 + (unsigned)half + (pos_in_seg - lower_before);
-                dst[d] = src[e];
+                dst[d] = mine[r4];
             }
         }
         __syncthreads();
-        cur ^= 1;
     }
     for (int e = tid; e < KD_GROUP; e += KD_THREADS) {
         size_t i = base + e;
-        if (i < n_pad) pts[i] = m.p[cur][e];
+        if (i < n_pad) pts[i] = m.p[e];
     }
 }
 

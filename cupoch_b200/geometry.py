@@ -367,6 +367,161 @@ class VoxelGrid:
                                                                mx + v * np.float32(0.5))
 
 
+class OccupancyVoxel:
+    """geometry::OccupancyVoxel (occupancygrid.h:33-72): grid_index (3 uint16), prob_log, color (the default (0, 0, 1):
+    nothing on this path ever changes it)."""
+
+    def __init__(self, grid_index=(0, 0, 0), prob_log=float("nan"), color=(0.0, 0.0, 1.0)):
+        self.grid_index = np.asarray(grid_index, np.uint16)
+        self.prob_log = float(prob_log)
+        self.color = np.asarray(color, np.float32)
+
+    def __repr__(self):
+        return "geometry::OccupancyVoxel with grid_index: (%d, %d, %d), prob_log: %f" % (*self.grid_index.tolist(), self.prob_log)
+
+
+class OccupancyGrid:
+    """geometry::OccupancyGrid (occupancygrid.h:74-147; pybind occupancygrid.cpp:77-126): dense log-odds grid on the device.
+    `voxel_size`, `origin` and the five probability parameters are plain attributes as in the reference."""
+
+    def __init__(self, voxel_size=0.05, resolution=512, origin=(0.0, 0.0, 0.0)):
+        _lib.require_gpu()
+        self._h = C.c_void_p()
+        self._voxel_size, self._resolution = float(voxel_size), int(resolution)
+        self._origin = np.asarray(origin, np.float32).reshape(3).copy()
+        p = _lib.OccGridParams()
+        _lib.lib().cphb_occgrid_default_params(C.byref(p))
+        self.clamping_thres_min, self.clamping_thres_max = p.clamping_thres_min, p.clamping_thres_max
+        self.prob_hit_log, self.prob_miss_log, self.occ_prob_thres_log = p.prob_hit_log, p.prob_miss_log, p.occ_prob_thres_log
+        self.visualize_free_area = True
+        _lib.check(_lib.lib().cphb_occgrid_create(self._voxel_size, self._resolution, self._f3(self._origin), None, C.byref(self._h)))
+
+    @staticmethod
+    def _f3(v):
+        return (C.c_float * 3)(*np.asarray(v, np.float32).reshape(3).tolist())
+
+    # voxel_size_ / origin_ are public members of the reference (its own tests assign them after construction)
+    voxel_size = property(lambda s: s._voxel_size, lambda s, v: s._set_geometry(voxel_size=v))
+    origin = property(lambda s: s._origin, lambda s, v: s._set_geometry(origin=v))
+    resolution = property(lambda s: s._resolution)
+
+    def _set_geometry(self, voxel_size=None, origin=None):
+        if voxel_size is not None:
+            self._voxel_size = float(voxel_size)
+        if origin is not None:
+            self._origin = np.asarray(origin, np.float32).reshape(3).copy()
+        _lib.check(_lib.lib().cphb_occgrid_set_geometry(self._h, self._voxel_size, self._f3(self._origin)))
+
+    def _sync_params(self):
+        p = _lib.OccGridParams(self.clamping_thres_min, self.clamping_thres_max, self.prob_hit_log, self.prob_miss_log,
+                               self.occ_prob_thres_log)
+        _lib.check(_lib.lib().cphb_occgrid_set_params(self._h, C.byref(p)))
+
+    def clear(self):
+        _lib.check(_lib.lib().cphb_occgrid_clear(self._h, None))
+        return self
+
+    def insert(self, pointcloud, viewpoint, max_range=-1.0):
+        """OccupancyGrid::Insert(pointcloud | points, viewpoint, max_range) (occupancygrid.cu:462-552)"""
+        pts = pointcloud.points if isinstance(pointcloud, PointCloud) else Vector3fVector(pointcloud)
+        self._sync_params()
+        if pts is not None and len(pts):
+            _lib.check(_lib.lib().cphb_occgrid_insert(self._h, pts.ptr, len(pts), self._f3(viewpoint), float(max_range), None))
+        return self
+
+    def add_voxel(self, voxel, occupied=False):
+        self._sync_params()
+        v = (C.c_int32 * 3)(*[int(x) for x in voxel])
+        _lib.check(_lib.lib().cphb_occgrid_add_voxel(self._h, v, int(bool(occupied)), None))
+        return self
+
+    def add_voxels(self, voxels, occupied=False):
+        self._sync_params()
+        d = voxels if isinstance(voxels, DeviceArray) else DeviceArray.from_numpy(np.ascontiguousarray(voxels, np.int32).reshape(-1, 3), np.int32)
+        if len(d):
+            _lib.check(_lib.lib().cphb_occgrid_add_voxels(self._h, d.ptr, len(d), int(bool(occupied)), None))
+        return self
+
+    def set_free_area(self, min_bound, max_bound):
+        self._sync_params()
+        _lib.check(_lib.lib().cphb_occgrid_set_free_area(self._h, self._f3(min_bound), self._f3(max_bound), None))
+        return self
+
+    def _bounds(self):
+        lo, hi = (C.c_int32 * 3)(), (C.c_int32 * 3)()
+        _lib.check(_lib.lib().cphb_occgrid_bounds(self._h, lo, hi, None))
+        return np.array(lo, np.int32), np.array(hi, np.int32)
+
+    def get_min_bound(self):                  # occupancygrid.cu:317-322
+        lo, _ = self._bounds()
+        return ((lo - self._resolution // 2).astype(np.float32) * np.float32(self._voxel_size) + self._origin).astype(np.float32)
+
+    def get_max_bound(self):                  # occupancygrid.cu:324-333
+        _, hi = self._bounds()
+        return ((hi - (self._resolution // 2 - 1)).astype(np.float32) * np.float32(self._voxel_size) + self._origin).astype(np.float32)
+
+    def _extract(self, which):
+        self._sync_params()
+        cnt = C.c_size_t(0)
+        _lib.check(_lib.lib().cphb_occgrid_extract(self._h, which, None, None, 0, C.byref(cnt), None))
+        m = int(cnt.value)
+        if m == 0:
+            return np.zeros((0, 3), np.int32), np.zeros(0, np.float32)
+        idx, pr = DeviceArray((m, 3), np.int32), DeviceArray((m,), np.float32)
+        _lib.check(_lib.lib().cphb_occgrid_extract(self._h, which, idx.ptr, pr.ptr, m, C.byref(cnt), None))
+        return idx.cpu(), pr.cpu()
+
+    def extract_known_voxels(self):
+        """-> (grid_index [m, 3] int32, prob_log [m] float32), bound-box order (ExtractKnownVoxels, occupancygrid.cu:380-388)"""
+        return self._extract(0)
+
+    def extract_free_voxels(self):
+        return self._extract(1)
+
+    def extract_occupied_voxels(self):
+        return self._extract(2)
+
+    @property
+    def voxels(self):
+        """the known voxels as OccupancyVoxel objects (pybind property, occupancygrid.cpp:98-101)"""
+        idx, pr = self._extract(0)
+        return [OccupancyVoxel(i, p) for i, p in zip(idx, pr)]
+
+    def get_voxel(self, point):
+        """-> (known, OccupancyVoxel)  (GetVoxel, occupancygrid.cu:351-356)"""
+        k, p, gi = C.c_int(0), C.c_float(0), (C.c_int32 * 3)()
+        _lib.check(_lib.lib().cphb_occgrid_get_voxel(self._h, self._f3(point), C.byref(k), C.byref(p), gi, None))
+        return bool(k.value), OccupancyVoxel(list(gi), p.value)
+
+    def is_occupied(self, point):             # occupancygrid.cu:335-341
+        k, v = self.get_voxel(point)
+        return bool(k and v.prob_log > self.occ_prob_thres_log)
+
+    def is_unknown(self, point):              # occupancygrid.cu:343-348
+        return not self.get_voxel(point)[0]
+
+    def has_voxels(self):
+        return True
+
+    def to_torch(self):
+        """zero-copy [res, res, res] float32 CUDA tensor of the log-odds (NaN = unknown)"""
+        import torch
+        r = self._resolution
+        return torch.as_tensor(DeviceArray((r, r, r), np.float32, ptr=_lib.lib().cphb_occgrid_data(self._h), base=self), device="cuda")
+
+    def __repr__(self):
+        return "geometry::OccupancyGrid with %d voxels." % len(self._extract(0)[1])
+
+    def __del__(self):
+        try:
+            if self._h:
+                _lib.lib().cphb_stream_synchronize(None)
+                _lib.lib().cphb_occgrid_destroy(self._h)
+                self._h = None
+        except Exception:
+            pass
+
+
 class KDTreeFlann:
     """knn::KDTreeFlann (kdtree_flann.h:43-124), exposed as cupoch.geometry.KDTreeFlann
     (kdtree_flann.cpp:93-95)."""

@@ -15,6 +15,7 @@
 #include <stdexcept>
 #include <tuple>
 #include <utility>
+#include <limits>
 #include <vector>
 
 #include "cupoch_b200.h"
@@ -514,6 +515,129 @@ public:
     Eigen::Vector3f origin_ = Eigen::Vector3f(0.f, 0.f, 0.f);
     utility::device_vector<Eigen::Vector3i> voxels_keys_;
     utility::device_vector<Eigen::Vector3f> voxels_colors_;
+};
+
+/// geometry::OccupancyVoxel (occupancygrid.h:33-72)
+class OccupancyVoxel {
+public:
+    OccupancyVoxel() {}
+    OccupancyVoxel(const Eigen::Vector3i &grid_index, float prob_log) : grid_index_(grid_index), prob_log_(prob_log) {}
+    Eigen::Vector3i grid_index_ = Eigen::Vector3i(0, 0, 0);           // (Vector3ui16 in the reference)
+    Eigen::Vector3f color_ = Eigen::Vector3f(0.0f, 0.0f, 1.0f);
+    float prob_log_ = std::numeric_limits<float>::quiet_NaN();
+};
+
+/// geometry::OccupancyGrid (occupancygrid.h:74-147): dense log-odds grid; Insert ray-casts a scan into it.  The members
+/// the reference exposes (voxel_size_, origin_, the probability parameters) are public here too and are handed to the
+/// engine at every call.  Extract* return host vectors of voxels (the reference returns device vectors of its 24-byte
+/// voxel struct; the engine stores 4.1 bytes per cell and materialises voxels on request).
+class OccupancyGrid {
+public:
+    OccupancyGrid() : OccupancyGrid(0.05f, 512) {}
+    OccupancyGrid(float voxel_size, size_t resolution = 512, const Eigen::Vector3f &origin = Eigen::Vector3f(0.f, 0.f, 0.f))
+        : voxel_size_(voxel_size), resolution_(resolution), origin_(origin) {
+        const float o[3] = {origin[0], origin[1], origin[2]};
+        utility::check(cphb_occgrid_create(voxel_size, (int)resolution, o, nullptr, &h_));
+    }
+    ~OccupancyGrid() { cphb_stream_synchronize(nullptr); cphb_occgrid_destroy(h_); }
+    OccupancyGrid(const OccupancyGrid &) = delete;
+    OccupancyGrid &operator=(const OccupancyGrid &) = delete;
+
+    OccupancyGrid &Clear() { utility::check(cphb_occgrid_clear(h_, nullptr)); return *this; }
+    bool HasVoxels() const { return true; }
+    bool HasColors() const { return true; }
+    Eigen::Vector3f GetMinBound() const {  // occupancygrid.cu:317-322
+        int32_t lo[3], hi[3];
+        utility::check(cphb_occgrid_bounds(h_, lo, hi, nullptr));
+        const int h = (int)resolution_ / 2;
+        return Eigen::Vector3f((lo[0] - h) * voxel_size_ + origin_[0], (lo[1] - h) * voxel_size_ + origin_[1], (lo[2] - h) * voxel_size_ + origin_[2]);
+    }
+    Eigen::Vector3f GetMaxBound() const {  // occupancygrid.cu:324-333
+        int32_t lo[3], hi[3];
+        utility::check(cphb_occgrid_bounds(h_, lo, hi, nullptr));
+        const int h = (int)resolution_ / 2 - 1;
+        return Eigen::Vector3f((hi[0] - h) * voxel_size_ + origin_[0], (hi[1] - h) * voxel_size_ + origin_[1], (hi[2] - h) * voxel_size_ + origin_[2]);
+    }
+    std::tuple<bool, OccupancyVoxel> GetVoxel(const Eigen::Vector3f &point) const {  // occupancygrid.cu:351-356
+        sync();
+        const float p[3] = {point[0], point[1], point[2]};
+        int known = 0, gi[3];
+        float prob = 0.f;
+        utility::check(cphb_occgrid_get_voxel(h_, p, &known, &prob, gi, nullptr));
+        return std::make_tuple(known != 0, OccupancyVoxel(Eigen::Vector3i(gi[0], gi[1], gi[2]), prob));
+    }
+    bool IsOccupied(const Eigen::Vector3f &point) const {
+        auto r = GetVoxel(point);
+        return std::get<0>(r) && std::get<1>(r).prob_log_ > occ_prob_thres_log_;
+    }
+    bool IsUnknown(const Eigen::Vector3f &point) const { return !std::get<0>(GetVoxel(point)); }
+    std::shared_ptr<std::vector<OccupancyVoxel>> ExtractKnownVoxels() const { return extract(0); }
+    std::shared_ptr<std::vector<OccupancyVoxel>> ExtractFreeVoxels() const { return extract(1); }
+    std::shared_ptr<std::vector<OccupancyVoxel>> ExtractOccupiedVoxels() const { return extract(2); }
+    OccupancyGrid &SetFreeArea(const Eigen::Vector3f &min_bound, const Eigen::Vector3f &max_bound) {
+        sync();
+        const float lo[3] = {min_bound[0], min_bound[1], min_bound[2]}, hi[3] = {max_bound[0], max_bound[1], max_bound[2]};
+        utility::check(cphb_occgrid_set_free_area(h_, lo, hi, nullptr));
+        return *this;
+    }
+    OccupancyGrid &Insert(const utility::device_vector<Eigen::Vector3f> &points, const Eigen::Vector3f &viewpoint, float max_range = -1.0f) {
+        sync();
+        const float v[3] = {viewpoint[0], viewpoint[1], viewpoint[2]};
+        if (points.size()) utility::check(cphb_occgrid_insert(h_, reinterpret_cast<const float *>(points.data()), points.size(), v, max_range, nullptr));
+        return *this;
+    }
+    OccupancyGrid &Insert(const std::vector<Eigen::Vector3f> &points, const Eigen::Vector3f &viewpoint, float max_range = -1.0f) {
+        return Insert(utility::device_vector<Eigen::Vector3f>(points), viewpoint, max_range);
+    }
+    OccupancyGrid &Insert(const PointCloud &pointcloud, const Eigen::Vector3f &viewpoint, float max_range = -1.0f) {
+        return Insert(pointcloud.points_, viewpoint, max_range);
+    }
+    OccupancyGrid &AddVoxel(const Eigen::Vector3i &voxel, bool occupied = false) {  // occupancygrid.cu:554-577
+        sync();
+        const int32_t v[3] = {voxel[0], voxel[1], voxel[2]};
+        if (cphb_occgrid_add_voxel(h_, v, occupied ? 1 : 0, nullptr) != CPHB_OK)
+            utility::LogError("[OccupancyGrid] a provided voxeld is not occupancy grid range.");
+        return *this;
+    }
+    OccupancyGrid &AddVoxels(const utility::device_vector<Eigen::Vector3i> &voxels, bool occupied = false) {
+        sync();
+        if (voxels.size()) utility::check(cphb_occgrid_add_voxels(h_, reinterpret_cast<const int32_t *>(voxels.data()), voxels.size(), occupied ? 1 : 0, nullptr));
+        return *this;
+    }
+
+public:
+    float voxel_size_ = 0.05f;
+    size_t resolution_ = 512;
+    Eigen::Vector3f origin_ = Eigen::Vector3f(0.f, 0.f, 0.f);
+    float clamping_thres_min_ = -2.0f;
+    float clamping_thres_max_ = 3.5f;
+    float prob_hit_log_ = 0.85f;
+    float prob_miss_log_ = -0.4f;
+    float occ_prob_thres_log_ = 0.0f;
+    bool visualize_free_area_ = true;
+
+private:
+    void sync() const {  // the public members are the source of truth, like the reference's
+        const float o[3] = {origin_[0], origin_[1], origin_[2]};
+        utility::check(cphb_occgrid_set_geometry(h_, voxel_size_, o));
+        cphb_occgrid_params p = {clamping_thres_min_, clamping_thres_max_, prob_hit_log_, prob_miss_log_, occ_prob_thres_log_};
+        utility::check(cphb_occgrid_set_params(h_, &p));
+    }
+    std::shared_ptr<std::vector<OccupancyVoxel>> extract(int which) const {
+        sync();
+        size_t m = 0;
+        utility::check(cphb_occgrid_extract(h_, which, nullptr, nullptr, 0, &m, nullptr));
+        auto out = std::make_shared<std::vector<OccupancyVoxel>>(m);
+        if (!m) return out;
+        utility::device_vector<Eigen::Vector3i> idx(m);
+        utility::device_vector<float> pr(m);
+        utility::check(cphb_occgrid_extract(h_, which, reinterpret_cast<int32_t *>(idx.data()), pr.data(), m, &m, nullptr));
+        const auto hi = idx.to_host();
+        const auto hp = pr.to_host();
+        for (size_t i = 0; i < m; ++i) (*out)[i] = OccupancyVoxel(hi[i], hp[i]);
+        return out;
+    }
+    cphb_occgrid *h_ = nullptr;
 };
 }  // namespace geometry
 

@@ -315,6 +315,47 @@ int cphb_compute_fpfh_feature(const float *points, const float *normals, size_t 
 int cphb_cluster_dbscan(const float *points, size_t n, float eps, int min_points, int max_edges,
                         int32_t *labels_out, int *h_n_clusters, void *stream);
 
+/* ------------------------------------------------------------------------ *
+ * geometry::OccupancyGrid (occupancygrid.h:74-147, occupancygrid.cu): a dense
+ * resolution^3 log-odds grid.  Cells are float prob_log (NaN = unknown); voxel
+ * (x, y, z) of the grid covers origin + (x - resolution/2 .. +1) * voxel_size.
+ * ------------------------------------------------------------------------ */
+typedef struct cphb_occgrid cphb_occgrid;
+typedef struct cphb_occgrid_params { /* occupancygrid.h:139-143 (defaults -2.0, 3.5, 0.85, -0.4, 0.0) */
+    float clamping_thres_min, clamping_thres_max, prob_hit_log, prob_miss_log, occ_prob_thres_log;
+} cphb_occgrid_params;
+void cphb_occgrid_default_params(cphb_occgrid_params *p);
+/* OccupancyGrid(voxel_size, resolution = 512, origin = 0) (occupancygrid.cu:289-297); the grid owns its device memory */
+int cphb_occgrid_create(float voxel_size, int resolution, const float origin[3], void *stream, cphb_occgrid **out);
+void cphb_occgrid_destroy(cphb_occgrid *grid);
+int cphb_occgrid_clear(cphb_occgrid *grid, void *stream);                       /* Clear (:310-315) */
+int cphb_occgrid_set_params(cphb_occgrid *grid, const cphb_occgrid_params *p);  /* the public members :139-143 */
+int cphb_occgrid_set_geometry(cphb_occgrid *grid, float voxel_size, const float origin[3]); /* voxel_size_ / origin_ */
+const float *cphb_occgrid_data(const cphb_occgrid *grid);                       /* device prob_log[resolution^3], borrowed */
+int cphb_occgrid_resolution(const cphb_occgrid *grid);
+/* OccupancyGrid::Insert(points, viewpoint, max_range = -1) (occupancygrid.cu:462-526): every voxel crossed by a ray
+ * viewpoint -> point gets prob_miss_log once, every voxel holding a point within max_range gets prob_hit_log once
+ * (occupied wins), both clamped.  points: device, packed xyz. */
+int cphb_occgrid_insert(cphb_occgrid *grid, const float *points, size_t n, const float viewpoint[3], float max_range,
+                        void *stream);
+/* AddVoxels(voxels, occupied) (:579-600): device [n][3] int32 grid indices inside the grid; AddVoxel (:554-577): one
+ * host index, range-checked (CPHB_ERR_INVALID outside, where the reference logs an error). */
+int cphb_occgrid_add_voxels(cphb_occgrid *grid, const int32_t *voxels, size_t n, int occupied, void *stream);
+int cphb_occgrid_add_voxel(cphb_occgrid *grid, const int32_t voxel[3], int occupied, void *stream);
+/* SetFreeArea(min_bound, max_bound) (:415-460): adds prob_miss_log to every cell of the (clipped) box and REPLACES the
+ * grid's bound box by it, as the reference does. */
+int cphb_occgrid_set_free_area(cphb_occgrid *grid, const float min_bound[3], const float max_bound[3], void *stream);
+/* min_bound_ / max_bound_ (grid indices; GetMinBound / GetMaxBound :317-333 convert them to coordinates) */
+int cphb_occgrid_bounds(const cphb_occgrid *grid, int32_t h_min[3], int32_t h_max[3], void *stream);
+/* ExtractKnownVoxels / ExtractFreeVoxels / ExtractOccupiedVoxels (:358-408): which = 0 / 1 / 2.  Voxels of the bound
+ * box that satisfy the predicate, in box order; out_index (device [capacity][3], the voxel's stored grid_index_) and
+ * out_prob (device [capacity]) may be null; *h_count = number of matching voxels (call with capacity 0 to size). */
+int cphb_occgrid_extract(const cphb_occgrid *grid, int which, int32_t *out_index, float *out_prob, size_t capacity,
+                         size_t *h_count, void *stream);
+/* GetVoxel(point) (:351-356, densegrid.inl:137-146): *h_known = inside the grid and not NaN */
+int cphb_occgrid_get_voxel(const cphb_occgrid *grid, const float point[3], int *h_known, float *h_prob_log,
+                           int32_t h_grid_index[3], void *stream);
+
 /* registration::EvaluateRegistration (registration.cu:106-119). */
 int cphb_evaluate_registration(const cphb_cloud *source, const cphb_cloud *target,
                                float max_correspondence_distance, const float h_T[16],

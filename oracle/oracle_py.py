@@ -334,3 +334,73 @@ def registration_icp(kind, src, tgt, max_distance, init=None, src_nrm=None, src_
 def num_threads():
     return int(lib().orc_num_threads())
 
+
+
+class OccupancyGrid:
+    """geometry::OccupancyGrid (occupancygrid.h / occupancygrid.cu) restated on numpy arrays: prob[res^3] float32 (NaN =
+    unknown), has_index[res^3] uint8, bounds u16[6] = (min_bound_, max_bound_)."""
+
+    def __init__(self, voxel_size=0.05, resolution=512, origin=(0, 0, 0)):
+        self.voxel_size, self.resolution = float(voxel_size), int(resolution)
+        self.origin = np.asarray(origin, np.float32).reshape(3).copy()
+        self.clamping_thres_min, self.clamping_thres_max = -2.0, 3.5
+        self.prob_hit_log, self.prob_miss_log, self.occ_prob_thres_log = 0.85, -0.4, 0.0
+        n = self.resolution ** 3
+        self.prob = np.full(n, np.nan, np.float32)
+        self.has_index = np.zeros(n, np.uint8)
+        self._stamp = np.zeros(n, np.uint8)
+        h = self.resolution // 2
+        self.bounds = np.array([h, h, h, h, h, h], np.uint16)
+
+    def _params(self):
+        return np.array([self.clamping_thres_min, self.clamping_thres_max, self.prob_hit_log, self.prob_miss_log], np.float32)
+
+    def add_voxels(self, voxels, occupied=False):
+        v = np.ascontiguousarray(voxels, np.int32).reshape(-1, 3)
+        lib().orc_occgrid_add_voxels(_p(self.prob), _p(self.has_index), _p(self.bounds), C.c_int(self.resolution),
+                                     _p(self._params()), _p(v), C.c_int(len(v)), C.c_int(int(occupied)))
+        return self
+
+    def insert(self, points, viewpoint, max_range=-1.0):
+        pts = _f(points).reshape(-1, 3)
+        vp = np.asarray(viewpoint, np.float32).reshape(3)
+        lib().orc_occgrid_insert(_p(self.prob), _p(self.has_index), _p(self._stamp), _p(self.bounds), C.c_int(self.resolution),
+                                 C.c_float(self.voxel_size), _p(self.origin), _p(self._params()), _p(pts), C.c_int(len(pts)),
+                                 _p(vp), C.c_float(max_range))
+        return self
+
+    def set_free_area(self, min_bound, max_bound):
+        lo, hi = np.asarray(min_bound, np.float32).reshape(3), np.asarray(max_bound, np.float32).reshape(3)
+        lib().orc_occgrid_set_free_area(_p(self.prob), _p(self.bounds), C.c_int(self.resolution), C.c_float(self.voxel_size),
+                                        _p(self.origin), C.c_float(self.prob_miss_log), _p(lo), _p(hi))
+        return self
+
+    def extract(self, which):
+        """which: 0 known, 1 free, 2 occupied -> (grid_index [m,3] int32, prob_log [m])"""
+        b = self.bounds.astype(np.int64)
+        cap = int(np.prod(b[3:] - b[:3] + 1))
+        idx, pr = np.empty((max(cap, 1), 3), np.int32), np.empty(max(cap, 1), np.float32)
+        lib().orc_occgrid_extract.restype = C.c_int
+        m = lib().orc_occgrid_extract(_p(self.prob), _p(self.has_index), _p(self.bounds), C.c_int(self.resolution),
+                                      C.c_float(self.occ_prob_thres_log), C.c_int(which), _p(idx), _p(pr))
+        return idx[:m].copy(), pr[:m].copy()
+
+    def voxel_index(self, point):
+        lib().orc_occgrid_voxel_index.restype = C.c_long
+        return int(lib().orc_occgrid_voxel_index(C.c_int(self.resolution), C.c_float(self.voxel_size), _p(self.origin),
+                                                 _p(np.asarray(point, np.float32).reshape(3))))
+
+    def get_voxel(self, point):
+        """-> (known, prob_log)"""
+        i = self.voxel_index(point)
+        if i < 0:
+            return False, float("nan")
+        return bool(not np.isnan(self.prob[i])), float(self.prob[i])
+
+    def get_min_bound(self):
+        h = self.resolution // 2
+        return ((self.bounds[:3].astype(np.int32) - h).astype(np.float32) * np.float32(self.voxel_size) + self.origin).astype(np.float32)
+
+    def get_max_bound(self):
+        h = self.resolution // 2
+        return ((self.bounds[3:].astype(np.int32) - (h - 1)).astype(np.float32) * np.float32(self.voxel_size) + self.origin).astype(np.float32)

@@ -3,6 +3,7 @@
 //   tests/geometry/pointcloud.cpp:676-693  PointCloud.RemoveRadiusOutliers
 //   tests/geometry/pointcloud.cpp:303-334  PointCloud.SelectByIndex
 //   tests/geometry/voxelgrid.cpp:40-68     VoxelGrid.GetVoxel, VoxelGrid.CreateFromPointCloudWithinBounds
+//   tests/geometry/occupancygrid.cpp:30-97 OccupancyGrid.Bounds, .GetVoxel, .Insert, .SetFreeArea
 // plus RemoveStatisticalOutliers on a cloud with planted outliers.  Exit code 0 = all expectations met.
 #include <algorithm>
 #include <cmath>
@@ -92,6 +93,31 @@ int main() {
         if (kv.first.size() == 1) EXPECT(kv.first[0][0] == 100 && kv.second[0].color_[0] == 1.0f);
         auto grid2 = geometry::VoxelGrid::CreateFromPointCloud(pc, 0.5f);
         EXPECT(grid2->voxels_keys_.size() == 1 && grid2->HasVoxels());
+    }
+    {   // OccupancyGrid: the reference's known-answer tests (tests/geometry/occupancygrid.cpp:30-97)
+        geometry::OccupancyGrid og;
+        EXPECT(std::fabs(og.voxel_size_ - 0.05f) < 1e-7f && og.resolution_ == 512);
+        og.voxel_size_ = 5;
+        og.AddVoxel(Eigen::Vector3i(0, 0, 0));
+        og.AddVoxel(Eigen::Vector3i(511, 511, 511));
+        EXPECT(og.GetMinBound()[0] == -512 * 5 * 0.5f && og.GetMaxBound()[2] == 512 * 5 * 0.5f);
+        geometry::OccupancyGrid g2;
+        g2.voxel_size_ = 1.0f;
+        g2.AddVoxel(Eigen::Vector3i(257, 256, 256), true);
+        g2.AddVoxel(Eigen::Vector3i(257, 256, 256), true);
+        g2.AddVoxel(Eigen::Vector3i(257, 256, 256), false);
+        auto r = g2.GetVoxel(Eigen::Vector3f(1.5f, 0.0f, 0.0f));
+        EXPECT(std::get<0>(r) && std::fabs(std::get<1>(r).prob_log_ - (2.0f * g2.prob_hit_log_ + g2.prob_miss_log_)) < 1e-6f);
+        geometry::OccupancyGrid g3;
+        g3.origin_ = Eigen::Vector3f(-0.5f, -0.5f, 0);
+        g3.voxel_size_ = 1.0f;
+        g3.Insert(std::vector<Eigen::Vector3f>{Eigen::Vector3f(0.0f, 0.0f, 3.5f)}, Eigen::Vector3f(0, 0, 0));
+        EXPECT(g3.ExtractKnownVoxels()->size() == 4);
+        EXPECT(std::get<0>(g3.GetVoxel(Eigen::Vector3f(0, 0, 0.5f))) && std::get<0>(g3.GetVoxel(Eigen::Vector3f(0, 0, 3.5f))));
+        EXPECT(!std::get<0>(g3.GetVoxel(Eigen::Vector3f(0, 0, 4.5f))) && g3.IsOccupied(Eigen::Vector3f(0, 0, 3.5f)));
+        geometry::OccupancyGrid g4;
+        g4.SetFreeArea(Eigen::Vector3f(0, 0, 0), Eigen::Vector3f(0.1f, 0.1f, 0.1f));
+        EXPECT(g4.ExtractFreeVoxels()->size() == 27);
     }
     {   // DBSCAN, FPFH, KabschWeighted: two well separated blobs of 60 points each
         std::vector<Eigen::Vector3f> pts, nrm;
