@@ -814,7 +814,10 @@ __device__ void icp_static_tail(const IcpArgs &a, IcpState *st, double (*s_rowbu
             st->cert_tiles = 0;
             st->tail_done = a.launch_idx + 1;
         }
-        if (!a.defer_finalize) icp_finalize<KIND>(a, st, s_solve);
+    }
+    __syncthreads();  // the sums are staged: warp 1 takes the determinant while warp 0 solves (icp_finalize<KIND, true>)
+    if (!a.defer_finalize) icp_finalize<KIND, true>(a, st, s_solve);
+    if (warp == 0) {
         __threadfence();
         if (lane == 0) dbg_time(a, 4, false);
     }
@@ -903,9 +906,11 @@ __device__ void icp_reduce_body(const IcpArgs &a, double (*s_acc)[32], unsigned 
             st->static_sched = ((unsigned long long)st->cert_tiles * 10ull >= (unsigned long long)n_tiles * 9ull) ? 1 : 0;
             st->cert_tiles = 0;
         }
-        if (!a.defer_finalize) icp_finalize<KIND>(a, st, s_solve);
-        __threadfence();
     }
+    static_assert(WARPS >= 2, "icp_finalize<KIND, true> needs a second warp");
+    __syncthreads();
+    if (!a.defer_finalize) icp_finalize<KIND, true>(a, st, s_solve);
+    if (threadIdx.x < 32) __threadfence();
 }
 
 // multi-GPU: runs after the all-reduce of st->local into st->total

@@ -146,22 +146,25 @@ __device__ void se3_exp(const float *x, float *T) {  // eigen.cu:28-50
     T[9] = w0 * s + w1 * w2 * oc;
     T[10] = c + w2 * w2 * oc;
 }
-__device__ bool solve_jtj(const double *S, float det_thresh, float *T) {
-    float A[36], b[6], x[6];
-    {
-        int p = 0;
+// the normal equations of the 32 sums: A (symmetric 6x6) and b = -JTr
+__device__ __forceinline__ void jtj_system(const double *S, float (&A)[36], float (&b)[6]) {
+    int p = 0;
 #pragma unroll
-        for (int a = 0; a < 6; ++a)
+    for (int a = 0; a < 6; ++a)
 #pragma unroll
-            for (int c = a; c < 6; ++c) { float v = (float)S[p++]; A[6 * a + c] = v; A[6 * c + a] = v; }
-    }
+        for (int c = a; c < 6; ++c) { float v = (float)S[p++]; A[6 * a + c] = v; A[6 * c + a] = v; }
 #pragma unroll
     for (int a = 0; a < 6; ++a) b[a] = -(float)S[21 + a];
+}
+// eigen.cu:88-100: the update is rejected (identity) when |det| < det_thresh or det is not finite
+__device__ __forceinline__ bool det_accepts(float det, float det_thresh) {
+    return !(fabsf(det) < det_thresh || isnan(det) || isinf(det));
+}
+__device__ bool solve_jtj(const double *S, float det_thresh, float *T) {
+    float A[36], b[6], x[6];
+    jtj_system(S, A, b);
     identity4(T);
-    if (det_thresh > 0) {  // eigen.cu:88-100
-        float det = det6_partial_piv(A);
-        if (fabsf(det) < det_thresh || isnan(det) || isinf(det)) return false;
-    }
+    if (det_thresh > 0 && !det_accepts(det6_partial_piv(A), det_thresh)) return false;
     ldlt6_solve(A, b, x);
     se3_exp(x, T);
     return true;
@@ -169,6 +172,7 @@ __device__ bool solve_jtj(const double *S, float det_thresh, float *T) {
 struct SolveSmem {
     float T[16];
     double S[32];  // the iteration's 32 sums, staged for the solving lane
+    float det;     // icp_finalize<KIND, true>: the determinant, computed by a second warp while the first one solves
 };
 
 __device__ void matmul4(const float *A, const float *B, float *C) {  // registration.cu:159
@@ -257,12 +261,30 @@ __device__ void kabsch_from_sums(const double *S, unsigned long long n_model, fl
     }
 }
 
-// registration.cu:71-78,154-172 -- runs in ONE WARP (all 32 lanes call it) after the grid-wide sum.
-// S = m.S: the 32 sums of this iteration, staged in shared memory by the caller (also in st->total for the host)
-template <int KIND>
+// registration.cu:71-78,154-172 -- after the grid-wide sum.
+// S = m.S: the 32 sums of this iteration, staged in shared memory by the caller (also in st->total for the host).
+// PAR = false: runs in ONE WARP (all 32 lanes call it).
+// PAR = true : called by EVERY warp of a block of >= 2 warps, after a __syncthreads that made m.S visible.  The 6x6
+//              determinant (partial-pivot LU) and the LDLT solve are independent chains of ~2.5 us each on one lane:
+//              warp 1 computes the determinant while warp 0 solves; one __syncthreads joins them.  Same operations,
+//              same results.
+template <int KIND, bool PAR = false>
 __device__ void icp_finalize(const IcpArgs &a, IcpState *st, SolveSmem &m) {
     const int lane = lane_id();
     const double *S = m.S;
+    if (PAR) {
+        const int warp = threadIdx.x >> 5;
+        constexpr bool uses_det = (KIND != CPHB_EST_POINT_TO_POINT && KIND != CPHB_EST_GENERALIZED_ICP);
+        if (warp == 1 && lane == 0 && uses_det && a.det_thresh > 0) {
+            float A[36], b[6];
+            jtj_system(S, A, b);
+            m.det = det6_partial_piv(A);
+        }
+        if (warp != 0) {
+            __syncthreads();
+            return;
+        }
+    }
     int action = 0;  // 0 = nothing more, 1 = compute an update
     double cnt = 0.0;
     if (lane == 0) {
@@ -289,7 +311,11 @@ __device__ void icp_finalize(const IcpArgs &a, IcpState *st, SolveSmem &m) {
     }
     action = __shfl_sync(CPHB_FULL, action, 0);
     if (lane == 0) dbg_time(a, 5, false);
-    if (!action) return;
+    bool joined = false;  // PAR: warp 0 meets the other warps at exactly one __syncthreads on every (warp-uniform) path
+    if (!action) {
+        if (PAR) __syncthreads();
+        return;
+    }
     const bool have_corr = __shfl_sync(CPHB_FULL, (int)(cnt > 0), 0) != 0;
     if (lane == 0) identity4(m.T);
     __syncwarp();
@@ -308,7 +334,20 @@ __device__ void icp_finalize(const IcpArgs &a, IcpState *st, SolveSmem &m) {
                 // one lane, everything in registers (the warp-parallel shared-memory version this replaces spent 7.4 us
                 // of a 60 us certified launch in __syncwarp-separated steps)
                 bool ok = true;
-                if (lane == 0) {
+                if (PAR) {
+                    if (lane == 0) {  // solve first, learn the determinant afterwards (it only decides accept / reject)
+                        float A[36], b[6], x[6];
+                        jtj_system(S, A, b);
+                        ldlt6_solve(A, b, x);
+                        se3_exp(x, m.T);
+                    }
+                    __syncthreads();
+                    joined = true;
+                    if (lane == 0) {
+                        if (dt > 0 && !det_accepts(m.det, dt)) ok = false;
+                        dbg_time(a, 6, false);
+                    }
+                } else if (lane == 0) {
                     ok = solve_jtj(S, dt, m.T);
                     dbg_time(a, 6, false);
                 }
@@ -328,6 +367,7 @@ __device__ void icp_finalize(const IcpArgs &a, IcpState *st, SolveSmem &m) {
             }
         }
     }
+    if (PAR && !joined) __syncthreads();
     // transformation = update * transformation (registration.cu:159): one output element per lane
     float tn = 0.f;
     if (lane < 16) {
