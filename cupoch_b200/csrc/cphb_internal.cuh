@@ -101,6 +101,9 @@ int cphb_compact_flags(const uint8_t *keep, size_t n, int32_t *indices_out, size
 // queries and targets share one curve).
 int cphb_hilbert_order(const float *xyz, size_t n, uint32_t *perm_out /*device n*/,
                        float *bounds_dev6 /*or NULL*/, int bounds_given, cudaStream_t s);
+// same, with the curve resolution chosen for n_ref points (query ordering: n_ref = size of the indexed cloud)
+int cphb_hilbert_order_n(const float *xyz, size_t n, uint32_t *perm_out, float *bounds_dev6, int bounds_given,
+                         size_t n_ref, cudaStream_t s);
 
 // ---------------------------------------------------------------------------
 // communicator for the sharded ICP (comm.cu)

@@ -139,7 +139,7 @@ static int launch_normals_fused(const cphb_index *ix, const float *points, size_
     if (!self_order && count > 32) {
         rc = cphb_alloc_async((void **)&perm, sizeof(uint32_t) * count, s);
         if (rc) return rc;
-        rc = cphb_hilbert_order(points + 3 * first, count, perm, ix->bounds, 1, s);
+        rc = cphb_hilbert_order_n(points + 3 * first, count, perm, ix->bounds, 1, count < n ? count : n, s);
         if (rc) { cphb_free_async(perm, s); return rc; }
     }
     const size_t per_warp = 2 * CPHB_LEAF * sizeof(float4) + 2 * sizeof(uint64_t) + (size_t)k * 32 * sizeof(unsigned long long);

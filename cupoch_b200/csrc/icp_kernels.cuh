@@ -36,6 +36,39 @@ __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_gr
 #define ICP_GD 2
 #endif
 #define ICP_NS (2 * ICP_GD)
+// Certified regime: the normal-equation sums of a tile on the FP64 tensor cores.  The 30 products a tile contributes per
+// row are entries of the Gram matrix of the 32 x 8 matrix V = (J0..J5, r, one): eight DMMA.8x8x4 (A = V^T, B = V, four
+// points per step; for a Gram matrix both fragments hold the SAME value per lane) accumulate it in a 2-register
+// fragment per lane -- instead of 30 float64 accumulators (60 registers) per lane and a 30-column warp reduction at
+// the end.  Products of two floats are exact in float64 and every accumulation step rounds once, exactly as DFMA does;
+// only the (fixed) order of the additions differs.  -DICP_DMMA=0 restores the per-lane DFMA accumulators.
+#ifndef ICP_DMMA
+#define ICP_DMMA 1
+#endif
+// float -> double.  F2F.F64.F32 runs on the XU pipe (shared with MUFU), which ncu shows as the busiest unit of a certified
+// launch (44 %) for nine conversions per row; the widening is exact, so it can also be done on the integer pipes (re-bias
+// the exponent, shift the mantissa by 29 bits; zero keeps its sign; denormals / inf / NaN take the hardware path).
+// Measured: the integer form is SLOWER (9365 vs 9570 it/s, A/B in profiles/r2_ab_f2d.txt) -- the XU pipe is busy but not
+// the limiter -- so the hardware conversion stays the default; -DICP_F2D_INT=1 selects the integer form.
+#ifndef ICP_F2D_INT
+#define ICP_F2D_INT 0
+#endif
+__device__ __forceinline__ double f2d(float f) {
+#if ICP_F2D_INT
+    const unsigned u = __float_as_uint(f);
+    const unsigned a = u & 0x7fffffffu;
+    if (a - 0x00800000u >= 0x7f000000u) {  // a < 2^-126 (zero, denormal) or a >= inf
+        if (a == 0u) return __hiloint2double((int)u, 0);
+        return (double)f;
+    }
+    return __hiloint2double((int)((u & 0x80000000u) | ((a >> 3) + 0x38000000u)), (int)(u << 29));
+#else
+    return (double)f;
+#endif
+}
+__device__ __forceinline__ void dmma_8x8x4(double &c0, double &c1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
 // pull the rows of target position p that a tile reads first into L1 (no register is tied up, nothing waits)
 template <int KIND>
 __device__ __forceinline__ void prefetch_target(const IcpArgs &a, size_t p) {
@@ -46,6 +79,9 @@ __device__ __forceinline__ void prefetch_target(const IcpArgs &a, size_t p) {
     if (KIND == CPHB_EST_GENERALIZED_ICP && a.tgt_cov) prefetch_l1(a.tgt_cov + 3 * p);  // 48 B: one or two sectors
 }
 
+#ifndef ICP_DMMA
+#define ICP_DMMA 1  // certified regime: normal-equation sums on the FP64 tensor cores (see dmma_8x8x4 below)
+#endif
 #define ICP_SEARCH_WARPS 4
 // Two instances of the kernel, launched back to back every iteration (the regime is decided on the DEVICE, so each
 // instance checks the state and the one whose regime is not current leaves at once):
@@ -55,7 +91,11 @@ __device__ __forceinline__ void prefetch_target(const IcpArgs &a, size_t p) {
 //   ROLE 1  certified regime (needs the registers: 30 float64 accumulators per lane) -- and, when the launch before it
 //           searched, the fixed-order sum of its tile sums + solve (what used to be a third kernel, icp_reduce_kernel).
 #ifndef ICP_MIN_BLOCKS
-#define ICP_MIN_BLOCKS 4  // ROLE 1: resident blocks / SM the register allocation targets (128 registers: 16 warps / SM)
+// ROLE 1: 4 blocks = 16 warps / SM.  The tensor-core accumulation would allow 24-32 warps (80-64 registers), but more
+// resident blocks make the certified launch SLOWER (A/B profiles/r2_ab_dmma_occupancy.txt: 4 / 5 / 6 / 7 / 8 blocks per SM
+// -> 9590 / 9300 / 9100 / 8970 / 8570 it/s): its SM throughput saturates near 16 warps and every extra block adds launch,
+// pipeline-fill and grid-sum work.
+#define ICP_MIN_BLOCKS 4
 #endif
 #ifndef ICP_MIN_BLOCKS_SEARCH
 #define ICP_MIN_BLOCKS_SEARCH 5  // ROLE 0 (96 registers: 20 warps / SM; A/B of 4 / 5 / 6 / 8 in profiles/r2_ab_search_occupancy.txt)
@@ -396,9 +436,9 @@ __device__ __forceinline__ bool search_tile(const IcpArgs &a, const LaunchCtx &c
     for (int q = 0; q < NROWS; ++q) {
         double *my = rows + lane * ROW_STRIDE;
 #pragma unroll
-        for (int k = 0; k < 6; ++k) my[k] = (double)J[q][k];
-        my[6] = (double)r[q];
-        my[7] = (q == 0 && found) ? (double)d2 : 0.0;
+        for (int k = 0; k < 6; ++k) my[k] = f2d(J[q][k]);
+        my[6] = f2d(r[q]);
+        my[7] = (q == 0 && found) ? f2d(d2) : 0.0;
         my[8] = (q == 0 && found) ? 1.0 : 0.0;
         __syncwarp();
 #pragma unroll 8
@@ -535,9 +575,15 @@ icp_iteration_kernel(const __grid_constant__ IcpArgs a) {
             return;
         }
         // ---- main role ----
+#if ICP_DMMA
+        double gc0 = 0.0, gc1 = 0.0;  // this lane's two elements of the warp's 8 x 8 Gram fragment: G[lane/4][2 (lane%4) + {0,1}]
+        double d2acc = 0.0;           // this lane's sum of d2 (not an entry of the Gram matrix of V)
+        float *stage = reinterpret_cast<float *>(s_rows[warp]);  // [32 points][8] floats (the searching code's row buffer, idle here)
+#else
         double lacc[32];
 #pragma unroll
         for (int p = 0; p < 32; ++p) lacc[p] = 0.0;
+#endif
         double wrow = 0.0;  // lane p: column p of what this warp has folded so far
         unsigned n_skipped = 0;
         bool searched_inline = false;
@@ -631,6 +677,21 @@ icp_iteration_kernel(const __grid_constant__ IcpArgs a) {
             lane_rows_vals<KIND, NROWS>(a, found, tv, s, sn, Cs, i, J, r);
             // this lane's own rows, every product into its own float64 accumulator (exact products, one rounding per
             // addition); the warp-wide reduction happens once, after the last tile
+#if ICP_DMMA
+#pragma unroll
+            for (int q = 0; q < NROWS; ++q) {
+                __syncwarp();  // every lane has read the previous row's stage
+                *reinterpret_cast<float4 *>(stage + lane * 8) = make_float4(J[q][0], J[q][1], J[q][2], J[q][3]);
+                *reinterpret_cast<float4 *>(stage + lane * 8 + 4) = make_float4(J[q][4], J[q][5], r[q], (q == 0 && found) ? 1.f : 0.f);
+                __syncwarp();
+#pragma unroll
+                for (int m4 = 0; m4 < 8; ++m4) {  // points 4 m4 .. 4 m4 + 3; lane: V[point 4 m4 + lane % 4][column lane / 4] (conflict-free)
+                    const double x = f2d(stage[(4 * m4 + (lane & 3)) * 8 + (lane >> 2)]);
+                    dmma_8x8x4(gc0, gc1, x, x);
+                }
+            }
+            if (found) d2acc += f2d(d2);
+#else
 #pragma unroll
             for (int q = 0; q < NROWS; ++q) {
                 const double v[9] = {(double)J[q][0], (double)J[q][1], (double)J[q][2], (double)J[q][3], (double)J[q][4],
@@ -641,11 +702,13 @@ icp_iteration_kernel(const __grid_constant__ IcpArgs a) {
                     if (pair_live(P2P, p))
                         lacc[p] = fma(v[P2P ? pair_p2p_a(p) : pair_jtj_a(p)], v[P2P ? pair_p2p_b(p) : pair_jtj_b(p)], lacc[p]);
             }
+#endif
         }
         if (!cold) break;
         // ---- cold: tile `tile` needs its search.  The accumulators are folded into the warp's running row first, so
         // they are dead while the search runs; then the hot loop resumes with the next tile.
         if (lane == 0) atomicOr(&flag_next[tile >> 5], 1u << (tile & 31));
+#if !ICP_DMMA
         if (!c.materialize) {
 #pragma unroll
             for (int p = 0; p < 32; ++p) {
@@ -656,14 +719,19 @@ icp_iteration_kernel(const __grid_constant__ IcpArgs a) {
                 if (lane == p) wrow += t;
             }
         }
-        {
+#endif
+        {   // (the Gram fragment is three registers: it simply stays live across the search)
             double acc;
+            __syncwarp();
             search_tile<KIND, TOP>(a, c, w, s_rows[warp], tile, cold_s, cold_pv, acc);
             searched_inline = true;
             wrow += acc;
+            __syncwarp();
         }
+#if !ICP_DMMA
 #pragma unroll
         for (int p = 0; p < 32; ++p) lacc[p] = 0.0;
+#endif
         if (a.dbg && lane == 0) atomicAdd(&a.dbg[128 + min(a.launch_idx, 63)], 1u);
         tile += main_warps;
         }
@@ -671,6 +739,30 @@ icp_iteration_kernel(const __grid_constant__ IcpArgs a) {
         if (lane == 0) { dbg_time(a, 1, false); dbg_time(a, searched_inline ? 9 : 8, false); }
         // warp reduction (xor butterfly: the same bits on every lane), lane p keeps column p
         double row = wrow;
+#if ICP_DMMA
+        if (!c.materialize) {
+            // the fragment IS the warp's sum: lay the 8 x 8 matrix out in shared memory and let lane p pick the entry
+            // of its column pair (JTJ kinds: columns 0..6 = J0..J5, r; 7 = one.  P2P: 0..5 = s, t; 7 = one)
+            double *gm = s_rows[warp];  // [8][8]
+            __syncwarp();
+            gm[(lane >> 2) * 8 + 2 * (lane & 3)] = gc0;
+            gm[(lane >> 2) * 8 + 2 * (lane & 3) + 1] = gc1;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) d2acc += __shfl_xor_sync(CPHB_FULL, d2acc, o);
+            __syncwarp();
+            const unsigned char(*pair)[2] = P2P ? c_pair_p2p : c_pair_jtj;
+            int ga = pair[lane][0], gb = pair[lane][1];
+            // the tables name 9 values (.., d2 = 7, one = 8); here 'one' is column 7 and sum d2 is carried separately
+            double g = 0.0;
+            if (ga == 7 && gb == 8) g = d2acc;  // (d2, one)
+            else {
+                ga = (ga == 8) ? 7 : ga;
+                gb = (gb == 8) ? 7 : gb;
+                g = gm[ga * 8 + gb];
+            }
+            if (pair_live(P2P, lane)) row += g;
+        }
+#else
         if (!c.materialize) {
 #pragma unroll
             for (int p = 0; p < 32; ++p) {
@@ -681,6 +773,7 @@ icp_iteration_kernel(const __grid_constant__ IcpArgs a) {
                 if (lane == p) row += t;
             }
         }
+#endif
         icp_static_tail<KIND>(a, st, (double(*)[32])s_pipe, s_solve, &s_flag, row, c.materialize, n_skipped);
         return;
     } else {
@@ -762,7 +855,12 @@ __device__ void icp_static_tail(const IcpArgs &a, IcpState *st, double (*s_rowbu
     __syncthreads();
     if (!*s_flag) return;
     __threadfence();
-    if (threadIdx.x == 0) dbg_time(a, 2, false);
+    if (threadIdx.x == 0) {
+        dbg_time(a, 2, false);
+        // the state the epilogue reads after the grid sum (previous fitness / rmse, pose): have it in L1 by then
+        prefetch_l1(&st->T[0]);
+        prefetch_l1(&st->fitness);
+    }
     const unsigned n_tiles = a.n_pad / 32;
     {   // every block has finished reading this launch's flag bitmap: clear it (it collects the flags of the launch after
         // next) and make the one written during this launch current
@@ -876,6 +974,10 @@ __device__ void icp_reduce_body(const IcpArgs &a, double (*s_acc)[32], unsigned 
     __syncthreads();
     if (!*s_last) return;
     __threadfence();
+    if (threadIdx.x == 0) {
+        prefetch_l1(&st->T[0]);
+        prefetch_l1(&st->fitness);
+    }
     for (int g = warp; g < GROUPS; g += WARPS) {  // the grid sum (fixed order: row groups of 8, then the 8 group sums)
         double t = 0.0;
         for (unsigned b = g; b < a.reduce_grid; b += 8 * GROUPS) {

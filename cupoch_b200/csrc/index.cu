@@ -465,6 +465,13 @@ __global__ void __launch_bounds__(256) upper_box_kernel(const Box *__restrict__ 
 // ---------------------------------------------------------------------------
 int cphb_hilbert_order(const float *xyz, size_t n, uint32_t *perm_out, float *bounds_dev6, int bounds_given,
                        cudaStream_t s) {
+    return cphb_hilbert_order_n(xyz, n, perm_out, bounds_dev6, bounds_given, n, s);
+}
+// resolution of the curve chosen for `n_ref` points instead of n: queries are ordered only to make every warp's 32
+// queries a compact cluster RELATIVE TO THE TARGET'S LEAVES, so the target's size decides how fine the curve has to be
+// (10 M queries against 2 M targets: 24-bit keys = 3 radix passes instead of 4)
+int cphb_hilbert_order_n(const float *xyz, size_t n, uint32_t *perm_out, float *bounds_dev6, int bounds_given,
+                         size_t n_ref, cudaStream_t s) {
     if (n == 0) return CPHB_OK;
     unsigned *b = (unsigned *)bounds_dev6;
     if (!b) bounds_given = 0;
@@ -489,7 +496,7 @@ int cphb_hilbert_order(const float *xyz, size_t n, uint32_t *perm_out, float *bo
     // cluster (every search is exact whatever the order; groups of 1024 are kd-refined afterwards), equal keys keep their
     // original order (stable sort).  CPHB_HILBERT_LEVELS overrides (tuning hook).
     int levels = 1;
-    while (levels < 10 && ((size_t)1 << (3 * levels)) < n) ++levels;
+    while (levels < 10 && ((size_t)1 << (3 * levels)) < (n_ref ? n_ref : n)) ++levels;
     levels = levels + 1 > 10 ? 10 : levels + 1;
     if (levels < 4) levels = 4;
     if (const char *e = getenv("CPHB_HILBERT_LEVELS")) { int v = atoi(e); if (v >= 1 && v <= 10) levels = v; }

@@ -120,7 +120,7 @@ static int search_impl(const cphb_index *index, const float *query, size_t nq, f
     if (nq > 32) {
         rc = cphb_alloc_async((void **)&perm, sizeof(uint32_t) * nq, s);
         if (rc) return rc;
-        rc = cphb_hilbert_order(query, nq, perm, index->bounds, 1, s);
+        rc = cphb_hilbert_order_n(query, nq, perm, index->bounds, 1, nq < index->v.n ? nq : (size_t)index->v.n, s);
         if (rc) { cphb_free_async(perm, s); return rc; }
     }
     if (h_count) {

@@ -21,6 +21,7 @@ def main():
     ap.add_argument("--radius", type=float, default=0.05)
     ap.add_argument("--reps", type=int, default=5)
     ap.add_argument("--attrs", default="p", help="p | pn | pnc")
+    ap.add_argument("--normals", type=int, default=0, help="also time EstimateNormals(KNN k) of the 10 M cloud (fused kernel, and the two-pass form)")
     ap.add_argument("--filters", action="store_true",
                     help="also time the SURVEY 8f rows: RemoveRadiusOutliers / RemoveStatisticalOutliers / VoxelGrid")
     args = ap.parse_args()
@@ -84,6 +85,20 @@ def main():
     s_med, s_min, (cnt2, idx2, _) = timed(lambda: self_tree.search_radius(pc.points, args.radius, 1), max(2, args.reps // 2))
     props["self_query_identity"] = bool((idx2.cpu()[:, 0] == np.arange(n)).mean() > 0.9999)
     extra = {}
+    if args.normals:
+        # EstimateNormals in one kernel (search + cumulants + eigen-solve) vs search -> [n][k] table -> kernel
+        param = cph.geometry.KDTreeSearchParamKNN(args.normals)
+        pc.estimate_normals(param)
+        f_med, f_min, _ = timed(lambda: pc.estimate_normals(param), max(2, args.reps // 2))
+        fused = pc.normals.cpu()
+        os.environ["CPHB_NORMALS_UNFUSED"] = "1"
+        pc.estimate_normals(param)
+        u_med, u_min, _ = timed(lambda: pc.estimate_normals(param), max(2, args.reps // 2))
+        two = pc.normals.cpu()
+        del os.environ["CPHB_NORMALS_UNFUSED"]
+        extra["estimate_normals"] = {"knn": args.normals, "fused_ms_median": f_med, "two_pass_ms_median": u_med,
+                                     "table_bytes_not_written_and_reread": int(2 * 8 * args.normals * n),
+                                     "fused_equals_two_pass_bit_for_bit": bool(np.array_equal(fused, two))}
     if args.filters:
         # SURVEY 8f rows on the same 10 M cloud: size-independent properties instead of an oracle run
         VG = cph.geometry.VoxelGrid

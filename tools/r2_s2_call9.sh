@@ -1,0 +1,7 @@
+#!/bin/bash
+mkdir -p gpurun_out
+T=${TAG:-s2c9}
+timeout 600 python -m pytest tests/test_gpu_icp.py tests/test_gpu_zz_certificates.py tests/test_gpu_baseline_sizes.py::test_config2_p2plane_1m_vs_oracle tests/test_gpu_baseline_sizes.py::test_config4_gicp_1m_vs_oracle tests/test_gpu_baseline_sizes.py::test_config5_colored_pyramid_2m_vs_oracle -m gpu -q -x --timeout 300 --timeout-method=thread 2>&1 | tail -2
+b() { env "$@" timeout 100 python bench.py --steps 8 --warmup 3 --no-cpu --no-extras 2>/dev/null | tail -1 | python -c "import json,sys; d=json.loads(sys.stdin.read()); print('$*', 'value', round(d['value']), 'loop', round(d['loop']['iters_per_sec']), 'e2e', round(d['e2e']['value']), d['step_ms'])"; }
+b X=1; b X=1
+CPHB_DEBUG_EVENTS=1 CPHB_DEBUG_CERT=1 timeout 120 python tools/one_registration.py --warm 1 2>&1 | grep -E "tile loops|timeline" | tail -2 | cut -c1-400
