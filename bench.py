@@ -16,9 +16,11 @@ ICPConvergenceCriteria(0, 0, 30): exactly 30 updates / 31 searches per registrat
   cpu_baseline    = the CPU oracle port (kd-tree + OpenMP, all host cores) on the same workload
   --impl reference= that CPU implementation timed as its own arm
 
-N > 1 (torchrun): the source is split into contiguous blocks, one per rank, the target and its
-index are replicated, and the 32 partial sums are all-reduced (NCCL) once per iteration: strong
-scaling of the same 1M -> 1M problem.
+N > 1 (torchrun): the source is split into contiguous blocks of its Hilbert order, one per rank, the
+target and its index are replicated, and the 32 partial sums are exchanged once per iteration (peer-
+memory mailboxes over NVLink fused into the launch's tail; --comm nccl for ncclAllReduce): strong
+scaling of the same 1M -> 1M problem.  Sub-records: certificates_off and config3 (N = 1), config4
+(Generalized ICP 5M -> 5M, the configuration BASELINE names for 8 GPUs) at every N.
 """
 import argparse
 import ctypes as C
