@@ -134,7 +134,10 @@ int cphb_nccl_allreduce_f64(void *nccl_comm, const double *send, double *recv, s
 // this rank's device memory (every rank executes the same sequence of exchanges, so the counters agree);
 // its parity selects one of two slot sets, which is what makes back-to-back exchanges safe: a peer can be
 // at most one exchange ahead.
-__device__ __forceinline__ double p2p_exchange_sum(const P2pView &v, double mine) {
+// The wait is bounded (~2 s of SM clock): if a peer never arrives -- its process died, or a one-sided host error kept
+// it from launching -- the warp stops waiting, raises *timed_out (when given) and returns what it has, so the GPU is
+// released instead of spinning for ever; the host turns the flag into an error (cphb_icp_run).
+__device__ __forceinline__ double p2p_exchange_sum(const P2pView &v, double mine, unsigned *timed_out = nullptr) {
     const int c = threadIdx.x & 31;
     unsigned long long *ctr = (unsigned long long *)(v.box[v.rank] + CPHB_P2P_BOX_BYTES);
     const unsigned long long epoch = *(volatile unsigned long long *)ctr + 1ull;
@@ -153,7 +156,12 @@ __device__ __forceinline__ double p2p_exchange_sum(const P2pView &v, double mine
         *f = epoch;  // lane c raises this rank's flag in peer c's mailbox
         volatile unsigned long long *mine_f =
             (volatile unsigned long long *)(v.box[v.rank] + CPHB_P2P_DATA_BYTES) + (size_t)par * CPHB_P2P_MAX_WORLD + c;
+        const long long t0 = clock64();
         while (*mine_f < epoch) {
+            if (clock64() - t0 > 4000000000ll) {
+                if (timed_out) atomicExch(timed_out, 1u);
+                break;
+            }
         }
     }
     __syncwarp();

@@ -540,6 +540,22 @@ extern "C" int cphb_icp_run(cphb_icp *icp, const float h_init[16], cphb_comm *co
     const bool lib_sharded = icp->prm.shard_world > 1;
     if (lib_sharded) n_total = icp->n_full;
     void *nccl_comm = nullptr;
+    if (comm && comm->world > 1) {
+        // a communicator that cannot exchange would fault (null mailboxes) or hang every peer's GPU: refuse it here
+        if (comm->kind == CPHB_COMM_P2P && !comm->connected) {
+            cphb_set_error("cphb_icp_run: peer-memory communicator is not connected (cphb_comm_p2p_connect)");
+            return CPHB_ERR_INVALID;
+        }
+        if (comm->kind == CPHB_COMM_NCCL && !comm->nccl) {
+            cphb_set_error("cphb_icp_run: NCCL communicator is not initialised");
+            return CPHB_ERR_INVALID;
+        }
+        if (lib_sharded && (comm->world != icp->prm.shard_world || comm->rank != icp->prm.shard_rank)) {
+            cphb_set_error("cphb_icp_run: communicator is rank %d of %d but the context was created as shard %d of %d", comm->rank,
+                           comm->world, icp->prm.shard_rank, icp->prm.shard_world);
+            return CPHB_ERR_INVALID;
+        }
+    }
     if (comm && comm->world > 1 && lib_sharded) {
         if (comm->kind == CPHB_COMM_NCCL) {
             nccl_comm = comm->nccl;
@@ -571,8 +587,12 @@ extern "C" int cphb_icp_run(cphb_icp *icp, const float h_init[16], cphb_comm *co
     // j < max_iter, launch j+1 re-runs that search only to materialise its correspondences;
     // launches after "done" exit at their first instruction.
     const unsigned long long launches0 = g_cphb_launches;
-    // after these launches; later ones are skipped by their certificates, whatever the tile order
-    unsigned long long retile_mask = (1ull << 1) | (1ull << 4);
+    // Re-tiling (the working copy re-ordered by the target position of every point's current match) after the launches
+    // whose bit is set.  It paid for itself while the rows were gathered through the caller's arrays (round 1: mask 0x12);
+    // with the target attributes in index order and the certified regime's cp.async row pipeline the ~70 us of a
+    // re-tiling are no longer earned back (mask sweep, profiles/r2_sweep_retile.txt: 0x12 9590, 0x2 9764, 0x4 9828,
+    // 0x0 10103 it/s on config 2; 1103 vs 1142 it/s in the loop of config 4), so the default is none.
+    unsigned long long retile_mask = 0ull;
     if (const char *e = getenv("CPHB_RETILE_MASK")) retile_mask = strtoull(e, nullptr, 0);  // tuning hook
     static const bool dbg_events = getenv("CPHB_DEBUG_EVENTS") != nullptr;
     std::vector<cudaEvent_t> evs;
@@ -609,6 +629,10 @@ extern "C" int cphb_icp_run(cphb_icp *icp, const float h_init[16], cphb_comm *co
     CPHB_CUDA(cudaMemcpyAsync(h, icp->st, offsetof(IcpState, pad_local), cudaMemcpyDeviceToHost, s));
     CPHB_CUDA(cudaStreamSynchronize(s));
     h_local = h->pad_local;
+    if (h->comm_timeout) {
+        cphb_set_error("cphb_icp_run: the peer-memory exchange timed out waiting for another rank; the result is invalid");
+        return CPHB_ERR_CUDA;
+    }
     memcpy(h_result->transformation, h->T, 64);
     h_result->fitness = h->fitness;
     h_result->inlier_rmse = h->rmse;

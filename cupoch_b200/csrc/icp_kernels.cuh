@@ -899,7 +899,7 @@ __device__ void icp_static_tail(const IcpArgs &a, IcpState *st, double (*s_rowbu
         double tt = 0.0;
 #pragma unroll
         for (int k = 0; k < ICP_SEARCH_WARPS; ++k) tt += s_rowbuf[k][lane];
-        if (a.use_p2p) tt = p2p_exchange_sum(a.p2p, tt);  // the collective, fused: NVLink stores + flags
+        if (a.use_p2p) tt = p2p_exchange_sum(a.p2p, tt, &st->comm_timeout);  // the collective, fused: NVLink stores + flags
         if (a.defer_finalize) st->local[lane] = tt;
         else st->total[lane] = tt;
         s_solve.S[lane] = tt;
@@ -997,7 +997,7 @@ __device__ void icp_reduce_body(const IcpArgs &a, double (*s_acc)[32], unsigned 
         double t = 0.0;
 #pragma unroll
         for (int k = 0; k < GROUPS; ++k) t += s_acc[k][threadIdx.x];
-        if (a.use_p2p) t = p2p_exchange_sum(a.p2p, t);  // the collective, fused: NVLink stores + flags
+        if (a.use_p2p) t = p2p_exchange_sum(a.p2p, t, &st->comm_timeout);  // the collective, fused: NVLink stores + flags
         if (a.defer_finalize) st->local[threadIdx.x] = t;
         else st->total[threadIdx.x] = t;
         s_solve.S[threadIdx.x] = t;

@@ -25,6 +25,7 @@ struct IcpState {
     unsigned block_ticket;  // arrival counter of that tail
     unsigned flag_parity;   // which of the two tile bitmaps holds the last certified launch's "needed a search" flags
     long long n_corr;
+    unsigned comm_timeout;  // the peer-memory exchange gave up waiting for a rank (cphb_internal.cuh)
     unsigned pad_local;  // host-side staging only (count of locally written correspondence pairs)
     unsigned pad_;
 };

@@ -11,8 +11,8 @@
  * Conventions
  *   - extern "C", plain pointers + sizes, no torch / thrust / Eigen types.
  *   - all data pointers are DEVICE pointers unless the name starts with h_;
- *     they are borrowed for the duration of the call (never retained, except
- *     cphb_icp_create which documents it), outputs are caller-allocated.
+ *     they are borrowed for the duration of the call and never retained
+ *     (contexts keep private re-packed copies), outputs are caller-allocated.
  *   - points / normals / colors: packed float32 xyz, 12-byte stride (the
  *     layout of cupoch's device_vector<Eigen::Vector3f>, pointcloud.h:259-262).
  *   - covariances: 9 float32 per point; cov_col_major=1 for Eigen's default

@@ -202,17 +202,22 @@ def test_icp_1m_properties():
     ctx.close()
 
 
-def test_retiling_does_not_change_results(orc):
-    """Re-ordering the working copy by matched target position is a pure permutation: same pose bits,
-    same correspondence set, with and without it (and both equal the oracle)."""
+def test_retiling_does_not_change_results(orc, monkeypatch):
+    """Re-ordering the working copy by matched target position (CPHB_RETILE_MASK; round 1's schedule 0x12, off by default
+    since round 2) is a pure permutation: same pose bits, same correspondence set, with and without it (and both equal
+    the oracle)."""
     src, sn, tgt, tn = small_pair(n=30000)
     crit = R.ICPConvergenceCriteria(0, 0, 14)
+    monkeypatch.setenv("CPHB_RETILE_MASK", "0x12")
     a = R.registration_icp(cloud(src), cloud(tgt, tn), 0.03, np.eye(4), R.TransformationEstimationPointToPlane(), crit)
-    R.DEFAULT_FLAGS = R.ICP_NO_RETILE
+    monkeypatch.delenv("CPHB_RETILE_MASK")
+    b = R.registration_icp(cloud(src), cloud(tgt, tn), 0.03, np.eye(4), R.TransformationEstimationPointToPlane(), crit)
+    R.DEFAULT_FLAGS = R.ICP_NO_RETILE           # (the API flag that forbids it whatever the mask says)
     try:
-        b = R.registration_icp(cloud(src), cloud(tgt, tn), 0.03, np.eye(4), R.TransformationEstimationPointToPlane(), crit)
+        c = R.registration_icp(cloud(src), cloud(tgt, tn), 0.03, np.eye(4), R.TransformationEstimationPointToPlane(), crit)
     finally:
         R.DEFAULT_FLAGS = 0
+    np.testing.assert_array_equal(b.transformation, c.transformation)
     # the float64 sums are added in a different order (1e-16 relative), so the float32 systems are the same
     # except on a rounding boundary: allow one ulp-level wobble of the pose, demand identical correspondences
     assert np.linalg.norm(a.transformation.astype(np.float64) - b.transformation) <= 1e-6
