@@ -494,21 +494,25 @@ def config4_record(cph, L, timed, peak, args, rank, world, comm, dist):
                                      return_correspondences=False, shard=shard)
     for _ in range(2):
         run()
-    reps = 3
-    ms, res = timed(run, reps)
-    loop_ms = res.loop_ms
+    reps = 5
+    steps, loops = [], []
+    for _ in range(reps):   # one step at a time: per-step device times, max over ranks, then the median step
+        m1, res = timed(run, 1)
+        steps.append(m1)
+        loops.append(res.loop_ms)
     if dist is not None:
         import torch
-        t = torch.tensor([ms, loop_ms], dtype=torch.float64, device="cuda")
+        t = torch.tensor([steps, loops], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms, loop_ms = [float(x) for x in t.tolist()]
-    ms /= reps
+        steps, loops = [float(x) for x in t[0].tolist()], [float(x) for x in t[1].tolist()]
+    ms, loop_ms = float(np.median(steps)), float(np.median(loops))
     units = n4 // world
     launch_ms = loop_ms / (ITERS + 1)
     ach = 96 * units / (launch_ms * 1e-3) / 1e9
     gt = datagen.gt_transform()
     return {"workload": "config4: Generalized ICP %d -> %d, %d iters, r=%.2f, eps=1e-3, source sharded x%d" % (n4, n4, ITERS, MAX_DIST, world),
             "points": n4, "value": ITERS * 1e3 / ms, "unit": "iter/s", "ms_per_registration": ms,
+            "step_ms": [round(x, 3) for x in steps], "aggregate": "median of %d steps (each the max over ranks)" % reps,
             "loop_iters_per_sec": ITERS * 1e3 / loop_ms, "scaling": "strong",
             "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
                          "algorithmic_bytes_per_launch": 96 * units, "launch_ms": launch_ms,
