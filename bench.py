@@ -20,7 +20,8 @@ N > 1 (torchrun): the source is split into contiguous blocks of its Hilbert orde
 target and its index are replicated, and the 32 partial sums are exchanged once per iteration (peer-
 memory mailboxes over NVLink fused into the launch's tail; --comm nccl for ncclAllReduce): strong
 scaling of the same 1M -> 1M problem.  Sub-records: certificates_off and config3 (N = 1), config4
-(Generalized ICP 5M -> 5M, the configuration BASELINE names for 8 GPUs) at every N.
+(Generalized ICP 5M -> 5M, the configuration BASELINE names for 8 GPUs) and config5 (Colored-ICP
+pyramid on a 20M-point pair) at every N.
 """
 import argparse
 import ctypes as C
@@ -373,6 +374,11 @@ def run_native(args, rank, world):
         c4 = config4_record(cph, L, timed, peaks()[0], args, rank, world, comm, dist)
         if rank == 0:
             extra["config4"] = c4
+    if not args.no_extras and args.points5 > 0:
+        # (d) config 5 of BASELINE.json at every N: Colored-ICP pyramid on a 20 M-point pair
+        c5 = config5_record(cph, L, timed, args, rank, world, comm, dist)
+        if rank == 0:
+            extra["config5"] = c5
     if rank == 0:
         sampler.stop_flag = True
         sampler.join(timeout=2)
@@ -522,6 +528,59 @@ def config4_record(cph, L, timed, peak, args, rank, world, comm, dist):
                       "T": np.asarray(res.transformation).round(7).tolist()}}
 
 
+def config5_record(cph, L, timed, args, rank, world, comm, dist):
+    """BASELINE.json config 5 as a sub-record at every N: Colored ICP 3-scale pyramid (voxel 0.05 / 0.025 / 0.0125, iterations
+    50 / 30 / 14, relative criteria 1e-6 as in examples/python/advanced/colored_pointcloud_registration.py:37-60) on a
+    20 M-point textured fragment pair over a 4 m x 4 m patch.  Per scale: VoxelDownSample -> EstimateNormals(radius 2v,
+    30) -> colour gradient -> RegistrationColoredICP.  The pre-processing runs replicated on every rank (it needs no
+    collective); the ICP loops shard the down-sampled source.  value = pyramids / s, end to end, clouds resident."""
+    from cupoch_b200.testing import datagen
+    R, G = cph.registration, cph.geometry
+    n5 = args.points5
+    tgt, _ = datagen.surface(n5, 31, extent=4.0)
+    tc = datagen.texture(tgt, 32, 0.01)
+    gt = datagen.gt_transform((0.0, 0.0, 2.0), (0.01, 0.0, 0.0))
+    src, sc = datagen.make_source(tgt, gt, 33, 34, 2e-4, attrs=[(tc, False)])
+    t_full, s_full = G.PointCloud(tgt), G.PointCloud(src)
+    t_full.colors, s_full.colors = tc, sc
+    shard = (rank, world) if world > 1 else None
+    info = {}
+
+    def pyramid():
+        T = np.eye(4, dtype=np.float32)
+        st = []
+        for v, iters in ((0.05, 50), (0.025, 30), (0.0125, 14)):
+            td, sd = t_full.voxel_down_sample(v), s_full.voxel_down_sample(v)
+            td.estimate_normals(G.KDTreeSearchParamRadius(2 * v, 30))
+            sd.estimate_normals(G.KDTreeSearchParamRadius(2 * v, 30))
+            res = R.registration_colored_icp(sd, td, v, T, R.ICPConvergenceCriteria(1e-6, 1e-6, iters), comm=comm,
+                                             return_correspondences=False, shard=shard)
+            T = res.transformation
+            st.append({"voxel": v, "n_src": len(sd), "n_tgt": len(td), "iterations": int(res.iterations), "fitness": res.fitness,
+                       "rmse": res.inlier_rmse})
+        info["stages"], info["T"] = st, T
+        return T
+    for _ in range(2):
+        pyramid()
+    reps = 3
+    steps = []
+    for _ in range(reps):
+        m1, _ = timed(pyramid, 1)
+        steps.append(m1)
+    if dist is not None:
+        import torch
+        t = torch.tensor(steps, dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        steps = [float(x) for x in t.tolist()]
+    ms = float(np.median(steps))
+    return {"workload": "config5: Colored ICP 3-scale pyramid (0.05/0.025/0.0125; 50/30/14 iters) on a %d-point RGB fragment pair, "
+                        "ICP loops sharded x%d, pre-processing replicated" % (n5, world),
+            "points": n5, "value": 1e3 / ms, "unit": "pyramids/s", "ms_per_pyramid": ms, "step_ms": [round(x, 3) for x in steps],
+            "aggregate": "median of %d steps (each the max over ranks)" % reps, "stages": info["stages"],
+            "final": {"pose_error_vs_ground_truth": float(np.linalg.norm(np.asarray(info["T"], np.float64) - gt)),
+                      "T": np.asarray(info["T"]).round(7).tolist()}}
+
+
 def config3_records(cph, L, timed, peak, args):
     """BASELINE.json config 3 as sub-records with their own roofline (SURVEY 8d bytes): VoxelDownSample(0.02) of 10 M
     uniform points in [0,4)x[0,4)x[0,1), then SearchRadius(k=1, r=0.05) of the 10 M points against the down-sampled
@@ -566,6 +625,7 @@ def main():
     ap.add_argument("--no-extras", action="store_true", help="skip the certificates-off and config-3 sub-records")
     ap.add_argument("--points3", type=int, default=10_000_000, help="size of the config-3 sub-records")
     ap.add_argument("--points4", type=int, default=5_000_000, help="size of the config-4 sub-record (0 = skip)")
+    ap.add_argument("--points5", type=int, default=20_000_000, help="size of the config-5 sub-record (0 = skip)")
     ap.add_argument("--comm", default="p2p", choices=["p2p", "nccl"],
                     help="N>1 exchange: p2p = peer-memory stores fused into the reduce kernel, nccl = ncclAllReduce")
     args = ap.parse_args()
