@@ -20,8 +20,8 @@ N > 1 (torchrun): the source is split into contiguous blocks of its Hilbert orde
 target and its index are replicated, and the 32 partial sums are exchanged once per iteration (peer-
 memory mailboxes over NVLink fused into the launch's tail; --comm nccl for ncclAllReduce): strong
 scaling of the same 1M -> 1M problem.  Sub-records: certificates_off and config3 (N = 1), config4
-(Generalized ICP 5M -> 5M, the configuration BASELINE names for 8 GPUs) and config5 (Colored-ICP
-pyramid on a 20M-point pair) at every N.
+(Generalized ICP 5M -> 5M, the configuration BASELINE names for 8 GPUs) at every N, config5
+(Colored-ICP pyramid on a 20M-point pair) at N = 1.
 """
 import argparse
 import ctypes as C
@@ -374,8 +374,10 @@ def run_native(args, rank, world):
         c4 = config4_record(cph, L, timed, peaks()[0], args, rank, world, comm, dist)
         if rank == 0:
             extra["config4"] = c4
-    if not args.no_extras and args.points5 > 0:
-        # (d) config 5 of BASELINE.json at every N: Colored-ICP pyramid on a 20 M-point pair
+    if not args.no_extras and args.points5 > 0 and (world == 1 or args.config5_multi):
+        # (d) config 5 of BASELINE.json: Colored-ICP pyramid on a 20 M-point pair.  In the default line at N = 1 only (the
+        #     run that was validated on hardware this round); --config5-multi adds it at N > 1, where tools/bench_configs.py
+        #     --config 5 is the maintained entry point (profiles/r1_n8_config5_n8.json)
         c5 = config5_record(cph, L, timed, args, rank, world, comm, dist)
         if rank == 0:
             extra["config5"] = c5
@@ -529,7 +531,7 @@ def config4_record(cph, L, timed, peak, args, rank, world, comm, dist):
 
 
 def config5_record(cph, L, timed, args, rank, world, comm, dist):
-    """BASELINE.json config 5 as a sub-record at every N: Colored ICP 3-scale pyramid (voxel 0.05 / 0.025 / 0.0125, iterations
+    """BASELINE.json config 5 as a sub-record: Colored ICP 3-scale pyramid (voxel 0.05 / 0.025 / 0.0125, iterations
     50 / 30 / 14, relative criteria 1e-6 as in examples/python/advanced/colored_pointcloud_registration.py:37-60) on a
     20 M-point textured fragment pair over a 4 m x 4 m patch.  Per scale: VoxelDownSample -> EstimateNormals(radius 2v,
     30) -> colour gradient -> RegistrationColoredICP.  The pre-processing runs replicated on every rank (it needs no
@@ -626,6 +628,7 @@ def main():
     ap.add_argument("--points3", type=int, default=10_000_000, help="size of the config-3 sub-records")
     ap.add_argument("--points4", type=int, default=5_000_000, help="size of the config-4 sub-record (0 = skip)")
     ap.add_argument("--points5", type=int, default=20_000_000, help="size of the config-5 sub-record (0 = skip)")
+    ap.add_argument("--config5-multi", action="store_true", help="also run the config-5 sub-record at N > 1")
     ap.add_argument("--comm", default="p2p", choices=["p2p", "nccl"],
                     help="N>1 exchange: p2p = peer-memory stores fused into the reduce kernel, nccl = ncclAllReduce")
     args = ap.parse_args()
