@@ -1,21 +1,22 @@
 // icp_kernels.cuh -- the kernels of one ICP iteration.  Part of the icp.cu translation unit (included there).
 //
-//   icp_iteration_kernel   transform -> certificate / exact 1-NN search -> estimator rows -> sums.  Two regimes, chosen on
-//                          the DEVICE from the previous launch's statistics (no host round trip inside the loop):
-//        searching regime  (tiles need searches, cost varies 10x): persistent warps claim tiles from an atomic counter, rows
-//                          are staged in shared memory and every tile writes its 32 column sums to tile_sums[tile]
-//                          (schedule-independent); icp_reduce_kernel adds them in a fixed order and solves.
-//        certified regime  (>= 90 % of the previous launch's tiles were skipped by their certificates): static round-robin
-//                          tile schedule, every lane accumulates the products of ITS OWN rows in float64 registers over all
-//                          the tiles of its warp, one warp reduction at the end, block rows -> last-arriving block adds them
-//                          in block order and runs the solve IN THE SAME LAUNCH (one launch per iteration, no reduce kernel).
-//   icp_reduce_kernel      fixed-order sum of the tile sums + solve for launches of the searching regime (returns at once
-//                          when the iteration kernel's own tail has done the work).
+//   icp_iteration_kernel<KIND, TOP, ROLE>   transform -> certificate / exact 1-NN search -> estimator rows -> sums -> solve.
+//       Two regimes, chosen on the DEVICE from the previous launch's statistics (no host round trip inside the loop), and
+//       two separately compiled instances launched back to back every iteration; the instance the current regime does not
+//       concern returns at its first instructions:
+//        ROLE 0, searching regime  (tiles need searches, cost varies 10x): persistent warps claim tiles from an atomic counter,
+//                          rows are staged in shared memory and every tile writes its 32 column sums to tile_sums[tile]
+//                          (schedule-independent).  Compiled for 96 registers = 20 warps / SM.
+//        ROLE 1, certified regime  (>= 90 % of the previous launch's tiles were skipped by their certificates): static round-
+//                          robin tile schedule, cp.async pipeline, the normal-equation sums of every tile on the FP64 tensor
+//                          cores (one 8 x 8 Gram fragment per warp), block rows -> last-arriving block adds them in block
+//                          order, exchanges them with the other ranks and runs the solve IN THE SAME LAUNCH.
+//        ROLE 1 after a searching launch: fixed-order sum of the tile sums + (exchange +) solve (icp_reduce_body).
+//   icp_finalize_kernel    the solve alone, after an NCCL all-reduce of the sums (multi-GPU, --comm nccl).
 //
 // Target attributes are read from the context's private copies in INDEX order (icp_types.cuh): the match of a source point
 // is remembered as a POSITION in the index, so the warm start, the certificate test and the rows read ix.pts[p] / tgt_nrm[p]
-// with one aligned 16-byte load each, and -- once the working copy has been re-tiled by match position -- the 32 lanes of
-// a warp read a few consecutive 512-byte leaves instead of 32 scattered sectors per attribute.
+// with one aligned 16-byte load each.
 #pragma once
 
 __device__ __forceinline__ void prefetch_l1(const void *p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
