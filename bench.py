@@ -11,8 +11,8 @@ ICPConvergenceCriteria(0, 0, 30): exactly 30 updates / 31 searches per registrat
                     and D2H of the result inside the timed region
   roofline        = algorithmic bytes of the fused iteration kernel (36 B / source point,
                     SURVEY.md 8d) / mean device time of one fused iteration = CUDA events around
-                    the launch loop / number of search launches (so the reduce/solve kernel and
-                    the amortised re-tiling are charged to the kernel: a conservative figure)
+                    the launch loop / number of iterations (so the idle instance, the fixed-order
+                    sum and the solve are charged to the kernel: a conservative figure)
   cpu_baseline    = the CPU oracle port (kd-tree + OpenMP, all host cores) on the same workload
   --impl reference= that CPU implementation timed as its own arm
 
@@ -398,8 +398,8 @@ def run_native(args, rank, world):
         value = ITERS * 1e3 / ms_step
         kern_ms = loop_ms / max(loop_launches, 1)
         # roofline: one "launch" = one fused iteration.  Its duration is the WHOLE launch loop (CUDA events around
-        # it inside cphb_icp_run) divided by the number of fused search launches -- i.e. the search kernel plus its
-        # reduce/solve kernel plus the amortised re-tiling, a conservative (upper) figure for the kernel alone.
+        # it inside cphb_icp_run) divided by the number of iterations -- i.e. both instances of the iteration kernel
+        # (search or certified pass; fixed-order sum + solve), a conservative (upper) figure for the kernel alone.
         n_fused = int(res.iterations) + 1
         fused_ms = loop_ms / max(n_fused, 1)
         units = (hi - lo)
@@ -429,7 +429,7 @@ def run_native(args, rank, world):
                          "traffic_source": (traffic["source"] if traffic else None),
                          "peak_source": peak_src, "kernel": "icp_iteration_kernel<PointToPlane>",
                          "launch_ms": fused_ms, "launches": n_fused,
-                         "launch_definition": "loop device time / fused search launches (search kernel + reduce/solve + amortised re-tiling)",
+                         "launch_definition": "loop device time / iterations (both instances of the iteration kernel: search or certified pass, fixed-order sum, solve)",
                          "algorithmic_bytes_per_launch": ALG_BYTES_PER_POINT * units},
             "clocks": sampler.summary(),
             "step_ms": resident_steps_ms,
