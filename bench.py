@@ -291,6 +291,7 @@ def run_native(args, rank, world):
     if rank == 0:
         sampler.start()
         sampler.ready.wait(timeout=20)
+    barrier()   # (ranks finish their set-up at different times; the first exchange of a registration waits for every peer)
     for _ in range(args.warmup):
         step_resident()
     barrier()
@@ -500,6 +501,9 @@ def config4_record(cph, L, timed, peak, args, rank, world, comm, dist):
     shard = (rank, world) if world > 1 else None
     run = lambda: R.registration_icp(s_c, t_c, MAX_DIST, np.eye(4, dtype=np.float32), est, crit, comm=comm,
                                      return_correspondences=False, shard=shard)
+    L.cphb_stream_synchronize(None)
+    if dist is not None:
+        dist.barrier()
     for _ in range(2):
         run()
     reps = 5

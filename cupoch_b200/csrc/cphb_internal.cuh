@@ -134,7 +134,8 @@ int cphb_nccl_allreduce_f64(void *nccl_comm, const double *send, double *recv, s
 // this rank's device memory (every rank executes the same sequence of exchanges, so the counters agree);
 // its parity selects one of two slot sets, which is what makes back-to-back exchanges safe: a peer can be
 // at most one exchange ahead.
-// The wait is bounded (~2 s of SM clock): if a peer never arrives -- its process died, or a one-sided host error kept
+// The wait is bounded (~60 s of SM clock -- far beyond any start-up skew between ranks, which wait for each other here
+// in their very first exchange): if a peer never arrives -- its process died, or a one-sided host error kept
 // it from launching -- the warp stops waiting, raises *timed_out (when given) and returns what it has, so the GPU is
 // released instead of spinning for ever; the host turns the flag into an error (cphb_icp_run).
 __device__ __forceinline__ double p2p_exchange_sum(const P2pView &v, double mine, unsigned *timed_out = nullptr) {
@@ -158,7 +159,7 @@ __device__ __forceinline__ double p2p_exchange_sum(const P2pView &v, double mine
             (volatile unsigned long long *)(v.box[v.rank] + CPHB_P2P_DATA_BYTES) + (size_t)par * CPHB_P2P_MAX_WORLD + c;
         const long long t0 = clock64();
         while (*mine_f < epoch) {
-            if (clock64() - t0 > 4000000000ll) {
+            if (clock64() - t0 > 120000000000ll) {
                 if (timed_out) atomicExch(timed_out, 1u);
                 break;
             }
