@@ -209,6 +209,18 @@ extern "C" int cphb_icp_create(const cphb_cloud *source, const cphb_cloud *targe
     }
     cphb_icp *icp = new cphb_icp();
     memset(icp, 0, sizeof(*icp));
+    uint32_t *perm_side = nullptr;
+    // one exit for CUDA errors after this point: the half-built context (index, arena, host staging) is released
+#define CREATE_TRY(call)                                                                                 \
+    do {                                                                                                 \
+        cudaError_t e__ = (call);                                                                        \
+        if (e__ != cudaSuccess) {                                                                        \
+            cphb_set_error("%s:%d %s: %s", __FILE__, __LINE__, #call, cudaGetErrorString(e__));          \
+            if (perm_side) cphb_free_async(perm_side, t_side.stream);                                    \
+            cphb_icp_destroy(icp);                                                                       \
+            return CPHB_ERR_CUDA;                                                                        \
+        }                                                                                                \
+    } while (0)
     icp->prm = *params;
     icp->tgt = *target;
     icp->stream = s;
@@ -216,19 +228,18 @@ extern "C" int cphb_icp_create(const cphb_cloud *source, const cphb_cloud *targe
     // The source's Hilbert ordering (bounds, keys, radix sort) does not depend on the target index: it runs on a side
     // stream, concurrently with the index build (both are short chains of small kernels: ~0.1 ms and ~0.25 ms at 1 M
     // points), and joins right before the source is gathered.
-    uint32_t *perm_side = nullptr;
     int cur_dev = 0;
     cudaGetDevice(&cur_dev);
     if (!t_side.stream || t_side.device != cur_dev) {  // (a thread that moved to another device gets a new one)
         t_side.device = cur_dev;
-        CPHB_CUDA(cudaStreamCreateWithFlags(&t_side.stream, cudaStreamNonBlocking));
-        CPHB_CUDA(cudaEventCreateWithFlags(&t_side.fork, cudaEventDisableTiming));
-        CPHB_CUDA(cudaEventCreateWithFlags(&t_side.join, cudaEventDisableTiming));
+        CREATE_TRY(cudaStreamCreateWithFlags(&t_side.stream, cudaStreamNonBlocking));
+        CREATE_TRY(cudaEventCreateWithFlags(&t_side.fork, cudaEventDisableTiming));
+        CREATE_TRY(cudaEventCreateWithFlags(&t_side.join, cudaEventDisableTiming));
     }
     int rc = CPHB_OK;
     if (n_full) {
-        CPHB_CUDA(cudaEventRecord(t_side.fork, s));
-        CPHB_CUDA(cudaStreamWaitEvent(t_side.stream, t_side.fork, 0));
+        CREATE_TRY(cudaEventRecord(t_side.fork, s));
+        CREATE_TRY(cudaStreamWaitEvent(t_side.stream, t_side.fork, 0));
         if (t_source_ready) {  // (host-buffer call: the source upload is still in flight on the copy stream)
             cudaStreamWaitEvent(t_side.stream, t_source_ready, 0);
             t_source_ready = nullptr;
@@ -236,7 +247,7 @@ extern "C" int cphb_icp_create(const cphb_cloud *source, const cphb_cloud *targe
         rc = cphb_alloc_async((void **)&perm_side, sizeof(uint32_t) * n_full, t_side.stream);
         if (!rc) rc = cphb_hilbert_order(source->points, n_full, perm_side, nullptr, 0, t_side.stream);
         if (rc) { cphb_free_async(perm_side, t_side.stream); delete icp; return rc; }
-        CPHB_CUDA(cudaEventRecord(t_side.join, t_side.stream));
+        CREATE_TRY(cudaEventRecord(t_side.join, t_side.stream));
     }
     rc = cphb_index_create(target->points, target->n, s, &icp->index);
     if (rc) {
@@ -356,9 +367,9 @@ extern "C" int cphb_icp_create(const cphb_cloud *source, const cphb_cloud *targe
     icp->cmp_total = (unsigned *)(b + o_ct);
     if (!t_cache.in_use) {
         if (!t_cache.h_st) {
-            CPHB_CUDA(cudaMallocHost((void **)&t_cache.h_st, sizeof(IcpState)));
-            CPHB_CUDA(cudaEventCreate(&t_cache.ev0));
-            CPHB_CUDA(cudaEventCreate(&t_cache.ev1));
+            CREATE_TRY(cudaMallocHost((void **)&t_cache.h_st, sizeof(IcpState)));
+            CREATE_TRY(cudaEventCreate(&t_cache.ev0));
+            CREATE_TRY(cudaEventCreate(&t_cache.ev1));
         }
         t_cache.in_use = true;
         icp->owns_host = false;
@@ -367,9 +378,9 @@ extern "C" int cphb_icp_create(const cphb_cloud *source, const cphb_cloud *targe
         icp->ev1 = t_cache.ev1;
     } else {  // a second live context on this thread gets its own
         icp->owns_host = true;
-        CPHB_CUDA(cudaMallocHost((void **)&icp->h_st, sizeof(IcpState)));
-        CPHB_CUDA(cudaEventCreate(&icp->ev0));
-        CPHB_CUDA(cudaEventCreate(&icp->ev1));
+        CREATE_TRY(cudaMallocHost((void **)&icp->h_st, sizeof(IcpState)));
+        CREATE_TRY(cudaEventCreate(&icp->ev0));
+        CREATE_TRY(cudaEventCreate(&icp->ev1));
     }
     if (t_source_ready) {  // (n_full == 0)
         cudaStreamWaitEvent(s, t_source_ready, 0);
@@ -380,15 +391,17 @@ extern "C" int cphb_icp_create(const cphb_cloud *source, const cphb_cloud *targe
                 source->covariances, source->cov_col_major, perm_side, lo, n, n_pad, icp->pristine_xyz, icp->pristine_nrm,
                 icp->src_col, icp->pristine_cov);
     cphb_free_async(perm_side, s);
+    perm_side = nullptr;
     if ((t_nrm || t_grad || t_cov) && nt_pad)
         CPHB_LAUNCH(gather_target_kernel, (unsigned)((nt_pad + 255) / 256), 256, 0, s, icp->index->v.pts, nt_pad, target->normals,
                     (est == CPHB_EST_COLORED_ICP) ? target->colors : nullptr, target->color_gradient, target->covariances,
                     target->cov_col_major, icp->tix_nrm, icp->tix_grad, icp->tix_cov);
-    CPHB_CHECK_LAUNCH();
+    CREATE_TRY(cudaGetLastError());
     *out = icp;
     return CPHB_OK;
 }
 
+#undef CREATE_TRY
 extern "C" void cphb_icp_destroy(cphb_icp *icp) {
     if (!icp) return;
     if (icp->arena) cudaFreeAsync(icp->arena, icp->stream);
@@ -769,27 +782,39 @@ extern "C" int cphb_registration_icp_host(const cphb_cloud *h_source, const cphb
     if (rc) return rc;
     auto dp = [&](size_t o) { return o == (size_t)-1 ? (float *)nullptr : (float *)(base + o); };
     cudaStream_t c = t_up.copy;
-    CPHB_CUDA(cudaEventRecord(t_up.ev[0], s));            // the arena exists from here on in stream order
-    CPHB_CUDA(cudaStreamWaitEvent(c, t_up.ev[0], 0));
+    // one exit for CUDA errors: no upload may still be reading the caller's buffers, and the arena goes back to the pool
+#define HOST_TRY(call)                                                                                   \
+    do {                                                                                                 \
+        cudaError_t e__ = (call);                                                                        \
+        if (e__ != cudaSuccess) {                                                                        \
+            cphb_set_error("%s:%d %s: %s", __FILE__, __LINE__, #call, cudaGetErrorString(e__));          \
+            cudaStreamSynchronize(c);                                                                    \
+            cphb_free_async(base, s);                                                                    \
+            return CPHB_ERR_CUDA;                                                                        \
+        }                                                                                                \
+    } while (0)
+    HOST_TRY(cudaEventRecord(t_up.ev[0], s));            // the arena exists from here on in stream order
+    HOST_TRY(cudaStreamWaitEvent(c, t_up.ev[0], 0));
     auto up = [&](size_t o, const void *hp, size_t bytes) {
         if (hp && bytes) cudaMemcpyAsync(base + o, hp, bytes, cudaMemcpyHostToDevice, c);
     };
     up(o_tp, h_target->points, 12 * nt);
-    CPHB_CUDA(cudaEventRecord(t_up.ev[1], c));            // target points: all the index build needs
+    HOST_TRY(cudaEventRecord(t_up.ev[1], c));            // target points: all the index build needs
     up(o_sp, h_source->points, 12 * ns);
     up(o_sn, h_source->normals, 12 * ns);
     up(o_sc, h_source->colors, 12 * ns);
     up(o_sv, h_source->covariances, 36 * ns);
-    CPHB_CUDA(cudaEventRecord(t_up.ev[2], c));            // source: first read by the Hilbert ordering
+    HOST_TRY(cudaEventRecord(t_up.ev[2], c));            // source: first read by the Hilbert ordering
     up(o_tn, h_target->normals, 12 * nt);
     up(o_tc, h_target->colors, 12 * nt);
     up(o_tv, h_target->covariances, 36 * nt);
     up(o_tg, h_target->color_gradient, 12 * nt);
-    CPHB_CUDA(cudaEventRecord(t_up.ev[3], c));            // target attributes: first read by the first iteration
+    HOST_TRY(cudaEventRecord(t_up.ev[3], c));            // target attributes: first read by the first iteration
     cphb_cloud ds = *h_source, dt = *h_target;
     ds.points = dp(o_sp); ds.normals = dp(o_sn); ds.colors = dp(o_sc); ds.covariances = dp(o_sv); ds.color_gradient = nullptr;
     dt.points = dp(o_tp); dt.normals = dp(o_tn); dt.colors = dp(o_tc); dt.covariances = dp(o_tv); dt.color_gradient = dp(o_tg);
-    CPHB_CUDA(cudaStreamWaitEvent(s, t_up.ev[1], 0));
+    HOST_TRY(cudaStreamWaitEvent(s, t_up.ev[1], 0));
+#undef HOST_TRY
     t_source_ready = t_up.ev[2];
     cphb_icp *icp = nullptr;
     rc = cphb_icp_create(&ds, &dt, params, stream, &icp);
