@@ -5,9 +5,11 @@
             cph.registration.TransformationEstimationPointToPlane())
 
 Mirrors `import cupoch as cph` for: cph.geometry.{PointCloud, KDTreeFlann, KDTreeSearchParamKNN,
-KDTreeSearchParamRadius}, cph.registration.{registration_icp, registration_generalized_icp,
-registration_colored_icp, ICPConvergenceCriteria, TransformationEstimation*, RegistrationResult},
-cph.utility.Vector3fVector.  All computation runs in libcupoch_b200.so (hand-written sm_100a CUDA);
+KDTreeSearchParamRadius, VoxelGrid, OccupancyGrid, OccupancyVoxel}, cph.registration.{registration_icp,
+registration_generalized_icp, registration_colored_icp, ICPConvergenceCriteria, TransformationEstimation*
+(user subclasses run the generic loop), RegistrationResult, compute_fpfh_feature, kabsch, kabsch_weighted},
+cph.utility.{Vector3fVector, compute_jtj_jtr, compute_weighted_jtj_jtr}; cupoch_b200.distributed holds the
+multi-GPU orchestration (torch.distributed).  All computation runs in libcupoch_b200.so (hand-written sm_100a CUDA);
 there is no CPU fallback.
 """
 from . import _lib, geometry, registration, utility  # noqa: F401
